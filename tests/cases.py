@@ -1,0 +1,69 @@
+"""Seeded small inputs that exercise the build quirks Q1-Q6 of SURVEY.md section 8a (shared by the golden generator and
+the tests, so a fixture only has to store the reference's *outputs*)."""
+import numpy as np
+import pandas as pd
+
+
+def toy_rnaseq():
+    """The 6 x 5 toy matrix of the reference (cell2cell/datasets/toy_data.py:5-31) -- data values restated."""
+    data = np.asarray([[5, 10, 8, 15, 2], [15, 5, 20, 1, 30], [18, 12, 5, 40, 20], [9, 30, 22, 5, 2],
+                       [2, 1, 1, 27, 15], [30, 11, 16, 5, 12]])
+    df = pd.DataFrame(data, index=["Protein-" + c for c in "ABCDEF"], columns=["C1", "C2", "C3", "C4", "C5"])
+    df.index.name = "gene_id"
+    return df
+
+
+def toy_ppi(prot_complex=True):
+    """The 10-row toy PPI list of the reference (cell2cell/datasets/toy_data.py:34-76)."""
+    pairs = [("A", "B"), ("B", "C"), ("C", "A"), ("B", "B"), ("B", "A"), ("E", "F"), ("F", "F"),
+             ("C&E" if prot_complex else "C", "F"), ("B", "E"), ("A&B" if prot_complex else "A", "F")]
+    def nm(x):
+        return "&".join("Protein-" + p for p in x.split("&"))
+    ppi = pd.DataFrame([[nm(a), nm(b)] for a, b in pairs], columns=["A", "B"])
+    return ppi.assign(score=1.0)
+
+
+def hard_case(seed, n_contexts=4, n_genes=14, n_cells=5, n_lr=24, dtype=np.float64):
+    """Mixed-case gene names, complexes on both sides (some with a subunit missing from some context or from the whole
+    universe), a complex name used on both sides (the ``elif`` quirk), duplicated LR rows, contexts with different gene /
+    cell sets and orders, real zeros, and a ``pathway`` column for grouping."""
+    rs = np.random.RandomState(seed)
+    genes = ["Gene%d" % i if i % 3 else "gene%d" % i for i in range(n_genes)]
+    cells = ["T%d" % i for i in range(n_cells)]
+    mats = []
+    for c in range(n_contexts):
+        p_drop = 0.15 if seed % 2 == 0 else 0.06
+        g_keep = [g for g in genes if rs.rand() > p_drop]
+        c_keep = [k for k in cells if rs.rand() > p_drop] or cells[:2]
+        if c and rs.rand() < 0.5:
+            g_keep = list(rs.permutation(g_keep))
+        if c and rs.rand() < 0.5:
+            c_keep = list(rs.permutation(c_keep))
+        e = rs.gamma(0.7, 2.0, size=(len(g_keep), len(c_keep))) * (rs.rand(len(g_keep), len(c_keep)) > 0.25)
+        mats.append(pd.DataFrame(e.astype(dtype), index=g_keep, columns=c_keep))
+    def pick():
+        r = rs.rand()
+        if r < 0.6:
+            return genes[rs.randint(n_genes)]
+        if r < 0.9:
+            a, b = rs.choice(n_genes, 2, replace=False)
+            return genes[a] + "&" + genes[b]
+        a, b, c3 = rs.choice(n_genes, 3, replace=False)
+        return genes[a] + "&" + genes[b] + "&" + genes[c3]
+    rows = [(pick(), pick()) for _ in range(n_lr)]
+    rows.append((rows[0][1], rows[0][0]))          # same names on the other side (complex 'elif' quirk when complex)
+    rows.append(rows[1])                            # duplicated LR row is kept
+    rows.append(("GENE1&NOTAGENE", genes[2]))       # complex with a subunit nobody expresses
+    ppi = pd.DataFrame(rows, columns=["A", "B"])
+    ppi["score"] = 1.0
+    ppi["pathway"] = ["P%d" % rs.randint(5) for _ in range(len(rows))]
+    return mats, ppi
+
+
+OPTION_GRID = [
+    dict(how=how, communication_score=score, complex_agg_method=agg, group_ppi_by=grp, group_ppi_method=gm)
+    for how in ("inner", "outer", "outer_genes", "outer_cells")
+    for score in ("expression_product", "expression_mean", "expression_gmean")
+    for agg in ("min", "mean", "gmean")
+    for grp, gm in ((None, "gmean"), ("pathway", "gmean"), ("pathway", "sum"), ("pathway", "mean"))
+]
