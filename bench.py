@@ -1,0 +1,310 @@
+"""Benchmark of the hot path on B200: NCP iterations/s at 60 x 2000 x 40 x 40, rank 10 (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload atlas|balf|asd|toy]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one factorization call of `--iters` (default 100, the reference's `n_iter_max`) fixed NCP-MU iterations
+(tol = -1: the stop rule never fires) on the synthetic tensor of the workload, rank 10, host-seeded random init.
+`value` = iterations/s with the tensor resident in HBM (CUDA events around the K steps, max over ranks);
+`e2e` = the same metric through the public API (`PreBuiltTensor(host array)` -> `compute_tensor_factorization`), with the
+pinned-host -> device copy of the tensor and the device -> host read of the factors inside the timed region.
+N > 1: every rank factorizes its own replica from its own seed (the independent (rank, seed) units of the elbow sweep --
+no data-path collective), `scaling` = "weak".
+`roofline` is for the two streaming kernels (plane_contract / fiber_contract): algorithmic bytes = 4 B x N_X per launch
+(one read of the tensor), duration from CUDA events around back-to-back launches of that kernel alone.
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference's tensorly path (oracle/ncp_oracle.py, float64
+numpy, all host cores through BLAS) on the same tensor -- the reference's arithmetic lives in tensorly, which is not
+installable here, so kind = "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "atlas": dict(shape=(60, 2000, 40, 40), rank=10),
+    "spatial": dict(shape=(500, 1000, 30, 30), rank=10),
+    "asd": dict(shape=(13, 1900, 17, 17), rank=10),
+    "balf": dict(shape=(12, 1054, 6, 6), rank=10),
+    "toy": dict(shape=(4, 300, 6, 6), rank=4),
+}
+METRIC = "NCP iterations/s at 60x2000x40x40 rank 10"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_host(shape, seed, pinned=True):
+    """Low-rank-5 gamma CP + 5 % uniform noise, fp32, host (pinned) memory."""
+    import torch
+    from cell2cell_b200.synthetic import synthetic_lowrank_tensor
+    x = synthetic_lowrank_tensor(shape, rank=5, noise=0.05, seed=seed)
+    t = torch.from_numpy(x)
+    return t.pin_memory() if pinned else t
+
+
+def cpu_iterations(x64, rank, n_iter, seed):
+    """n_iter MU iterations of the oracle from a host-seeded random init; returns seconds."""
+    from oracle import ncp_oracle as o
+    init = (np.ones(rank), o.random_init(x64.shape, rank, seed))
+    t0 = time.perf_counter()
+    o.non_negative_parafac(x64, rank, n_iter_max=n_iter, init=init, tol=-1.0)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank_id, world):
+    wl = WORKLOADS[args.workload]
+    if rank_id != 0:
+        return
+    from threadpoolctl import threadpool_info
+    threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    x64 = synth_host(wl["shape"], 1, pinned=False).numpy().astype(np.float64)
+    iters = args.ref_iters
+    for _ in range(args.warmup if args.ref_warm else 0):
+        cpu_iterations(x64, wl["rank"], iters, 888)
+    times = [cpu_iterations(x64, wl["rank"], iters, 888 + s) for s in range(args.steps)]
+    total = sum(times)
+    val = args.steps * iters / total
+    sample = "%d steps x %d MU iterations (of the %d-iteration run) on the full %s fp64 tensor, rank %d" % (
+        args.steps, iters, args.iters, "x".join(map(str, wl["shape"])), wl["rank"])
+    line = {"impl": "reference", "metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": val,
+            "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup if args.ref_warm else 0,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s %s rank %d, non_negative_cp (MU), random init" % (
+                args.workload, "x".join(map(str, wl["shape"])), wl["rank"]), "iterations_per_step": iters},
+            "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_kernel(fn, reps):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def run_ours(args, rank_id, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from cell2cell_b200 import engine
+    from cell2cell_b200.tensor import PreBuiltTensor
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    shape, rank, iters = wl["shape"], wl["rank"], args.iters
+    n_x = int(np.prod(shape))
+    x_host = synth_host(shape, 1 + rank_id)
+    X = x_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    ws = engine.Workspace(shape, rank, False, dev)
+    norm_x2 = engine.sumsq(X)
+
+    def fresh_factors(seed):
+        rs = np.random.RandomState(seed)
+        return [engine.pack_factor(rs.random_sample((s, rank)).astype(np.float32), rank, dev) for s in shape]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: tensor resident in HBM -----------------------------------------------------------------------------
+    seeds = [888 + rank_id * 1000 + s for s in range(args.warmup + args.steps)]
+    facs = [fresh_factors(s) for s in seeds]
+    for s in range(args.warmup):
+        engine.ncp_run(X, None, facs[s], rank, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws)
+    barrier()
+    n0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        ev0.record()
+        last_err = None
+        for s in range(args.warmup, args.warmup + args.steps):
+            last_err = engine.ncp_run(X, None, facs[s], rank, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2,
+                                      ws=ws, sync=False)
+        ev1.record()
+        barrier()
+    launches = engine.launch_count() - n0
+    sec = ev0.elapsed_time(ev1) * 1e-3
+    final_err = float(last_err[0][iters - 1].item())
+    assert np.isfinite(final_err) and 0.0 < final_err < 1.0, final_err
+
+    # ---- e2e: public API, host buffers ------------------------------------------------------------------------------
+    names = [list(range(s)) for s in shape]
+
+    def api_step(seed):
+        t = PreBuiltTensor(x_host, order_names=names, device=dev)
+        t.compute_tensor_factorization(rank=rank, init="random", random_state=seed, n_iter_max=iters, tol=-1.0)
+        return t
+    for s in range(max(1, args.warmup // 3)):
+        api_step(s)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 5))
+    e0.record()
+    for s in range(e2e_steps):
+        t = api_step(1000 + s)
+    e1.record()
+    barrier()
+    e2e_sec = e0.elapsed_time(e1) * 1e-3
+    d2h = sum(s * rank * 4 for s in shape) * 2 + iters * 8
+
+    # ---- per-kernel roofline (rank 0 only reports) ---------------------------------------------------------------------
+    f = fresh_factors(1)
+    T = torch.empty((int(np.prod(shape[:-2])), engine.ldr_of(rank)), dtype=torch.float32, device=dev)
+    U = torch.empty((shape[-2] * shape[-1], engine.ldr_of(rank)), dtype=torch.float32, device=dev)
+    reps = 20 if n_x * 4 > 256e6 else 200
+    t_plane = time_kernel(lambda: engine.plane_contract(X, None, f, rank, ws=ws, out=T), reps)
+    t_fiber = time_kernel(lambda: engine.fiber_contract(X, None, f, rank, ws=ws, out=U), reps)
+
+    times = torch.tensor([sec, e2e_sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    sec, e2e_sec = float(times[0]), float(times[1])
+    if rank_id != 0:
+        return
+    peak, peak_kind = peaks()
+    total_iters = world * args.steps * iters
+    value = total_iters / sec
+    worst = max(t_plane, t_fiber)
+    name = "plane_contract" if t_plane >= t_fiber else "fiber_contract (+ partial reduce)"
+    line = {
+        "metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": value, "unit": "iterations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s %s rank %d, non_negative_cp (MU), random init" % (
+                       args.workload, "x".join(map(str, shape)), rank),
+                   "iterations_per_step": iters, "tensor_bytes": n_x * 4,
+                   "l2": "tensor (%.0f MB) larger than L2, no flush needed" % (n_x * 4 / 1e6) if n_x * 4 > 2 * 126e6
+                         else "tensor fits in L2 (L2-resident after first touch)",
+                   "multi_gpu": "independent (rank, seed) factorizations per GPU, no collective"},
+        "e2e": {"value": world * e2e_steps * iters / e2e_sec, "unit": "iterations/s", "h2d_bytes_per_step": n_x * 4,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_sec / e2e_steps,
+                "api": "PreBuiltTensor(pinned host fp32).compute_tensor_factorization(rank, init='random', n_iter_max=%d, tol=-1)" % iters},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": n_x * 4 / worst / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": n_x * 4 / worst / 1e9 / peak, "traffic": None, "peak_kind": "of " + peak_kind,
+                     "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
+                     "plane_contract_gbs": n_x * 4 / t_plane / 1e9, "fiber_contract_gbs": n_x * 4 / t_fiber / 1e9,
+                     "iteration": {"algorithmic_bytes": 4 * n_x * 4, "achieved_gbs": 4 * n_x * 4 * value / world / 1e9,
+                                   "frac_of_4_pass_roofline": 4 * n_x * 4 * value / world / 1e9 / peak,
+                                   "passes_made": 2}},
+        "final_rec_error": final_err,
+    }
+    if not args.no_cpu:
+        from threadpoolctl import threadpool_info
+        threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+        x64 = x_host.numpy().astype(np.float64)
+        n_it = args.ref_iters
+        tcpu = cpu_iterations(x64, rank, n_it, 888)
+        line["cpu_baseline"] = {"value": n_it / tcpu, "unit": "iterations/s", "cores": threads, "kind": "port",
+                                "sample": "%d MU iterations on the full %s fp64 tensor, rank %d, numpy restatement of the "
+                                          "tensorly path (oracle/ncp_oracle.py)" % (n_it, "x".join(map(str, shape)), rank)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="atlas", choices=sorted(WORKLOADS))
+    ap.add_argument("--iters", type=int, default=100, help="NCP iterations per step (the reference's n_iter_max)")
+    ap.add_argument("--ref-iters", type=int, default=2, help="CPU iterations per step of the reference arm / cpu_baseline")
+    ap.add_argument("--ref-warm", action="store_true", help="also run the warm-up steps on the CPU reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank_id = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank_id, world)
+        return
+    import torch.distributed as dist
+    if world > 1:
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank_id, local_rank, world)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

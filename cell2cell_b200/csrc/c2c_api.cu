@@ -1,0 +1,771 @@
+// libc2c_b200.so -- the C ABI declared in include/c2c_b200.h: argument checks, workspace carving, launch geometry and
+// the per-iteration launch sequence of the factorization.  Kernels live in c2c_contract.cuh (the streaming passes over
+// the tensor) and c2c_small.cuh (everything that runs out of L2).
+//
+// One NCP iteration on an N-way tensor with two trailing (in-plane) modes, unmasked:
+//   plane_contract  X -> T[P x R]                      (pass 1 over X; serves every leading mode: T depends on A_{N-2},
+//   for each leading mode k: lead_mttkrp T -> M_k,      A_{N-1} only, which do not change until the trailing updates)
+//                            update A_k, Gram S_k
+//   fiber_contract  X -> U[E x R] (partials + reduce)   (pass 2 over X; w = prod of the UPDATED leading factors)
+//   trailing mode N-2: trail_mttkrp U -> M, update; trailing mode N-1: trail_mttkrp U (with updated A_{N-2}) -> M, update
+//   error scalar + convergence flag on the device.
+// Exactly the Gauss-Seidel order of tensorly's non_negative_parafac (mode 0, 1, ..., N-1) -- each M_n is the MTTKRP
+// with the factors as they stand when mode n is updated -- with 2 reads of X per iteration instead of N * R.
+// Masked: the imputed entries follow the current factors, so T (resp. U) is recomputed before every mode: N passes.
+#include "c2c_contract.cuh"
+#include "c2c_small.cuh"
+#include "../../include/c2c_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#define C2C_VERSION 100
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+// kernels enqueued by this library (all threads); graph replays add the captured iteration's launch count
+static std::atomic<long long> g_launches{0};
+#define CK(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, what); } while (0)
+#define CKL(what) do { g_launches.fetch_add(1, std::memory_order_relaxed); CK(cudaGetLastError(), what); } while (0)
+
+extern "C" int c2c_version(void) { return C2C_VERSION; }
+extern "C" const char* c2c_last_error(void) { return g_err; }
+extern "C" long long c2c_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int sm_count()
+{
+    static thread_local int dev_cached = -1, n_cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != dev_cached) {
+        if (cudaDeviceGetAttribute(&n_cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_cached = 148;
+        dev_cached = dev;
+    }
+    return n_cached;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ldr_of(int rank) { return (rank + 3) / 4 * 4; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// geometry of a tensor seen as P planes of E = I2 x I3 entries
+// ---------------------------------------------------------------------------------------------------------------------
+struct Geo {
+    int ndim; long long shape[C2C_MAX_DIMS];
+    long long P, E; int I2, I3; long long maxI;
+    int vec_plane, vec_fiber;
+    // fiber_contract launch
+    int fc_block, fc_nvec, fc_nvec_total, fc_nslots, fc_gx, fc_gy; long long fc_ppc; long long fc_nparts;
+    int np2;     // rank pairs per chunk
+    int nchunk;  // rank chunks
+};
+
+static int fiber_geometry(Geo& g, int np2_chunk)
+{
+    const int maxT = C2C_FC_MAXTHREADS(np2_chunk);
+    g.fc_nvec_total = (int)(g.E / g.vec_fiber);
+    if (g.fc_nvec_total >= maxT) {
+        g.fc_nvec = maxT; g.fc_nslots = 1; g.fc_block = maxT;
+        g.fc_gy = (g.fc_nvec_total + maxT - 1) / maxT;
+    } else {
+        g.fc_nvec = g.fc_nvec_total; g.fc_nslots = maxT / g.fc_nvec;
+        if ((long long)g.fc_nslots > g.P) g.fc_nslots = (int)g.P;
+        g.fc_block = (g.fc_nslots * g.fc_nvec + 31) / 32 * 32;
+        g.fc_gy = 1;
+    }
+    // enough CTAs to fill the machine (occupancy ~ 2048 / block CTAs per SM), each owning >= one tile of planes per slot
+    const int per_sm = 2048 / g.fc_block > 0 ? (2048 / g.fc_block > 4 ? 4 : 2048 / g.fc_block) : 1;
+    long long want = (long long)sm_count() * per_sm / g.fc_gy;
+    if (want < 1) want = 1;
+    const long long min_ppc = (long long)g.fc_nslots * C2C_FC_UNROLL;
+    long long gx = (g.P + min_ppc - 1) / min_ppc;
+    if (gx > want) gx = want;
+    if (gx < 1) gx = 1;
+    g.fc_ppc = (g.P + gx - 1) / gx;
+    g.fc_gx = (int)((g.P + g.fc_ppc - 1) / g.fc_ppc);
+    g.fc_nparts = (long long)g.fc_gx * g.fc_nslots;
+    return 0;
+}
+
+static int make_geo(Geo& g, int ndim, const int64_t* shape, int rank)
+{
+    if (ndim < 3 || ndim > C2C_MAX_DIMS) return fail(-1, "ndim must be in [3, %d], got %d", C2C_MAX_DIMS, ndim);
+    if (rank < 1 || rank > C2C_MAX_RANK) return fail(-2, "rank must be in [1, %d], got %d", C2C_MAX_RANK, rank);
+    g.ndim = ndim; g.P = 1; g.maxI = 0;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] < 1 || shape[i] > 0x7fffffffLL) return fail(-3, "shape[%d] = %lld out of range", i, (long long)shape[i]);
+        g.shape[i] = shape[i];
+        if (i < ndim - 2) g.P *= shape[i];
+        if (shape[i] > g.maxI) g.maxI = shape[i];
+    }
+    g.I2 = (int)shape[ndim - 2]; g.I3 = (int)shape[ndim - 1];
+    g.E = (long long)g.I2 * g.I3;
+    g.vec_plane = (g.I3 % 4 == 0) ? 4 : ((g.I3 % 2 == 0) ? 2 : 1);
+    g.vec_fiber = (g.E % 4 == 0) ? 4 : ((g.E % 2 == 0) ? 2 : 1);
+    const int np2 = (rank + 1) / 2;
+    g.nchunk = (np2 + C2C_MAX_NP2 - 1) / C2C_MAX_NP2;
+    g.np2 = (np2 + g.nchunk - 1) / g.nchunk;
+    // shared memory of plane_contract: A2 as (a,a) pairs + A3
+    const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);
+    if (smem > 200 * 1024)
+        return fail(-4, "trailing modes %d x %d at rank %d need %zu B of shared memory (> 200 KiB): put the two smallest modes last",
+                    g.I2, g.I3, rank, smem);
+    return fiber_geometry(g, g.np2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------------------------------
+struct Ws {
+    float* T; float* part; float* U; float* M; float* G; float* Bmat; float* Xh;
+    double* S; double* gram_part; double* iprod_part; double* normX2; double* sums_part; double* scratch_d;
+    int* flags;
+    size_t bytes;
+};
+
+#define C2C_SUMSQ_BLOCKS 1184     // 148 x 8
+#define C2C_SUMS_BLOCKS  1184
+
+static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
+{
+    const int ldr = ldr_of(rank);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    const long long nblk = (g.maxI + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS;
+    w.T = (float*)take((size_t)g.P * ldr * sizeof(float));
+    w.part = (float*)take((size_t)g.fc_nparts * g.E * ldr * sizeof(float));
+    w.U = (float*)take((size_t)g.E * ldr * sizeof(float));
+    w.M = (float*)take((size_t)g.maxI * ldr * sizeof(float));
+    w.G = (float*)take((size_t)ldr * ldr * sizeof(float));
+    w.Bmat = (float*)take(masked ? (size_t)g.E * ldr * sizeof(float) : 0);
+    // ranks beyond one chunk: the masked passes need the full-rank reconstruction, so the imputed tensor is materialised
+    w.Xh = (float*)take((masked && g.nchunk > 1) ? (size_t)g.P * g.E * sizeof(float) : 0);
+    w.S = (double*)take((size_t)g.ndim * ldr * ldr * sizeof(double));
+    w.gram_part = (double*)take((size_t)nblk * ldr * ldr * sizeof(double));
+    w.iprod_part = (double*)take((size_t)nblk * sizeof(double));
+    w.normX2 = (double*)take(sizeof(double));
+    w.sums_part = (double*)take((size_t)C2C_SUMS_BLOCKS * 5 * sizeof(double));
+    w.scratch_d = (double*)take(16 * sizeof(double));
+    w.flags = (int*)take(4 * sizeof(int));
+    w.bytes = off;
+}
+
+extern "C" size_t c2c_ncp_workspace_bytes(int ndim, const int64_t* shape, int rank, int masked)
+{
+    Geo g;
+    if (make_geo(g, ndim, shape, rank) != 0) return 0;
+    Ws w;
+    carve(w, g, rank, masked, nullptr);
+    return w.bytes;
+}
+
+static int get_ws(Ws& w, const Geo& g, int rank, int masked, void* ws, size_t ws_bytes)
+{
+    carve(w, g, rank, masked, nullptr);
+    if (ws == nullptr || ws_bytes < w.bytes)
+        return fail(-5, "workspace too small: need %zu bytes, got %zu (query c2c_ncp_workspace_bytes)", w.bytes, ws_bytes);
+    if (((uintptr_t)ws & 255) != 0) return fail(-6, "workspace must be 256-byte aligned");
+    carve(w, g, rank, masked, (char*)ws);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------------------------
+static void fill_lead(LeadInfo& li, const Geo& g, const float* const* A)
+{
+    li.nl = g.ndim - 2;
+    for (int k = 0; k < C2C_MAX_LEAD; ++k) { li.dim[k] = 1; li.fac[k] = nullptr; }
+    for (int k = 0; k < li.nl; ++k) { li.dim[k] = (int)g.shape[k]; li.fac[k] = A[k]; }
+}
+
+static ContractArgs base_args(const Geo& g, const float* X, const uint8_t* mask, const float* const* A, int ldr, int rank,
+                              const int* done)
+{
+    ContractArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = X; a.mask = mask; a.P = g.P; a.I2 = g.I2; a.I3 = g.I3; a.R = rank; a.ldr = ldr; a.r0 = 0;
+    a.A2 = A[g.ndim - 2]; a.A3 = A[g.ndim - 1];
+    fill_lead(a.lead, g, A);
+    a.done = done;
+    return a;
+}
+
+static int plane_grid(const Geo& g, int vec)
+{
+    const int nstrips = g.I3 / vec;
+    const int G = nstrips < 32 ? nstrips : 32;
+    const int ppw = 32 / G;
+    const long long warps = (g.P + ppw - 1) / ppw;
+    long long blocks = (warps + (C2C_PC_THREADS / 32) - 1) / (C2C_PC_THREADS / 32);
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// T[P x ldr] = plane contraction of Xh with the two trailing factors
+static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cudaStream_t st)
+{
+    const int vec = g.vec_plane;
+    const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);
+    const int grid = plane_grid(g, vec);
+    a.out = T;
+    for (int c = 0; c < g.nchunk; ++c) {
+        a.r0 = c * 2 * g.np2;
+        if (a.r0 >= a.R) break;
+        cudaError_t e;
+        if (masked) {
+            e = vec == 4 ? c2c_launch_plane_v4_m1(g.np2, a, grid, smem, st)
+              : vec == 2 ? c2c_launch_plane_v2_m1(g.np2, a, grid, smem, st) : c2c_launch_plane_v1_m1(g.np2, a, grid, smem, st);
+        } else {
+            e = vec == 4 ? c2c_launch_plane_v4_m0(g.np2, a, grid, smem, st)
+              : vec == 2 ? c2c_launch_plane_v2_m0(g.np2, a, grid, smem, st) : c2c_launch_plane_v1_m0(g.np2, a, grid, smem, st);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "plane_contract launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return 0;
+}
+
+// U[E x ldr] = fiber contraction of Xh with the Khatri-Rao rows of the leading factors (partials + fixed-order reduce)
+static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, cudaStream_t st)
+{
+    const int vec = g.vec_fiber;
+    a.out = w.part;
+    if (masked) {
+        const long long n = g.E * a.ldr;
+        bmat_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(a.A2, a.A3, g.I2, g.I3, a.ldr, w.Bmat, a.done);
+        CKL("bmat launch");
+        a.Bmat = w.Bmat;
+    }
+    const dim3 grid(g.fc_gx, g.fc_gy);
+    for (int c = 0; c < g.nchunk; ++c) {
+        a.r0 = c * 2 * g.np2;
+        if (a.r0 >= a.R) break;
+        cudaError_t e;
+        if (masked) {
+            e = vec == 4 ? c2c_launch_fiber_v4_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
+              : vec == 2 ? c2c_launch_fiber_v2_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
+                         : c2c_launch_fiber_v1_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st);
+        } else {
+            e = vec == 4 ? c2c_launch_fiber_v4_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
+              : vec == 2 ? c2c_launch_fiber_v2_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
+                         : c2c_launch_fiber_v1_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_contract launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    const long long n = g.E * a.ldr;
+    int rb = (int)((n + 255) / 256);
+    fiber_reduce_kernel<<<rb, 256, 0, st>>>(w.part, (int)g.fc_nparts, g.E, a.R, a.ldr, w.U, a.done);
+    CKL("fiber_reduce launch");
+    return 0;
+}
+
+// Xh = mask ? X : reconstruction (used when the rank does not fit one chunk)
+__global__ void __launch_bounds__(256)
+impute_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, long long P, int I2, int I3, LeadInfo lead,
+              const float* __restrict__ A2, const float* __restrict__ A3, int R, int ldr, float* __restrict__ Xh,
+              const int* done)
+{
+    if (run_done(done)) return;
+    const long long E = (long long)I2 * I3, n = P * E;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = X[i];
+        if (!mask[i]) {
+            const long long p = i / E; const int e = (int)(i - p * E);
+            const int s = e / I3, v = e - s * I3;
+            float rec = 0.0f;
+            for (int q = 0; q < R; ++q)
+                rec = fmaf(lead_weight_col(p, lead, ldr, q, -1) * A2[(size_t)s * ldr + q], A3[(size_t)v * ldr + q], rec);
+            x = rec;
+        }
+        Xh[i] = x;
+    }
+}
+
+// recon_sums for ranks beyond one chunk: one thread per entry, full-rank reconstruction in a loop (the factors are
+// L2-resident); per-CTA partial sums in the same layout as the plane_contract<SUMS> kernel.
+__global__ void __launch_bounds__(256)
+recon_sums_generic_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, long long P, int I2, int I3,
+                          LeadInfo lead, const float* __restrict__ A2, const float* __restrict__ A3, int R, int ldr,
+                          double* __restrict__ sums)
+{
+    const long long E = (long long)I2 * I3, n = P * E;
+    double v[5] = {0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        const long long p = i / E; const int e = (int)(i - p * E);
+        const int s = e / I3, c = e - s * I3;
+        float rec = 0.0f;
+        for (int q = 0; q < R; ++q)
+            rec = fmaf(lead_weight_col(p, lead, ldr, q, -1) * A2[(size_t)s * ldr + q], A3[(size_t)c * ldr + q], rec);
+        const double x = X[i], d = x - (double)rec;
+        v[0] += d; v[1] += d * d; v[2] += x; v[3] += x * x; v[4] += 1.0;
+    }
+    __shared__ double red[5][8];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const double t = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0;
+        for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+        sums[(size_t)blockIdx.x * 5 + threadIdx.x] = t;
+    }
+}
+
+static int maybe_impute(const Geo& g, ContractArgs& a, bool& masked, const Ws& w, cudaStream_t st)
+{
+    if (masked && g.nchunk > 1) {
+        impute_kernel<<<sm_count() * 8, 256, 0, st>>>(a.X, a.mask, g.P, g.I2, g.I3, a.lead, a.A2, a.A3, a.R, a.ldr, w.Xh, a.done);
+        CKL("impute launch");
+        a.X = w.Xh; a.mask = nullptr; masked = false;
+    }
+    return 0;
+}
+
+static int check_common(const float* X, const float* const* A, int ndim, int ldr, int rank)
+{
+    if (!X) return fail(-10, "X is NULL");
+    if (!A) return fail(-11, "A is NULL");
+    for (int i = 0; i < ndim; ++i) if (!A[i]) return fail(-11, "A[%d] is NULL", i);
+    if (ldr != ldr_of(rank)) return fail(-12, "ldr must be rank rounded up to a multiple of 4 (%d), got %d", ldr_of(rank), ldr);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 / K1b
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int c2c_build_ccc(const float* expr, const int64_t* expr_off, const int32_t* expr_ld, const int32_t* cell_col,
+                             const int32_t* a_first, const int32_t* a_count, const int32_t* b_first, const int32_t* b_count,
+                             const int32_t* sub_rows, int C, int L, int K, int score_kind, int agg_kind,
+                             float* X, uint8_t* mask, void* stream)
+{
+    if (C < 0 || L < 0 || K < 0) return fail(-1, "negative dimension");
+    if ((long long)C * L * K == 0) return 0;
+    if (!expr || !expr_off || !expr_ld || !cell_col || !a_first || !a_count || !b_first || !b_count || !sub_rows || !X)
+        return fail(-2, "NULL argument");
+    if (score_kind < 0 || score_kind > 2) return fail(-3, "score_kind %d not in {product, mean, gmean}", score_kind);
+    if (agg_kind < 0 || agg_kind > 2) return fail(-4, "agg_kind %d not in {min, mean, gmean}", agg_kind);
+    if (((uintptr_t)X & 15) != 0 || (mask && ((uintptr_t)mask & 3) != 0)) return fail(-5, "X must be 16-byte and mask 4-byte aligned");
+    BuildArgs a;
+    a.expr = expr; a.expr_off = (const long long*)expr_off; a.expr_ld = expr_ld; a.cell_col = cell_col;
+    a.first[0] = a_first; a.count[0] = a_count; a.first[1] = b_first; a.count[1] = b_count; a.sub_rows = sub_rows;
+    a.C = C; a.L = L; a.K = K; a.score = score_kind; a.agg = agg_kind; a.X = X; a.mask = mask;
+    const long long P = (long long)C * L;
+    const long long ntiles = (P + C2C_BUILD_TILE - 1) / C2C_BUILD_TILE;
+    const size_t smem = (size_t)C2C_BUILD_TILE * 2 * K * sizeof(double);
+    if (smem > 48 * 1024) return fail(-6, "K = %d too large for the build tile", K);
+    long long grid = ntiles; const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    build_ccc_kernel<<<(int)grid, C2C_SMALL_THREADS, smem, (cudaStream_t)stream>>>(a);
+    CKL("build_ccc launch");
+    return 0;
+}
+
+extern "C" int c2c_group_aggregate(const float* X_in, const uint8_t* mask_in, const int32_t* grp_off, const int32_t* grp_rows,
+                                   int C, int L, int n_groups, int64_t E, int method, float* X_out, uint8_t* mask_out,
+                                   void* stream)
+{
+    if (C < 0 || L < 0 || n_groups < 0 || E < 0) return fail(-1, "negative dimension");
+    if (method != C2C_AGG_GMEAN && method != C2C_AGG_SUM && method != C2C_AGG_MEAN) return fail(-3, "method %d not in {gmean, sum, mean}", method);
+    const long long n = (long long)C * n_groups * E;
+    if (n == 0) return 0;
+    if (!X_in || !grp_off || !grp_rows || !X_out) return fail(-2, "NULL argument");
+    long long grid = (n + 255) / 256; const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    group_aggregate_kernel<<<(int)grid, C2C_SMALL_THREADS, 0, (cudaStream_t)stream>>>(X_in, mask_in, grp_off, grp_rows, C, L, n_groups,
+                                                                                       E, method, X_out, mask_out);
+    CKL("group_aggregate launch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ||X||^2
+// ---------------------------------------------------------------------------------------------------------------------
+static int sumsq_into(const float* X, long long n, double* out, double* part, cudaStream_t st)
+{
+    int blocks = C2C_SUMSQ_BLOCKS;
+    const long long need = (n / 4 + 255) / 256;
+    if (need < blocks) blocks = (int)(need < 1 ? 1 : need);
+    sumsq_partial_kernel<<<blocks, C2C_SMALL_THREADS, 0, st>>>(X, n, part);
+    CKL("sumsq launch");
+    sum_partials_kernel<<<1, 32, 0, st>>>(part, blocks, 1, 1, out);
+    CKL("sumsq reduce launch");
+    return 0;
+}
+
+extern "C" int c2c_sumsq(const float* X, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!X || !out) return fail(-1, "NULL argument");
+    if (n < 0) return fail(-2, "negative length");
+    if (((uintptr_t)X & 15) != 0) return fail(-3, "X must be 16-byte aligned");
+    if (!ws || ws_bytes < C2C_SUMSQ_BLOCKS * sizeof(double)) return fail(-5, "workspace too small: need %zu bytes", C2C_SUMSQ_BLOCKS * sizeof(double));
+    return sumsq_into(X, n, out, (double*)ws, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// factor-sized steps
+// ---------------------------------------------------------------------------------------------------------------------
+static int launch_gram_partial(const float* A, const float* M, long long I, int R, int ldr, const Ws& w, bool want_ip,
+                               const int* done, cudaStream_t st)
+{
+    const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+    const size_t smem = (size_t)C2C_UPD_ROWS * R * sizeof(float);
+    gram_partial_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(A, M, I, R, ldr, w.gram_part, want_ip ? w.iprod_part : nullptr, done);
+    CKL("gram_partial launch");
+    return 0;
+}
+
+static int launch_mu(float* A, const float* M, const float* G, long long I, int R, int ldr, float eps, const Ws& w,
+                     bool want_gram, bool want_ip, const int* done, cudaStream_t st)
+{
+    const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+    const size_t smem = (size_t)2 * C2C_UPD_ROWS * R * sizeof(float);
+    mu_update_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(A, M, G, I, R, ldr, eps, want_gram ? w.gram_part : nullptr,
+                                                           want_ip ? w.iprod_part : nullptr, done);
+    CKL("mu_update launch");
+    return 0;
+}
+
+static int launch_hals(float* A, const float* M, const float* G, long long I, int R, int ldr, int max_sweeps, float tol,
+                       const int* done, cudaStream_t st)
+{
+    int threads = (int)(I < 1024 ? (I + 31) / 32 * 32 : 1024);
+    hals_update_kernel<<<1, threads, (size_t)R * R * sizeof(float), st>>>(A, M, G, I, R, ldr, max_sweeps, tol, done);
+    CKL("hals_update launch");
+    return 0;
+}
+
+static FinalizeArgs fin_args(const Geo& g, int R, int ldr, const Ws& w, const int* done)
+{
+    FinalizeArgs f;
+    memset(&f, 0, sizeof(f));
+    f.S = w.S; f.N = g.ndim; f.R = R; f.ldr = ldr; f.k = -1; f.next = -1; f.done = done;
+    return f;
+}
+
+// M for mode `mode` given fresh T (leading) or U (trailing)
+static int launch_mode_mttkrp(const Geo& g, const float* const* A, int mode, int R, int ldr, const Ws& w, float* M,
+                              const int* done, cudaStream_t st)
+{
+    if (mode < g.ndim - 2) {
+        LeadInfo li; fill_lead(li, g, A);
+        lead_mttkrp_kernel<<<(int)g.shape[mode], C2C_SMALL_THREADS, 0, st>>>(w.T, li, mode, g.P, R, ldr, M, done);
+        CKL("lead_mttkrp launch");
+    } else {
+        const int which = mode - (g.ndim - 2);
+        const float* oth = which == 0 ? A[g.ndim - 1] : A[g.ndim - 2];
+        const long long n = (long long)(which == 0 ? g.I2 : g.I3) * ldr;
+        trail_mttkrp_kernel<<<(int)((n + 127) / 128), 128, 0, st>>>(w.U, oth, g.I2, g.I3, which, R, ldr, M, done);
+        CKL("trail_mttkrp launch");
+    }
+    return 0;
+}
+
+extern "C" int c2c_mttkrp(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                          int ldr, int rank, int mode, float* M, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (mode < 0 || mode >= ndim) return fail(-13, "mode %d out of range", mode);
+    if (!M) return fail(-14, "M is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ContractArgs a = base_args(g, X, mask, A, ldr, rank, nullptr);
+    bool masked = mask != nullptr;
+    if ((rc = maybe_impute(g, a, masked, w, st)) != 0) return rc;
+    if (mode < ndim - 2) { if ((rc = launch_plane(g, a, masked, w.T, st)) != 0) return rc; }
+    else                 { if ((rc = launch_fiber(g, a, masked, w, st)) != 0) return rc; }
+    return launch_mode_mttkrp(g, A, mode, rank, ldr, w, M, nullptr, st);
+}
+
+extern "C" int c2c_plane_contract(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                                  int ldr, int rank, float* T, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!T) return fail(-14, "T is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    ContractArgs a = base_args(g, X, mask, A, ldr, rank, nullptr);
+    bool masked = mask != nullptr;
+    if ((rc = maybe_impute(g, a, masked, w, (cudaStream_t)stream)) != 0) return rc;
+    return launch_plane(g, a, masked, T, (cudaStream_t)stream);
+}
+
+extern "C" int c2c_fiber_contract(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                                  int ldr, int rank, float* U, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!U) return fail(-14, "U is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    ContractArgs a = base_args(g, X, mask, A, ldr, rank, nullptr);
+    bool masked = mask != nullptr;
+    if ((rc = maybe_impute(g, a, masked, w, (cudaStream_t)stream)) != 0) return rc;
+    if ((rc = launch_fiber(g, a, masked, w, (cudaStream_t)stream)) != 0) return rc;
+    CK(cudaMemcpyAsync(U, w.U, (size_t)g.E * ldr * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "copy U");
+    return 0;
+}
+
+extern "C" int c2c_gram_hadamard(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank, int skip_mode,
+                                 float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if (!A) return fail(-11, "A is NULL");
+    for (int i = 0; i < ndim; ++i) if (!A[i]) return fail(-11, "A[%d] is NULL", i);
+    if (ldr != ldr_of(rank)) return fail(-12, "ldr must be %d", ldr_of(rank));
+    if (skip_mode < -1 || skip_mode >= ndim) return fail(-13, "skip_mode %d out of range", skip_mode);
+    Ws w;
+    if ((rc = get_ws(w, g, rank, 0, ws, ws_bytes)) != 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int k = 0; k < ndim; ++k) {
+        if ((rc = launch_gram_partial(A[k], nullptr, g.shape[k], rank, ldr, w, false, nullptr, st)) != 0) return rc;
+        FinalizeArgs f = fin_args(g, rank, ldr, w, nullptr);
+        f.k = k; f.gram_part = w.gram_part; f.nblk = (int)((g.shape[k] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+        if (k == ndim - 1) { f.next = skip_mode < 0 ? ndim : skip_mode; f.G = G; f.rec_norm2 = rec_norm2; }
+        gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);
+        CKL("gram_finalize launch");
+    }
+    return 0;
+}
+
+extern "C" int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, float eps,
+                             void* ws, size_t ws_bytes, void* stream)
+{
+    (void)ws; (void)ws_bytes;
+    if (!A_mode || !M || !G) return fail(-1, "NULL argument");
+    if (I < 1 || rank < 1 || rank > C2C_MAX_RANK || ldr != ldr_of(rank)) return fail(-2, "bad I / rank / ldr");
+    Ws w; memset(&w, 0, sizeof(w));
+    return launch_mu(A_mode, M, G, I, rank, ldr, eps, w, false, false, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int c2c_hals_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, int max_sweeps,
+                               float tol, void* stream)
+{
+    if (!A_mode || !M || !G) return fail(-1, "NULL argument");
+    if (I < 1 || rank < 1 || rank > C2C_MAX_RANK || ldr != ldr_of(rank)) return fail(-2, "bad I / rank / ldr");
+    return launch_hals(A_mode, M, G, I, rank, ldr, max_sweeps, tol, nullptr, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K6 final sums
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                              int ldr, int rank, double* out, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!out) return fail(-14, "out is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ContractArgs a = base_args(g, X, mask, A, ldr, rank, nullptr);
+    a.sums = w.sums_part;
+    if (g.nchunk > 1) {
+        recon_sums_generic_kernel<<<C2C_SUMS_BLOCKS, 256, 0, st>>>(X, mask, g.P, g.I2, g.I3, a.lead, a.A2, a.A3, rank, ldr, w.sums_part);
+        CKL("recon_sums (generic) launch");
+        sum_partials_kernel<<<1, 32, 0, st>>>(w.sums_part, C2C_SUMS_BLOCKS, 5, 5, out);
+        CKL("recon_sums reduce launch");
+        return 0;
+    }
+    const int vec = g.vec_plane;
+    const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);
+    int grid = plane_grid(g, vec);
+    if (grid > C2C_SUMS_BLOCKS) grid = C2C_SUMS_BLOCKS;
+    cudaError_t e = vec == 4 ? c2c_launch_sums_v4(g.np2, a, grid, smem, st)
+                  : vec == 2 ? c2c_launch_sums_v2(g.np2, a, grid, smem, st) : c2c_launch_sums_v1(g.np2, a, grid, smem, st);
+    if (e != cudaSuccess) return cuda_fail(e, "recon_sums launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    sum_partials_kernel<<<1, 32, 0, st>>>(w.sums_part, grid, 5, 5, out);
+    CKL("recon_sums reduce launch");
+    return 0;
+}
+
+extern "C" int c2c_cp_normalize(float* const* A, int ndim, const int64_t* shape, int ldr, int rank, float* weights, void* stream)
+{
+    if (!A || !shape || !weights) return fail(-1, "NULL argument");
+    if (ndim < 1 || ndim > C2C_MAX_DIMS) return fail(-2, "bad ndim");
+    if (rank < 1 || rank > C2C_MAX_RANK || ldr != ldr_of(rank)) return fail(-3, "bad rank / ldr");
+    for (int k = 0; k < ndim; ++k) {
+        if (!A[k]) return fail(-1, "A[%d] is NULL", k);
+        cp_normalize_kernel<<<1, C2C_SMALL_THREADS, 0, (cudaStream_t)stream>>>(A[k], shape[k], rank, ldr, weights, k == 0 ? 1 : 0);
+        CKL("cp_normalize launch");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// whole factorization
+// ---------------------------------------------------------------------------------------------------------------------
+struct RunCtx {
+    Geo g; Ws w; const float* X; const uint8_t* mask; float* const* A; int ldr, R, algo, n_iter_max; double tol; int cvg;
+    const double* normX2; double* errors; int* state; cudaStream_t st; float eps;
+};
+
+static int update_mode(const RunCtx& c, int mode, bool last)
+{
+    const Geo& g = c.g; int rc;
+    const int* done = c.state + 1;
+    const float* const* A = (const float* const*)c.A;
+    if ((rc = launch_mode_mttkrp(g, A, mode, c.R, c.ldr, c.w, c.w.M, done, c.st)) != 0) return rc;
+    if (c.algo == C2C_ALGO_MU) {
+        if ((rc = launch_mu(c.A[mode], c.w.M, c.w.G, g.shape[mode], c.R, c.ldr, c.eps, c.w, true, last, done, c.st)) != 0) return rc;
+    } else {
+        if ((rc = launch_hals(c.A[mode], c.w.M, c.w.G, g.shape[mode], c.R, c.ldr, 100, 1e-8f, done, c.st)) != 0) return rc;
+        if ((rc = launch_gram_partial(c.A[mode], c.w.M, g.shape[mode], c.R, c.ldr, c.w, last, done, c.st)) != 0) return rc;
+    }
+    FinalizeArgs f = fin_args(g, c.R, c.ldr, c.w, done);
+    f.k = mode; f.gram_part = c.w.gram_part; f.nblk = (int)((g.shape[mode] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+    f.next = (mode + 1) % g.ndim; f.G = c.w.G;
+    if (last) {
+        f.iprod_part = c.w.iprod_part; f.nblk_ip = f.nblk; f.normX2 = c.normX2; f.errors = c.errors; f.state = c.state;
+        f.n_iter_max = c.n_iter_max; f.tol = c.tol; f.cvg = c.cvg;
+    }
+    gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, c.st>>>(f);
+    CKL("gram_finalize launch");
+    return 0;
+}
+
+static int enqueue_iteration(const RunCtx& c)
+{
+    const Geo& g = c.g; int rc;
+    const int* done = c.state + 1;
+    const float* const* A = (const float* const*)c.A;
+    const int nlead = g.ndim - 2;
+    const bool has_mask = c.mask != nullptr;
+    for (int mode = 0; mode < g.ndim; ++mode) {
+        const bool need_pass = has_mask || mode == 0 || mode == nlead;
+        if (need_pass) {
+            ContractArgs a = base_args(g, c.X, c.mask, A, c.ldr, c.R, done);
+            bool masked = has_mask;
+            if ((rc = maybe_impute(g, a, masked, c.w, c.st)) != 0) return rc;
+            if (mode < nlead) { if ((rc = launch_plane(g, a, masked, c.w.T, c.st)) != 0) return rc; }
+            else              { if ((rc = launch_fiber(g, a, masked, c.w, c.st)) != 0) return rc; }
+        }
+        if ((rc = update_mode(c, mode, mode == g.ndim - 1)) != 0) return rc;
+    }
+    return 0;
+}
+
+extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
+                           int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
+                           double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
+{
+    RunCtx c; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(c.g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, (const float* const*)A, ndim, ldr, rank)) != 0) return rc;
+    if (algo != C2C_ALGO_MU && algo != C2C_ALGO_HALS) return fail(-20, "algo %d not in {MU, HALS}", algo);
+    if (algo == C2C_ALGO_HALS && mask) return fail(-21, "HALS does not take a mask (tensorly non_negative_parafac_hals has none)");
+    if (cvg_criterion != C2C_CVG_ABS_REC_ERROR && cvg_criterion != C2C_CVG_REC_ERROR) return fail(-22, "unknown cvg_criterion %d", cvg_criterion);
+    if (n_iter_max < 0) return fail(-23, "n_iter_max < 0");
+    if (!errors || !state) return fail(-24, "errors / state is NULL");
+    if (((uintptr_t)X & 15) != 0) return fail(-25, "X must be 16-byte aligned");
+    if ((rc = get_ws(c.w, c.g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    c.X = X; c.mask = mask; c.A = A; c.ldr = ldr; c.R = rank; c.algo = algo; c.n_iter_max = n_iter_max; c.tol = tol;
+    c.cvg = cvg_criterion; c.errors = errors; c.state = state; c.st = (cudaStream_t)stream;
+    c.eps = 1.1920928955078125e-07f;      // finfo(float32).eps: tensorly clips numerator and denominator at the dtype's eps
+    cudaStream_t st = c.st;
+    const Geo& g = c.g;
+
+    CK(cudaMemsetAsync(state, 0, 2 * sizeof(int), st), "memset state");
+    if (normX2) c.normX2 = normX2;
+    else {
+        if ((rc = sumsq_into(X, g.P * g.E, c.w.normX2, c.w.sums_part, st)) != 0) return rc;
+        c.normX2 = c.w.normX2;
+    }
+    // Grams of the initial factors; G for mode 0
+    for (int k = 0; k < ndim; ++k) {
+        if ((rc = launch_gram_partial(A[k], nullptr, g.shape[k], rank, ldr, c.w, false, nullptr, st)) != 0) return rc;
+        FinalizeArgs f = fin_args(g, rank, ldr, c.w, nullptr);
+        f.k = k; f.gram_part = c.w.gram_part; f.nblk = (int)((g.shape[k] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+        if (k == ndim - 1) { f.next = 0; f.G = c.w.G; }
+        gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);
+        CKL("gram_finalize launch");
+    }
+    if (n_iter_max == 0) return 0;
+
+    // one iteration is captured once and replayed: ~15 launches per iteration become one graph launch
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    bool use_graph = n_iter_max >= 3;
+    long long per_iter = 0;
+    if (use_graph) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+            (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone))
+            use_graph = false;                                        // the caller is capturing: just enqueue
+    }
+    if (use_graph) {
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot capture) and replayed
+        // on the caller's stream
+        cudaStream_t cap = nullptr;
+        CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "create capture stream");
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cap); return cuda_fail(e, "begin capture"); }
+        const long long before = g_launches.load(std::memory_order_relaxed);
+        RunCtx cc = c; cc.st = cap;
+        rc = enqueue_iteration(cc);
+        per_iter = g_launches.load(std::memory_order_relaxed) - before;
+        g_launches.fetch_sub(per_iter, std::memory_order_relaxed);     // captured, not executed
+        e = cudaStreamEndCapture(cap, &graph);
+        cudaStreamDestroy(cap);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "end capture");
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "graph instantiate"); }
+    }
+    int host_state[2] = {0, 0};
+    rc = 0;
+    for (int it = 0; it < n_iter_max; ++it) {
+        if (use_graph) {
+            cudaError_t e = cudaGraphLaunch(exec, st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "graph launch"); break; }
+            g_launches.fetch_add(per_iter, std::memory_order_relaxed);
+        } else if ((rc = enqueue_iteration(c)) != 0) break;
+        if (check_every > 0 && (it + 1) % check_every == 0 && it + 1 < n_iter_max) {
+            cudaError_t e = cudaMemcpyAsync(host_state, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "poll state"); break; }
+            if (host_state[1]) break;
+        }
+    }
+    if (use_graph) {
+        // the exec object must outlive its in-flight launches
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+    }
+    return rc;
+}

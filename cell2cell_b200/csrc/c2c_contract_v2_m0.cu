@@ -1,0 +1,3 @@
+#define C2C_INST_VEC 2
+#define C2C_INST_MASKED 0
+#include "c2c_contract_inst.cuh"

@@ -1,0 +1,270 @@
+"""Device-side driver: torch owns device memory and streams, ``libc2c_b200.so`` does the work.
+
+Every function here takes CUDA tensors (or uploads numpy arrays) and calls the C ABI of ``include/c2c_b200.h`` through
+``_lib``.  Factor matrices travel as ``[I_n, ldr]`` fp32 tensors with ``ldr = rank`` rounded up to a multiple of 4 and zero
+padding columns (``pack_factor`` / ``unpack_factor``).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, lib
+
+__all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
+           "plane_contract", "fiber_contract", "launch_count",
+           "mu_update", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "build_ccc", "group_aggregate"]
+
+_vp = ctypes.c_void_p
+
+
+def require_cuda(device=None):
+    """Resolve ``device`` to a CUDA ``torch.device`` or raise: there is no CPU path."""
+    if not torch.cuda.is_available():
+        raise C2CError("no CUDA device is visible: cell2cell_b200 runs on B200 (sm_100a) only and has no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise C2CError("device %r is not a CUDA device: cell2cell_b200 has no CPU fallback" % (device,))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def ldr_of(rank):
+    return (int(rank) + 3) // 4 * 4
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return _vp(0) if t is None else _vp(t.data_ptr())
+
+
+def _shape_arr(shape):
+    return (ctypes.c_int64 * len(shape))(*[int(s) for s in shape])
+
+
+def _ptr_arr(tensors):
+    return (_vp * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def pack_factor(f, rank, device):
+    """numpy / torch ``[I, rank]`` -> contiguous fp32 ``[I, ldr]`` on ``device`` with zero padding columns."""
+    t = torch.as_tensor(np.ascontiguousarray(f) if isinstance(f, np.ndarray) else f)
+    out = torch.zeros((t.shape[0], ldr_of(rank)), dtype=torch.float32, device=device)
+    out[:, :rank] = t.to(device=device, dtype=torch.float32)
+    return out
+
+
+def unpack_factor(t, rank):
+    return t[:, :rank]
+
+
+def _check_tensor(X, mask):
+    if not (isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()):
+        raise C2CError("tensor must be a contiguous fp32 CUDA tensor")
+    if not 3 <= X.dim() <= MAX_NDIM:
+        raise C2CError("tensor must have between 3 and %d dimensions, got %d" % (MAX_NDIM, X.dim()))
+    if mask is not None:
+        if not (isinstance(mask, torch.Tensor) and mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
+                and mask.shape == X.shape and mask.device == X.device):
+            raise C2CError("mask must be a contiguous uint8 CUDA tensor of the tensor's shape on the same device")
+
+
+class Workspace:
+    """Scratch buffer for the factorization entry points, sized by ``c2c_ncp_workspace_bytes``."""
+
+    def __init__(self, shape, rank, masked, device):
+        self.shape = tuple(int(s) for s in shape)
+        self.rank = int(rank)
+        self.masked = bool(masked)
+        nbytes = lib().c2c_ncp_workspace_bytes(len(self.shape), _shape_arr(self.shape), self.rank, int(self.masked))
+        if nbytes == 0:
+            check(-1, "c2c_ncp_workspace_bytes")
+        self.nbytes = int(nbytes)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+
+    @property
+    def ptr(self):
+        return _vp(self.buf.data_ptr())
+
+    def fits(self, shape, rank, masked):
+        return self.shape == tuple(int(s) for s in shape) and self.rank == int(rank) and (self.masked or not masked)
+
+
+def _ws_for(X, rank, mask, ws):
+    if ws is not None and ws.fits(X.shape, rank, mask is not None) and ws.buf.device == X.device:
+        return ws
+    return Workspace(X.shape, rank, mask is not None, X.device)
+
+
+def sumsq(X, ws=None):
+    """sum(X**2) with fp64 accumulation (tensorly ``tl.norm(tensor, 2) ** 2``)."""
+    with torch.cuda.device(X.device):
+        out = torch.zeros(1, dtype=torch.float64, device=X.device)
+        scratch = torch.empty(1184 * 8, dtype=torch.uint8, device=X.device)
+        check(lib().c2c_sumsq(_ptr(X), X.numel(), _ptr(out), _ptr(scratch), scratch.numel(), _stream()), "c2c_sumsq")
+        return float(out.item())
+
+
+def mttkrp(X, mask, factors, rank, mode, ws=None):
+    """Fused (masked) MTTKRP of one mode; returns ``M`` as ``[I_mode, ldr]``."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, mask, ws)
+        M = torch.empty((X.shape[mode], ldr_of(rank)), dtype=torch.float32, device=X.device)
+        check(lib().c2c_mttkrp(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                               mode, _ptr(M), ws.ptr, ws.nbytes, _stream()), "c2c_mttkrp")
+        return M
+
+
+def plane_contract(X, mask, factors, rank, ws=None, out=None):
+    """T[P, ldr]: contraction of every plane with the two trailing factors (one read of X)."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, mask, ws)
+        P = int(np.prod(X.shape[:-2]))
+        T = out if out is not None else torch.empty((P, ldr_of(rank)), dtype=torch.float32, device=X.device)
+        check(lib().c2c_plane_contract(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank),
+                                       rank, _ptr(T), ws.ptr, ws.nbytes, _stream()), "c2c_plane_contract")
+        return T
+
+
+def fiber_contract(X, mask, factors, rank, ws=None, out=None):
+    """U[I_{N-2} * I_{N-1}, ldr]: contraction of every in-plane position with the leading Khatri-Rao rows (one read of X)."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, mask, ws)
+        E = int(X.shape[-2] * X.shape[-1])
+        U = out if out is not None else torch.empty((E, ldr_of(rank)), dtype=torch.float32, device=X.device)
+        check(lib().c2c_fiber_contract(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank),
+                                       rank, _ptr(U), ws.ptr, ws.nbytes, _stream()), "c2c_fiber_contract")
+        return U
+
+
+def launch_count():
+    """Kernels enqueued by libc2c_b200.so so far in this process."""
+    return int(lib().c2c_launch_count())
+
+
+def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None):
+    """(G, cp_norm^2): Hadamard product of the factor Grams, skipping ``skip_mode`` (-1: none)."""
+    dev = factors[0].device
+    with torch.cuda.device(dev):
+        if ws is None:
+            ws = Workspace(shape, rank, False, dev)
+        ldr = ldr_of(rank)
+        G = torch.empty((ldr, ldr), dtype=torch.float32, device=dev)
+        n2 = torch.zeros(1, dtype=torch.float64, device=dev)
+        check(lib().c2c_gram_hadamard(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr, rank, skip_mode, _ptr(G),
+                                      _ptr(n2), ws.ptr, ws.nbytes, _stream()), "c2c_gram_hadamard")
+        return G, float(n2.item())
+
+
+def mu_update(A, M, G, rank, eps=float(np.finfo(np.float32).eps)):
+    with torch.cuda.device(A.device):
+        check(lib().c2c_mu_update(_ptr(A), _ptr(M), _ptr(G), A.shape[0], rank, ldr_of(rank), eps, _vp(0), 0, _stream()),
+              "c2c_mu_update")
+    return A
+
+
+def hals_update(A, M, G, rank, max_sweeps=100, tol=1e-8):
+    with torch.cuda.device(A.device):
+        check(lib().c2c_hals_update(_ptr(A), _ptr(M), _ptr(G), A.shape[0], rank, ldr_of(rank), max_sweeps, tol, _stream()),
+              "c2c_hals_update")
+    return A
+
+
+def recon_sums(X, mask, factors, rank, ws=None):
+    """fp64 ``[sum m(x-rec), sum m(x-rec)^2, sum m x, sum m x^2, sum m]`` in one pass (m = mask, all ones if None)."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, mask, ws)
+        out = torch.zeros(5, dtype=torch.float64, device=X.device)
+        check(lib().c2c_recon_sums(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                   _ptr(out), ws.ptr, ws.nbytes, _stream()), "c2c_recon_sums")
+        return out.cpu().numpy()
+
+
+def cp_normalize(factors, rank, weights=None):
+    """In-place ``cp_normalize`` of packed factors; returns the weights (fp32 ``[rank]`` CUDA tensor)."""
+    dev = factors[0].device
+    with torch.cuda.device(dev):
+        w = torch.ones(rank, dtype=torch.float32, device=dev) if weights is None else weights.to(dev, torch.float32).clone()
+        shape = [f.shape[0] for f in factors]
+        check(lib().c2c_cp_normalize(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr_of(rank), rank, _ptr(w),
+                                     _stream()), "c2c_cp_normalize")
+        return w
+
+
+def ncp_run(X, mask, factors, rank, tf_type="non_negative_cp", n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error",
+            check_every=10, norm_x2=None, ws=None, sync=True):
+    """Run tensorly-semantics NCP on the device, updating the packed ``factors`` in place.
+
+    Returns ``(errors, n_iter, converged)``; ``errors`` is a float64 numpy array with one entry per iteration done.
+    With ``sync=False`` returns the raw device buffers ``(errors_dev, state_dev)`` without waiting."""
+    _check_tensor(X, mask)
+    if rank < 1 or rank > MAX_RANK:
+        raise C2CError("rank must be in [1, %d], got %r" % (MAX_RANK, rank))
+    if tf_type not in ALGO:
+        raise C2CError("tf_type %r is not one of %s" % (tf_type, sorted(ALGO)))
+    if cvg_criterion not in CVG:
+        raise C2CError("cvg_criterion %r is not one of %s" % (cvg_criterion, sorted(CVG)))
+    if len(factors) != X.dim():
+        raise C2CError("need one factor per mode")
+    for f, s in zip(factors, X.shape):
+        if f.shape != (s, ldr_of(rank)) or f.dtype != torch.float32 or not f.is_contiguous() or f.device != X.device:
+            raise C2CError("factors must be packed fp32 [I_n, ldr] tensors on the tensor's device (pack_factor)")
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, mask, ws)
+        errors = torch.zeros(max(int(n_iter_max), 1), dtype=torch.float64, device=X.device)
+        state = torch.zeros(2, dtype=torch.int32, device=X.device)
+        nx2 = None
+        if norm_x2 is not None:
+            nx2 = torch.tensor([float(norm_x2)], dtype=torch.float64, device=X.device)
+        check(lib().c2c_ncp_run(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                ALGO[tf_type], int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(nx2), _ptr(errors),
+                                _ptr(state), int(check_every), ws.ptr, ws.nbytes, _stream()), "c2c_ncp_run")
+        if not sync:
+            return errors, state
+        st = state.cpu().numpy()
+        n_iter = int(st[0])
+        return errors[:n_iter].cpu().numpy(), n_iter, bool(st[1])
+
+
+def build_ccc(expr, expr_off, expr_ld, cell_col, a_first, a_count, b_first, b_count, sub_rows, C, L, K, score, agg,
+              with_mask, device):
+    """K1: returns ``(X [C, L, K, K] fp32, mask uint8 or None)`` on ``device``.  Index arrays are host numpy arrays."""
+    dev = require_cuda(device)
+    with torch.cuda.device(dev):
+        def up(a, dt):
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=True)
+        d_expr = expr if isinstance(expr, torch.Tensor) else up(expr, np.float32)
+        d = [up(expr_off, np.int64), up(expr_ld, np.int32), up(cell_col, np.int32), up(a_first, np.int32),
+             up(a_count, np.int32), up(b_first, np.int32), up(b_count, np.int32),
+             up(sub_rows if len(sub_rows) else np.zeros(1, np.int32), np.int32)]
+        X = torch.empty((C, L, K, K), dtype=torch.float32, device=dev)
+        mask = torch.empty((C, L, K, K), dtype=torch.uint8, device=dev) if with_mask else None
+        check(lib().c2c_build_ccc(_ptr(d_expr), *[_ptr(t) for t in d], C, L, K, SCORE[score], AGG[agg], _ptr(X), _ptr(mask),
+                                  _stream()), "c2c_build_ccc")
+        return X, mask
+
+
+def group_aggregate(X, mask, grp_off, grp_rows, method):
+    """K1b: aggregate LR rows of ``X [C, L, ...]`` into groups; returns ``(X_out, mask_out)``."""
+    dev = X.device
+    C, L = int(X.shape[0]), int(X.shape[1])
+    E = int(np.prod(X.shape[2:]))
+    ng = len(grp_off) - 1
+    with torch.cuda.device(dev):
+        d_off = torch.as_tensor(np.ascontiguousarray(grp_off, dtype=np.int32)).to(dev)
+        d_rows = torch.as_tensor(np.ascontiguousarray(grp_rows, dtype=np.int32)).to(dev)
+        Xo = torch.empty((C, ng) + tuple(X.shape[2:]), dtype=torch.float32, device=dev)
+        mo = torch.empty(Xo.shape, dtype=torch.uint8, device=dev)
+        check(lib().c2c_group_aggregate(_ptr(X), _ptr(mask), _ptr(d_off), _ptr(d_rows), C, L, ng, E, AGG[method], _ptr(Xo),
+                                        _ptr(mo), _stream()), "c2c_group_aggregate")
+        return Xo, mo

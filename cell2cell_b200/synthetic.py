@@ -86,4 +86,4 @@ def synthetic_lowrank_tensor(shape, rank=5, noise=0.05, seed=1, dtype=np.float32
     x = np.einsum(expr, *factors, optimize=True)
     x = x / x.mean()
     x += noise * rs.random_sample(x.shape)
-    return x.astype(dtype)
+    return np.ascontiguousarray(x, dtype=dtype)

@@ -1,0 +1,9 @@
+"""Drop-in for the hot-path part of ``cell2cell.tensor`` (cell2cell/tensor/__init__.py:1-8)."""
+from .metrics import correlation_index, pairwise_correlation_index
+from .tensor import (BaseTensor, InteractionTensor, PreBuiltTensor, build_context_ccc_tensor, generate_tensor_metadata)
+from .factorization import (non_negative_parafac, non_negative_parafac_hals, normalized_error)
+from .cp import CPTensor
+
+__all__ = ["BaseTensor", "InteractionTensor", "PreBuiltTensor", "build_context_ccc_tensor", "generate_tensor_metadata",
+           "correlation_index", "pairwise_correlation_index", "non_negative_parafac", "non_negative_parafac_hals",
+           "normalized_error", "CPTensor"]

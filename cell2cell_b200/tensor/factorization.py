@@ -1,0 +1,238 @@
+"""Factorization front end: same functions and signatures as ``cell2cell/tensor/factorization.py``, with the tensorly
+calls replaced by the device driver (``cell2cell_b200.engine`` -> ``libc2c_b200.so``).
+
+* ``non_negative_parafac`` / ``non_negative_parafac_hals`` keep tensorly's signatures (the reference forwards ``**kwargs``
+  verbatim, factorization.py:101) and semantics: host-seeded or device-svd init, Gauss-Seidel mode order, eps clipping,
+  the Gram-form reconstruction error, ``abs(err[-2] - err[-1]) < tol`` stop rule, masked imputation with the current
+  factors before every mode.
+* ``_compute_tensor_factorization`` (factorization.py:14-143), ``_run_elbow_analysis`` (:186-269),
+  ``_multiple_runs_elbow_analysis`` (:272-373), ``_compute_norm_error`` (:376-432), ``normalized_error`` (:435-458) and
+  ``_compute_elbow`` (:146-183, Kneedle restated in ``elbow.py`` because kneed is not installable here).
+"""
+import numpy as np
+import torch
+from tqdm.auto import tqdm
+
+from .. import engine
+from .._lib import C2CError
+from .cp import CPTensor, initialize_factors
+from .elbow import kneedle_elbow
+
+__all__ = ["non_negative_parafac", "non_negative_parafac_hals", "_compute_tensor_factorization", "_compute_elbow",
+           "_run_elbow_analysis", "_multiple_runs_elbow_analysis", "_compute_norm_error", "normalized_error",
+           "as_device_tensor", "as_device_mask"]
+
+
+def as_device_tensor(tensor, device=None):
+    """fp32 contiguous CUDA view / copy of ``tensor`` (numpy or torch, any float or int dtype)."""
+    if isinstance(tensor, torch.Tensor) and tensor.is_cuda and device is None:
+        dev = tensor.device
+    else:
+        dev = engine.require_cuda(device)
+    if isinstance(tensor, torch.Tensor):
+        t = tensor.to(device=dev, dtype=torch.float32)
+    else:
+        arr = np.asarray(tensor)
+        t = torch.as_tensor(np.ascontiguousarray(arr)).to(device=dev, dtype=torch.float32)
+    return t.contiguous()
+
+
+def as_device_mask(mask, like):
+    """uint8 contiguous CUDA mask on ``like``'s device (non-zero = observed), or None."""
+    if mask is None:
+        return None
+    if isinstance(mask, torch.Tensor):
+        m = mask.to(device=like.device)
+    else:
+        m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask))).to(like.device)
+    if m.shape != like.shape:
+        raise ValueError("mask and tensor must have the same shape")
+    if m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    return m.contiguous()
+
+
+def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, verbose, return_errors, mask,
+               cvg_criterion, normalize_factors, fixed_modes, check_every=10):
+    if normalize_factors:
+        raise NotImplementedError("normalize_factors=True is not supported by the B200 path (cell2cell never sets it)")
+    if fixed_modes:
+        raise NotImplementedError("fixed_modes is not supported by the B200 path (cell2cell never sets it)")
+    rank = int(rank)
+    X = as_device_tensor(tensor)
+    M = as_device_mask(mask, X)
+    host_factors = initialize_factors(X, rank, init=init, svd=svd, random_state=random_state)
+    factors = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in host_factors]
+    # tensorly records no errors when tol is falsy; the reference would then fail on errors[-1] -- we always record them.
+    errors, n_iter, converged = engine.ncp_run(X, M, factors, rank, tf_type=algo, n_iter_max=int(n_iter_max),
+                                               tol=float(tol) if tol else -1.0, cvg_criterion=cvg_criterion,
+                                               check_every=check_every)
+    if M is None and n_iter > 0:
+        # The per-iteration errors are tensorly's Gram form sqrt(|nx2 + rn2 - 2 ip|) / sqrt(nx2): in fp32 it cancels once
+        # the error is small.  The last one -- the value cell2cell keeps (tensor.py:311-315, factorization.py:262,356) --
+        # is replaced by the directly accumulated ||X - rec|| / ||X|| (one extra fused pass, fp64 sums), which is what the
+        # fp64 reference's Gram form equals.
+        s = engine.recon_sums(X, None, factors, rank)
+        errors = np.array(errors, dtype=np.float64)
+        errors[-1] = np.sqrt(s[1]) / np.sqrt(s[3])
+    if verbose:
+        for it, e in enumerate(errors):
+            print("iteration {}, reconstruction error: {}".format(it, e))
+        if converged:
+            print("PARAFAC converged after {} iterations".format(n_iter))
+    out = [engine.unpack_factor(f, rank).cpu().numpy() for f in factors]
+    cp = CPTensor(np.ones(rank, dtype=np.float32), out, device=X.device)
+    if return_errors:
+        return cp, [np.float64(e) for e in errors]
+    return cp
+
+
+def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-7, random_state=None,
+                         verbose=0, normalize_factors=False, return_errors=False, mask=None,
+                         cvg_criterion="abs_rec_error", fixed_modes=None):
+    """tensorly ``non_negative_parafac`` (multiplicative updates) on the device."""
+    return _factorize(tensor, rank, "non_negative_cp", n_iter_max, init, svd, tol, random_state, verbose, return_errors,
+                      mask, cvg_criterion, normalize_factors, fixed_modes)
+
+
+def non_negative_parafac_hals(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-8, random_state=None,
+                              sparsity_coefficients=None, fixed_modes=None, nn_modes="all", exact=False,
+                              normalize_factors=False, verbose=False, return_errors=False, cvg_criterion="abs_rec_error"):
+    """tensorly ``non_negative_parafac_hals`` (HALS column sweeps, exact=False) on the device."""
+    if sparsity_coefficients is not None and any(s for s in sparsity_coefficients):
+        raise NotImplementedError("sparsity_coefficients are not supported by the B200 path")
+    if nn_modes not in ("all", None) and set(nn_modes) != set(range(np.ndim(tensor))):
+        raise NotImplementedError("nn_modes other than 'all' is not supported by the B200 path")
+    if exact:
+        raise NotImplementedError("exact=True (active-set NNLS) is not supported by the B200 path")
+    # tensorly's HALS variant always returns (cp, errors) to cell2cell (factorization.py:107)
+    cp, errors = _factorize(tensor, rank, "non_negative_cp_hals", n_iter_max, init, svd, tol, random_state, verbose, True,
+                            None, cvg_criterion, normalize_factors, fixed_modes)
+    return (cp, errors) if return_errors else cp
+
+
+def _compute_tensor_factorization(tensor, rank, tf_type="non_negative_cp", init="svd", svd="truncated_svd",
+                                  random_state=None, mask=None, n_iter_max=100, tol=10e-7, verbose=False, **kwargs):
+    """Same contract as the reference's ``_compute_tensor_factorization`` (factorization.py:14-143)."""
+    return_errors = bool(kwargs.get("return_errors", False)) if kwargs else False
+    kwargs = dict(kwargs or {})
+    if tf_type == "non_negative_cp":
+        kwargs.pop("return_errors", None)
+        cp_tf = non_negative_parafac(tensor=tensor, rank=rank, init="random" if mask is not None else init, svd=svd,
+                                     random_state=random_state, mask=mask, n_iter_max=n_iter_max, tol=tol,
+                                     verbose=verbose, return_errors=True, **kwargs)
+        cp_tf, errors = cp_tf
+    elif tf_type == "non_negative_cp_hals":
+        kwargs.pop("return_errors", None)
+        cp_tf, errors = non_negative_parafac_hals(tensor=tensor, rank=rank, init=init, svd=svd, random_state=random_state,
+                                                  n_iter_max=n_iter_max, tol=tol, verbose=verbose, return_errors=True,
+                                                  **kwargs)
+    elif tf_type in ("parafac", "constrained_parafac"):
+        raise NotImplementedError("tf_type=%r is outside the B200 hot path (non_negative_cp, non_negative_cp_hals)" % tf_type)
+    else:
+        raise ValueError("Not a valid tf_type.")
+    if return_errors:
+        return cp_tf, errors
+    return cp_tf
+
+
+def _compute_elbow(loss, S=1.0, curve="convex", direction="decreasing", interp_method="interp1d"):
+    """x coordinate of the elbow of ``loss`` = [(x, y), ...] (factorization.py:146-183, kneed's KneeLocator)."""
+    x, y = zip(*loss)
+    return kneedle_elbow(x, y, S=S, curve=curve, direction=direction, interp_method=interp_method)
+
+
+def _loss_of(tensor, tl_object, errors, mask):
+    if mask is None:
+        return np.float64(errors[-1])
+    return _compute_norm_error(tensor, tl_object, mask)
+
+
+def _run_elbow_analysis(tensor, upper_rank=50, tf_type="non_negative_cp", init="svd", svd="truncated_svd",
+                        random_state=None, mask=None, n_iter_max=100, tol=10e-7, verbose=False, disable_pbar=False,
+                        **kwargs):
+    """One factorization per rank 1..upper_rank; list of (rank, loss) (factorization.py:186-269)."""
+    kwargs = dict(kwargs or {})
+    kwargs["return_errors"] = True
+    X = as_device_tensor(tensor)
+    M = as_device_mask(mask, X)
+    loss = []
+    for r in tqdm(range(1, upper_rank + 1), disable=disable_pbar):
+        tl_object, errors = _compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd,
+                                                          random_state=random_state, mask=M, n_iter_max=n_iter_max,
+                                                          tol=tol, verbose=verbose, **kwargs)
+        loss.append((r, _loss_of(X, tl_object, errors, M)))
+    return loss
+
+
+def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_negative_cp", init="svd",
+                                  svd="truncated_svd", metric="error", random_state=None, mask=None, n_iter_max=100,
+                                  tol=10e-7, verbose=False, **kwargs):
+    """``runs`` factorizations per rank; ndarray (runs x upper_rank) of losses (factorization.py:272-373).
+
+    The ``upper_rank * runs`` units are independent; when ``torch.distributed`` is initialised they are spread over the
+    ranks (one process per GPU, no data-path collective -- see ``cell2cell_b200.parallel``)."""
+    assert isinstance(runs, int), "runs must be an integer"
+    assert metric in ("similarity", "error"), "`metric` must be either 'similarity' or 'error'"
+    from ..parallel import run_units
+    kwargs = dict(kwargs or {})
+    kwargs["return_errors"] = True
+    X = as_device_tensor(tensor)
+    M = as_device_mask(mask, X)
+    units = [(r, run) for r in range(1, upper_rank + 1) for run in range(runs)]
+
+    def one(unit):
+        r, run = unit
+        seed = None if random_state is None else random_state + run
+        tl_object, errors = _compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=seed,
+                                                          mask=M, n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs)
+        if metric == "error":
+            return float(_loss_of(X, tl_object, errors, M))
+        return tl_object
+
+    if metric == "error":
+        vals = run_units(units, one, cost=lambda u: u[0], gather="float")
+        all_loss = np.asarray(vals, dtype=np.float64).reshape(upper_rank, runs)
+    else:
+        from .metrics import pairwise_correlation_index
+        from scipy.spatial.distance import squareform
+        objs = run_units(units, one, cost=lambda u: u[0], gather="object")
+        rows = []
+        for i in range(upper_rank):
+            fs = [objs[i * runs + j].factors for j in range(runs)]
+            rows.append((1.0 - squareform(pairwise_correlation_index(fs))).tolist())
+        all_loss = np.asarray(rows, dtype=np.float64)
+    return all_loss.T
+
+
+def _compute_norm_error(tensor, tl_object, mask=None):
+    """``||M*X - M*rec|| / ||M*X||`` (factorization.py:376-432) in one fused pass, without materialising ``rec``."""
+    X = as_device_tensor(tensor)
+    M = as_device_mask(mask, X)
+    weights, factors = tl_object
+    rank = int(np.asarray(factors[0]).shape[1])
+    fs = []
+    for i, f in enumerate(factors):
+        f = np.asarray(f, dtype=np.float64)
+        if i == 0 and weights is not None:
+            f = f * np.asarray(weights, dtype=np.float64)[None, :]
+        fs.append(engine.pack_factor(f.astype(np.float32), rank, X.device))
+    s = engine.recon_sums(X, M, fs, rank)
+    return np.float64(np.sqrt(s[1]) / np.sqrt(s[3]))
+
+
+def normalized_error(reference_tensor, reconstructed_tensor):
+    """``||ref - rec|| / ||ref||`` of two full tensors (factorization.py:435-458); plain device arithmetic."""
+    a = as_device_tensor(reference_tensor)
+    b = as_device_tensor(reconstructed_tensor, a.device)
+    return float(torch.linalg.vector_norm((a - b).double()) / torch.linalg.vector_norm(a.double()))
+
+
+def require_device():
+    """Raises unless a CUDA device and the native library are usable (no CPU fallback)."""
+    from .._lib import lib
+    lib()
+    return engine.require_cuda()
+
+
+_ = C2CError

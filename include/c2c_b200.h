@@ -1,0 +1,155 @@
+/* c2c_b200.h -- C ABI of libc2c_b200.so: the B200 (sm_100a) hot path of Tensor-cell2cell.
+ *
+ * The reference (earmingol/cell2cell v0.8.1) is pure Python and has no FFI of its own; the boundary this library
+ * replaces is the set of Python/tensorly calls named beside each entry point (file:line relative to the reference
+ * repository).  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its comment says "host"; buffers are caller-owned, nothing is retained
+ *     after return, the library allocates no persistent device memory: scratch comes in as (ws, ws_bytes), sized by the
+ *     matching *_workspace_bytes() query;
+ *   - tensors are C-ordered fp32; the mask is uint8 (1 = observed, 0 = missing); factor matrices are [I_n x ldr]
+ *     row-major fp32 with ldr = rank rounded up to a multiple of 4 and the padding columns zero;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, and unless stated otherwise the call
+ *     returns without synchronising;
+ *   - return value: 0 = OK, < 0 = argument error, > 0 = cudaError_t; c2c_last_error() describes the last failure of
+ *     the calling thread.  No entry point falls back to the CPU.
+ */
+#ifndef C2C_B200_H
+#define C2C_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2C_MAX_NDIM 8
+#define C2C_MAX_RANK 128
+
+/* communication scores: cell2cell/core/communication_scores.py:195-203 */
+#define C2C_SCORE_PRODUCT 0
+#define C2C_SCORE_MEAN 1
+#define C2C_SCORE_GMEAN 2
+/* complex aggregation: cell2cell/preprocessing/rnaseq.py:185-192; group aggregation: communication_scores.py:235-242 */
+#define C2C_AGG_MIN 0
+#define C2C_AGG_MEAN 1
+#define C2C_AGG_GMEAN 2
+#define C2C_AGG_SUM 3
+/* factorization algorithms: cell2cell/tensor/factorization.py:91-104 (MU) and :106-115 (HALS) */
+#define C2C_ALGO_MU 0
+#define C2C_ALGO_HALS 1
+/* tensorly cvg_criterion */
+#define C2C_CVG_ABS_REC_ERROR 0
+#define C2C_CVG_REC_ERROR 1
+
+int c2c_version(void);
+const char* c2c_last_error(void);
+/* kernels this library has enqueued so far in the process (graph replays count every kernel they run) */
+long long c2c_launch_count(void);
+
+/* ---- K1: context-wise ligand-receptor score build --------------------------------------------------------------
+ * Replaces add_complexes_to_expression (cell2cell/preprocessing/rnaseq.py:176-196), the generate_ccc_tensor loop
+ * (cell2cell/tensor/tensor.py:1195-1202), compute_ccc_matrix (cell2cell/core/communication_scores.py:195-203) and the
+ * mask / nan_to_num step (cell2cell/tensor/tensor.py:1141-1145).
+ *
+ * expr      all contexts' expression matrices, concatenated; context c is [G_c x expr_ld[c]] row-major at float offset
+ *           expr_off[c]
+ * cell_col  [C x K]: column of tensor cell type k in context c's matrix, or -1 when that context lacks it (-> NaN)
+ * For side A (ligand) and side B (receptor), per (context c, LR pair l), entry c*L + l:
+ *   count >= 1 : the partner is the aggregate (agg_kind) of rows sub_rows[first .. first+count) of context c
+ *                (count = 1: a plain gene; count > 1: a complex whose subunits are all present in the context)
+ *   count == 0 : partner absent from the context -> NaN -> X = 0, mask = 0
+ *   count == -1: complex with a subunit missing from the context -> a row of zeros (rnaseq.py:195)
+ * X         out [C, L, K, K] fp32 (NaN -> 0, +-inf -> +-FLT_MAX, as numpy.nan_to_num)
+ * mask      out [C, L, K, K] uint8, 1 where the score is not NaN; may be NULL (how='inner')
+ */
+int c2c_build_ccc(const float* expr, const int64_t* expr_off, const int32_t* expr_ld, const int32_t* cell_col,
+                  const int32_t* a_first, const int32_t* a_count, const int32_t* b_first, const int32_t* b_count,
+                  const int32_t* sub_rows, int C, int L, int K, int score_kind, int agg_kind,
+                  float* X, uint8_t* mask, void* stream);
+
+/* ---- K1b: aggregate LR pairs into groups ------------------------------------------------------------------------
+ * Replaces aggregate_ccc_tensor (cell2cell/tensor/tensor.py:1245-1252) -> aggregate_ccc_matrices
+ * (cell2cell/core/communication_scores.py:235-242).  X_in/mask_in are [C, L, E]; group g aggregates LR rows
+ * grp_rows[grp_off[g] .. grp_off[g+1]) ; outputs are [C, n_groups, E].  mask_in NULL = every entry valid.
+ * method: C2C_AGG_GMEAN (exp(mean(log x)): zero -> 0, NaN / negative -> NaN), C2C_AGG_SUM (nansum), C2C_AGG_MEAN (nanmean).
+ */
+int c2c_group_aggregate(const float* X_in, const uint8_t* mask_in, const int32_t* grp_off, const int32_t* grp_rows,
+                        int C, int L, int n_groups, int64_t E, int method, float* X_out, uint8_t* mask_out,
+                        void* stream);
+
+/* ---- workspace query for every factorization entry point below -------------------------------------------------- */
+size_t c2c_ncp_workspace_bytes(int ndim, const int64_t* shape /*host*/, int rank, int masked);
+
+/* ---- ||X||^2 (fp64 accumulation): tensorly tl.norm(tensor, 2) in non_negative_parafac ---------------------------- */
+int c2c_sumsq(const float* X, int64_t n, double* out /*device, 1 double*/, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K2: fused (masked) MTTKRP for one mode ---------------------------------------------------------------------
+ * Replaces tensorly unfolding_dot_khatri_rao + the masked imputation `tensor*mask + cp_to_tensor(.., mask=1-mask)`
+ * (mirrored in-repo at cell2cell/tensor/coupled_factorization.py:342-345).  One pass over X (+mask):
+ *   M[i, r] = sum_{idx: idx[mode] = i} Xh[idx] * prod_{k != mode} A_k[idx[k], r]
+ * A: host array of ndim device pointers.  M: [shape[mode] x ldr].
+ */
+int c2c_mttkrp(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+               const float* const* A /*host array*/, int ldr, int rank, int mode, float* M,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* The two streaming passes of K2 on their own (what c2c_mttkrp and c2c_ncp_run are built from):
+ *   plane contraction  T[p, r]    = sum_{s,v} Xh[p, s, v] * A_{N-2}[s, r] * A_{N-1}[v, r]        T: [P x ldr], P = prod of leading dims
+ *   fiber contraction  U[s, v, r] = sum_p     Xh[p, s, v] * prod_{k < N-2} A_k[i_k(p), r]        U: [I_{N-2} * I_{N-1} x ldr]
+ * T serves the MTTKRP of every leading mode, U that of the two trailing modes. */
+int c2c_plane_contract(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+                       const float* const* A /*host array*/, int ldr, int rank, float* T,
+                       void* ws, size_t ws_bytes, void* stream);
+int c2c_fiber_contract(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+                       const float* const* A /*host array*/, int ldr, int rank, float* U,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3: Gram / Hadamard ------------------------------------------------------------------------------------------
+ * G = prod_{k != skip_mode} A_k^T A_k  (fp32 [ldr x ldr]); rec_norm2 (device double, may be NULL) receives
+ * sum_{r,s} prod_{all k} (A_k^T A_k)[r,s] = cp_norm^2.  skip_mode = -1 skips nothing.
+ * Mirrors cell2cell/tensor/coupled_factorization.py:336-340 (accum) and tensorly cp_norm.
+ */
+int c2c_gram_hadamard(const float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
+                      int skip_mode, float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K4: multiplicative update  A <- A * max(M, eps) / max(A G, eps)  (coupled_factorization.py:346-348) ---------- */
+int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, float eps,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K5: HALS column sweeps (tensorly hals_nnls reached from cell2cell/tensor/factorization.py:106-115) ------------
+ * sweeps k = 0..R-1: A[:,k] <- max(A[:,k] + (M[:,k] - A G[:,k]) / G[k,k], 0); stops when the squared change of a sweep
+ * falls below tol * (first sweep's) or after min(max_sweeps, 2 + 0.5 * (1 + 2 I R / (R R + R))) sweeps. */
+int c2c_hals_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, int max_sweeps,
+                    float tol, void* stream);
+
+/* ---- K6: reconstruction error sums (cell2cell/tensor/factorization.py:408-431, 458; tensor.py:659-688) -------------
+ * out[0..4] (device doubles) = sum m (x - rec), sum m (x - rec)^2, sum m x, sum m x^2, sum m  with m = mask (1 if NULL). */
+int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+                   const float* const* A /*host array*/, int ldr, int rank, double* out,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K8: cp_normalize (cell2cell/tensor/tensor.py:327): unit-norm columns in place, norms multiplied into
+ * weights [rank] (device, fp32; input value = current weights, folded into factor 0 first). */
+int c2c_cp_normalize(float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
+                     float* weights, void* stream);
+
+/* ---- whole factorization (tensorly non_negative_parafac / non_negative_parafac_hals semantics) --------------------
+ * Factors A hold the initial values on entry (K7: host-seeded random or svd init is done by the caller) and the result
+ * on exit.  errors: device double[n_iter_max] (tensorly's rec_errors); state: device int[2] = {iterations done,
+ * converged flag}.  The convergence test runs on the device every iteration; the host polls the flag every
+ * `check_every` iterations (0 = never: run exactly n_iter_max iterations unless the device flag turns the remaining
+ * launches into no-ops).  Synchronises the stream before returning only when it polls.
+ * normX2: device double holding ||X||^2, or NULL to have it computed here.
+ */
+int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+                float* const* A /*host array*/, int ldr, int rank, int algo, int n_iter_max, double tol,
+                int cvg_criterion, const double* normX2, double* errors, int* state, int check_every,
+                void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2C_B200_H */

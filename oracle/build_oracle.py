@@ -13,6 +13,7 @@ reference on fresh random inputs.
 
 Each function cites the reference lines it follows.
 """
+import warnings
 from collections import Counter, OrderedDict
 
 import numpy as np
@@ -104,21 +105,21 @@ def score_matrix(v, w, communication_score):
 
 
 def aggregate_group(mats, method):
-    """``aggregate_ccc_matrices`` (communication_scores.py:206-244).  'gmean' is scipy.stats.mstats.gmean: a masked
-    geometric mean -- log of values <= 0 and of NaN is masked out, so zeros and missing entries are *skipped*; an
-    element with nothing left is masked and ``.tolist()`` turns it into ``None`` (-> NaN once stacked as float)."""
+    """``aggregate_ccc_matrices`` (communication_scores.py:206-244).  'gmean' is ``scipy.stats.mstats.gmean``; with the
+    scipy the reference runs on here (1.18.1, the version the golden fixtures were made with) that is a plain
+    ``exp(mean(log(x)))`` along axis 0: a zero in the group gives 0, a NaN or a negative value gives NaN (older scipy
+    releases masked such entries instead -- the fixtures pin the behaviour restated here).  'sum' / 'mean' are
+    ``np.nansum`` / ``np.nanmean`` (an all-NaN group sums to 0 and averages to NaN)."""
     mats = np.asarray(mats, dtype=float)
-    if method == "gmean":
-        from scipy.stats.mstats import gmean
-        return gmean(mats)
-    if method == "sum":
-        return np.nansum(mats, axis=0)
-    if method == "mean":
-        with np.errstate(invalid="ignore"):
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore", category=RuntimeWarning)
-                return np.nanmean(mats, axis=0)
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        if method == "gmean":
+            from scipy.stats.mstats import gmean   # same third-party call as the reference (its last bit depends on scipy's mean)
+            return np.asarray(gmean(mats))
+        if method == "sum":
+            return np.nansum(mats, axis=0)
+        if method == "mean":
+            return np.nanmean(mats, axis=0)
     raise ValueError("Not a valid method")
 
 

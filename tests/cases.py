@@ -23,7 +23,7 @@ def toy_ppi(prot_complex=True):
     return ppi.assign(score=1.0)
 
 
-def hard_case(seed, n_contexts=4, n_genes=14, n_cells=5, n_lr=24, dtype=np.float64):
+def hard_case(seed, n_contexts=4, n_genes=14, n_cells=5, n_lr=24, dtype=np.float64, fp32_values=False):
     """Mixed-case gene names, complexes on both sides (some with a subunit missing from some context or from the whole
     universe), a complex name used on both sides (the ``elif`` quirk), duplicated LR rows, contexts with different gene /
     cell sets and orders, real zeros, and a ``pathway`` column for grouping."""
@@ -40,6 +40,8 @@ def hard_case(seed, n_contexts=4, n_genes=14, n_cells=5, n_lr=24, dtype=np.float
         if c and rs.rand() < 0.5:
             c_keep = list(rs.permutation(c_keep))
         e = rs.gamma(0.7, 2.0, size=(len(g_keep), len(c_keep))) * (rs.rand(len(g_keep), len(c_keep)) > 0.25)
+        if fp32_values:                      # float64 frames holding fp32-representable values (GPU parity inputs)
+            e = e.astype(np.float32).astype(np.float64)
         mats.append(pd.DataFrame(e.astype(dtype), index=g_keep, columns=c_keep))
     def pick():
         r = rs.rand()

@@ -3,7 +3,7 @@
 
     python tests/golden/make_golden.py
 
-Outputs (committed): tests/golden/build_toy.npz, tests/golden/build_hard.npz.  The inputs are not stored: they are
+Outputs (committed): tests/golden/build_toy.npz, tests/golden/build_hard.npz, tests/golden/build_hard32.npz.  The inputs are not stored: they are
 regenerated from seeds by tests/cases.py, which this script shares with the tests.
 """
 import json
@@ -20,6 +20,7 @@ from oracle.ref_harness import load_reference  # noqa: E402
 from tests.cases import OPTION_GRID, hard_case, toy_ppi, toy_rnaseq  # noqa: E402
 
 HARD_SEEDS = (0, 1)
+HARD32_SEEDS = (2, 3)
 
 
 def run_reference(ref, mats, ppi, **kw):
@@ -63,6 +64,14 @@ def main():
                 res = run_reference(ref, mats, ppi, complex_sep="&", upper_letter_comparison=up, **opt)
                 pack(hard, "%d|%d|%d" % (seed, i, up), res)
     np.savez_compressed(os.path.join(HERE, "build_hard.npz"), **hard)
+    # fp32-representable inputs (float64 frames): what the GPU path is compared with after rounding to fp32
+    hard32 = {}
+    for seed in HARD32_SEEDS:
+        mats, ppi = hard_case(seed, fp32_values=True)
+        for i, opt in enumerate(OPTION_GRID):
+            res = run_reference(ref, mats, ppi, complex_sep="&", **opt)
+            pack(hard32, "%d|%d|1" % (seed, i), res)
+    np.savez_compressed(os.path.join(HERE, "build_hard32.npz"), **hard32)
     print("toy cases:", len([k for k in toy if k.endswith("/tensor")]),
           "hard cases:", len([k for k in hard if k.endswith("/tensor")]))
 

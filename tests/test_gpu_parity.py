@@ -1,0 +1,480 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through the C ABI (ctypes -> libc2c_b200.so),
+against the oracles on identical seeded inputs and against the reference-made golden fixtures.
+
+Tolerances (BASELINE.json north_star): tensor build -- mask / names / ordering bit-exact, scores within 1 ulp fp32 of the
+fp32-rounded reference value; factorization -- factors and final reconstruction error within 1e-4 relative after a fixed
+iteration count from identical initial factors.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import ncp_oracle as o                                   # noqa: E402
+from oracle.build_oracle import interaction_tensor_oracle            # noqa: E402
+from tests.cases import OPTION_GRID, hard_case, toy_ppi, toy_rnaseq  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+FACTOR_RTOL = 1e-4
+ERROR_RTOL = 1e-4
+
+
+def ulp_distance(a32, b32):
+    """Units in the last place between two fp32 arrays of equal sign (scores are >= 0 or both -/+)."""
+    a = np.ascontiguousarray(a32, dtype=np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b32, dtype=np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def lowrank(shape, rank, seed=0, noise=0.05):
+    rs = np.random.RandomState(seed)
+    fs = [rs.gamma(1.0, 1.0, size=(s, rank)) for s in shape]
+    x = o.cp_to_tensor(None, fs)
+    x = x / x.mean() + noise * rs.random_sample(x.shape)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K1 / K1b: tensor build
+# ----------------------------------------------------------------------------------------------------------------------
+def _check_build(t, ref_tensor, ref_mask, ref_names, ref_genes, max_ulp=1):
+    from cell2cell_b200.tensor import InteractionTensor  # noqa: F401
+    X = t.tensor.cpu().numpy()
+    assert X.dtype == np.float32 and X.shape == ref_tensor.shape
+    want = np.asarray(ref_tensor, dtype=np.float64)
+    want32 = np.clip(want, -np.finfo(np.float32).max, np.finfo(np.float32).max).astype(np.float32)
+    d = ulp_distance(X, want32)
+    assert d.max() <= max_ulp, "max ulp distance %d" % d.max()
+    if ref_mask is None:
+        assert t.mask is None
+    else:
+        np.testing.assert_array_equal(t.mask.cpu().numpy(), np.asarray(ref_mask).astype(np.uint8))
+    assert [list(x) for x in t.order_names] == [list(x) for x in ref_names]
+    assert list(t.genes) == list(ref_genes)
+    return float((d == 0).mean())
+
+
+def test_build_toy_golden_bit_exact():
+    """Integer-valued toy data (cell2cell/datasets/toy_data.py): every score is exactly representable -> 0 ulp allowed
+    for product / mean, 1 ulp for gmean."""
+    from cell2cell_b200.tensor import InteractionTensor
+    store = np.load(os.path.join(GOLD, "build_toy.npz"))
+    for score in ("expression_product", "expression_mean", "expression_gmean"):
+        for cplx in (True, False):
+            key = "%s|%d" % (score, cplx)
+            t = InteractionTensor([toy_rnaseq()], toy_ppi(cplx), communication_score=score,
+                                  complex_sep="&" if cplx else None, verbose=False)
+            names = json.loads(str(store[key + "/names"]))
+            _check_build(t, store[key + "/tensor"], None, names, json.loads(str(store[key + "/genes"])),
+                         max_ulp=1 if score == "expression_gmean" else 0)
+            np.testing.assert_array_equal(t.loc_zeros.cpu().numpy(), store[key + "/loc_zeros"])
+    a = toy_rnaseq()
+    b = toy_rnaseq().drop(columns=["C2"]).drop(index=["Protein-D"]) * 2
+    for how in ("inner", "outer", "outer_genes", "outer_cells"):
+        key = "two|" + how
+        t = InteractionTensor([a, b], toy_ppi(True), communication_score="expression_gmean", complex_sep="&", how=how,
+                              verbose=False)
+        mask = store[key + "/mask"] if bool(store[key + "/has_mask"]) else None
+        _check_build(t, store[key + "/tensor"], mask, json.loads(str(store[key + "/names"])),
+                     json.loads(str(store[key + "/genes"])))
+        np.testing.assert_array_equal(t.loc_zeros.cpu().numpy(), store[key + "/loc_zeros"])
+
+
+@pytest.mark.parametrize("seed", [2, 3])
+def test_build_hard_golden_all_options(seed):
+    """Every how x score x complex aggregation x grouping option on the quirk-laden seeded case, fp32-representable
+    inputs, against the reference's own outputs (tests/golden/build_hard32.npz)."""
+    from cell2cell_b200.tensor import InteractionTensor
+    store = np.load(os.path.join(GOLD, "build_hard32.npz"))
+    mats, ppi = hard_case(seed, fp32_values=True)
+    exact = []
+    for i, opt in enumerate(OPTION_GRID):
+        key = "%d|%d|1" % (seed, i)
+        t = InteractionTensor([m.copy() for m in mats], ppi.copy(), complex_sep="&", verbose=False, **opt)
+        mask = store[key + "/mask"] if bool(store[key + "/has_mask"]) else None
+        # grouped scores aggregate fp32-rounded members (<= 1 ulp each) -> 2 ulp on the aggregate
+        exact.append(_check_build(t, store[key + "/tensor"], mask, json.loads(str(store[key + "/names"])),
+                                  json.loads(str(store[key + "/genes"])), max_ulp=1 if opt["group_ppi_by"] is None else 2))
+        np.testing.assert_array_equal(t.loc_zeros.cpu().numpy(), store[key + "/loc_zeros"])
+    assert np.mean(exact) > 0.9
+
+
+def test_build_matches_oracle_on_synthetic_config_shape():
+    """BASELINE config 3 shape family (how='outer', complexes, gmean score), L scaled down so the pandas oracle is fast."""
+    from cell2cell_b200.synthetic import synthetic_case
+    from cell2cell_b200.tensor import InteractionTensor
+    mats, ppi, kw = synthetic_case("asd", scale=0.03)
+    mats64 = [m.astype(np.float64) for m in mats]
+    ref = interaction_tensor_oracle(mats64, ppi, **{k: v for k, v in kw.items() if k != "verbose"})
+    t = InteractionTensor(mats, ppi, **kw)
+    _check_build(t, ref["tensor"], ref["mask"], ref["order_names"], ref["genes"])
+    assert abs(t.excluded_value_fraction() - (1 - ref["mask"].mean())) < 1e-12
+    assert abs(t.sparsity_fraction() - ref["loc_zeros"].mean()) < 1e-12
+    assert abs(t.missing_fraction() - ref["loc_nans"].mean()) < 1e-12
+
+
+def test_build_edge_cases():
+    import pandas as pd
+    from cell2cell_b200.tensor import InteractionTensor, build_context_ccc_tensor
+    a = toy_rnaseq().astype(float)
+    # no LR pair survives the filter -> empty LR mode
+    ppi = pd.DataFrame({"A": ["X1"], "B": ["X2"]})
+    t = InteractionTensor([a], ppi, verbose=False)
+    assert t.tensor.shape == (1, 0, 5, 5)
+    # NaN and inf already in the input: mask 0 / FLT_MAX (numpy.nan_to_num semantics in fp32)
+    b = a.copy()
+    b.iloc[0, 0] = np.nan
+    b.iloc[1, 1] = np.inf
+    # direct build_context_ccc_tensor upper-cases the PPI names only (reference quirk Q3): the lookup of the upper-cased
+    # partner in the original-case index raises KeyError, as the reference's .loc does
+    with pytest.raises(KeyError):
+        build_context_ccc_tensor([a, b], toy_ppi(False), how="outer", communication_score="expression_product")
+    ref = interaction_tensor_oracle([a, b], toy_ppi(False), how="outer", communication_score="expression_product",
+                                    upper_letter_comparison=True)
+    up = [m.rename(index=str.upper) for m in (a, b)]
+    X, genes, cells, names, mask = build_context_ccc_tensor(up, toy_ppi(False), how="outer",
+                                                            communication_score="expression_product")
+    np.testing.assert_array_equal(mask.cpu().numpy(), ref["mask"].astype(np.uint8))
+    got = X.cpu().numpy()
+    want = ref["tensor"]
+    big = want > 1e300
+    assert (got[big] == np.finfo(np.float32).max).all()
+    np.testing.assert_array_equal(got[~big], want[~big].astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K2..K8 one at a time
+# ----------------------------------------------------------------------------------------------------------------------
+SHAPES = [(4, 30, 6, 6), (3, 5, 7, 9), (5, 11, 17, 17), (2, 3, 4, 8, 4), (10, 6, 8), (3, 40, 40, 40)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("rank", [1, 4, 10, 25, 40])
+@pytest.mark.parametrize("masked", [False, True])
+def test_mttkrp_every_mode(shape, rank, masked):
+    from cell2cell_b200 import engine
+    rs = np.random.RandomState(len(shape) * 100 + rank)
+    x = lowrank(shape, 3, seed=rank)
+    fs = [rs.random_sample((s, rank)) for s in shape]
+    mask = (rs.rand(*shape) > 0.2).astype(np.uint8) if masked else None
+    X = torch.as_tensor(x).cuda()
+    Mk = torch.as_tensor(mask).cuda() if masked else None
+    dfs = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in fs]
+    f32 = [f.astype(np.float32).astype(np.float64) for f in fs]
+    xh = x.astype(np.float64)
+    if masked:
+        xh = xh * mask + o.cp_to_tensor(None, f32) * (1 - mask)
+    for mode in range(len(shape)):
+        got = engine.unpack_factor(engine.mttkrp(X, Mk, dfs, rank, mode), rank).cpu().numpy()
+        want = o.mttkrp(xh, None, f32, mode)
+        assert rel_err(got, want) < 2e-6, (mode, rel_err(got, want))
+
+
+def test_small_steps_match_numpy():
+    from cell2cell_b200 import engine
+    rs = np.random.RandomState(0)
+    shape, rank = (7, 33, 5, 6), 6
+    fs = [rs.random_sample((s, rank)) for s in shape]
+    dfs = [engine.pack_factor(f.astype(np.float32), rank, "cuda") for f in fs]
+    f32 = [f.astype(np.float32).astype(np.float64) for f in fs]
+    for skip in (-1, 0, 2):
+        G, n2 = engine.gram_hadamard(dfs, shape, rank, skip)
+        want = np.ones((rank, rank))
+        for k, f in enumerate(f32):
+            if k != skip:
+                want = want * (f.T @ f)
+        assert rel_err(G[:rank, :rank].cpu().numpy(), want) < 1e-6
+        assert abs(n2 - o.cp_norm(None, f32) ** 2) / n2 < 1e-12
+    # MU and HALS single updates
+    M = rs.random_sample((33, rank)) * 5
+    G = (f32[0].T @ f32[0]) * (f32[2].T @ f32[2]) * (f32[3].T @ f32[3])
+    dM = engine.pack_factor(M.astype(np.float32), rank, "cuda")
+    dG = engine.pack_factor(G.astype(np.float32), rank, "cuda")
+    eps = np.finfo(np.float32).eps
+    A = dfs[1].clone()
+    engine.mu_update(A, dM, dG, rank)
+    M32, G32 = M.astype(np.float32).astype(np.float64), G.astype(np.float32).astype(np.float64)
+    want = f32[1] * np.clip(M32, eps, None) / np.clip(f32[1] @ G32, eps, None)
+    assert rel_err(A[:, :rank].cpu().numpy(), want) < 1e-6
+    A = dfs[1].clone()
+    engine.hals_update(A, dM, dG, rank)
+    want = o.hals_nnls(M32.T, G32, f32[1].T, n_iter_max=100).T
+    assert rel_err(A[:, :rank].cpu().numpy(), want) < 1e-5
+    # cp_normalize
+    w = engine.cp_normalize(dfs, rank)
+    wr, nf = o.cp_normalize(None, f32)
+    assert rel_err(w.cpu().numpy(), wr) < 1e-6
+    for a, b in zip(dfs, nf):
+        assert rel_err(a[:, :rank].cpu().numpy(), b) < 1e-6
+
+
+@pytest.mark.parametrize("shape,rank", [((4, 30, 6, 6), 4), ((5, 11, 17, 17), 10), ((2, 3, 4, 8, 4), 3), ((6, 9, 8, 12), 40)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_recon_sums_and_sumsq(shape, rank, masked):
+    from cell2cell_b200 import engine
+    rs = np.random.RandomState(3)
+    x = lowrank(shape, 3, seed=5)
+    fs = [rs.random_sample((s, rank)) for s in shape]
+    mask = (rs.rand(*shape) > 0.3).astype(np.uint8) if masked else None
+    X = torch.as_tensor(x).cuda()
+    Mk = torch.as_tensor(mask).cuda() if masked else None
+    dfs = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in fs]
+    f32 = [f.astype(np.float32).astype(np.float64) for f in fs]
+    rec = o.cp_to_tensor(None, f32)
+    m = np.ones(shape) if mask is None else mask.astype(np.float64)
+    d = (x.astype(np.float64) - rec) * m
+    want = np.array([d.sum(), (d * d).sum(), (x * m).sum(), (x.astype(np.float64) ** 2 * m).sum(), m.sum()])
+    got = engine.recon_sums(X, Mk, dfs, rank)
+    np.testing.assert_allclose(got, want, rtol=2e-5)
+    assert abs(engine.sumsq(X) - float((x.astype(np.float64) ** 2).sum())) / want[3] < 1e-12 or masked
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# whole factorization against the oracle, identical initial factors, fixed iteration count
+# ----------------------------------------------------------------------------------------------------------------------
+def _compare_run(x, rank, n_iter, mask=None, hals=False, seed=888, init="random"):
+    from cell2cell_b200.tensor.factorization import non_negative_parafac, non_negative_parafac_hals, _compute_norm_error
+    x64 = x.astype(np.float64)
+    if hals:
+        ref, ref_err = o.non_negative_parafac_hals(x64, rank, n_iter_max=n_iter, init=init, tol=-1.0, random_state=seed)
+        got, got_err = non_negative_parafac_hals(x, rank, n_iter_max=n_iter, init=init, tol=-1.0, random_state=seed,
+                                                 return_errors=True)
+    else:
+        m64 = None if mask is None else mask.astype(np.float64)
+        ref, ref_err = o.non_negative_parafac(x64, rank, n_iter_max=n_iter, init=init, tol=-1.0, random_state=seed, mask=m64)
+        got, got_err = non_negative_parafac(x, rank, n_iter_max=n_iter, init=init, tol=-1.0, random_state=seed,
+                                            mask=mask, return_errors=True)
+    assert len(got_err) == len(ref_err) == n_iter
+    for a, b in zip(got.factors, ref.factors):
+        assert a.shape == b.shape and (a >= 0).all()
+        assert rel_err(a, b) < FACTOR_RTOL, rel_err(a, b)
+    assert abs(got_err[-1] - ref_err[-1]) <= ERROR_RTOL * abs(ref_err[-1])
+    # per-iteration errors come from the Gram form sqrt(|nx2 + rn2 - 2 ip|), which cancels in fp32 when the error is small
+    np.testing.assert_allclose(np.asarray(got_err), np.asarray(ref_err), rtol=ERROR_RTOL, atol=3e-6)
+    if mask is not None:
+        e_ref = o.masked_norm_error(x64, ref, mask.astype(np.float64))
+        e_got = _compute_norm_error(x, got, mask)
+        assert abs(e_got - e_ref) <= ERROR_RTOL * e_ref
+    return got, got_err
+
+
+def test_ncp_config1_toy_rank4():
+    """BASELINE config 1: 4 x 300 x 6 x 6, rank 4, random init, full size, 100 iterations."""
+    _compare_run(lowrank((4, 300, 6, 6), 5, seed=1), 4, 100)
+
+
+def test_ncp_config2_balf_rank10():
+    """BASELINE config 2: 12 x 1054 x 6 x 6, rank 10, full size, 100 iterations."""
+    _compare_run(lowrank((12, 1054, 6, 6), 5, seed=2), 10, 100)
+
+
+def test_ncp_config3_asd_masked_rank10():
+    """BASELINE config 3 family: 13 x L x 17 x 17 masked (L scaled to 150 for the numpy oracle), rank 10, 60 iterations."""
+    shape = (13, 150, 17, 17)
+    x = lowrank(shape, 5, seed=3)
+    rs = np.random.RandomState(4)
+    mask = np.ones(shape, dtype=np.uint8)
+    mask[2::3, :, 5, :] = 0          # a cell type missing from every 3rd context (sender rows and receiver columns)
+    mask[2::3, :, :, 5] = 0
+    mask[rs.rand(13, 150) < 0.05] = 0  # gene pairs missing from a context: whole planes
+    mask[rs.rand(*shape) < 0.02] = 0   # and arbitrary user-masked entries
+    _compare_run(x * mask, 10, 60, mask=mask)
+
+
+def test_ncp_config4_shape_family_rank20():
+    """BASELINE config 4 family (K = 40 planes, rank 20), C and L scaled down for the oracle."""
+    _compare_run(lowrank((6, 50, 40, 40), 6, seed=5), 20, 40)
+
+
+@pytest.mark.parametrize("shape,rank", [((3, 5, 7, 9), 3), ((10, 6, 8), 2), ((2, 3, 4, 8, 4), 5), ((4, 12, 6, 6), 40),
+                                        ((5, 7, 3, 3), 1)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_ncp_odd_shapes(shape, rank, masked):
+    x = lowrank(shape, 3, seed=7)
+    mask = None
+    if masked:
+        mask = (np.random.RandomState(8).rand(*shape) > 0.15).astype(np.uint8)
+        x = x * mask
+    _compare_run(x, rank, 30, mask=mask)
+
+
+@pytest.mark.parametrize("shape,rank", [((4, 60, 6, 6), 4), ((5, 20, 17, 17), 10), ((10, 6, 8), 3)])
+def test_hals_parity(shape, rank):
+    _compare_run(lowrank(shape, 4, seed=9), rank, 25, hals=True)
+
+
+def test_tol_stop_matches_oracle_iteration_count():
+    x = lowrank((6, 40, 6, 6), 3, seed=11)
+    from cell2cell_b200.tensor.factorization import non_negative_parafac
+    ref, ref_err = o.non_negative_parafac(x.astype(np.float64), 3, n_iter_max=500, init="random", tol=1e-5, random_state=1)
+    got, got_err = non_negative_parafac(x, 3, n_iter_max=500, init="random", tol=1e-5, random_state=1, return_errors=True)
+    # the stop rule compares successive fp32-derived errors with tol: the count may move by a few iterations
+    assert abs(len(got_err) - len(ref_err)) <= 0.15 * len(ref_err)
+    assert abs(got_err[-2] - got_err[-1]) < 1e-5
+    # ... and the error is still falling by ~tol per iteration when the rule fires
+    assert abs(got_err[-1] - ref_err[-1]) < 1e-4 * ref_err[-1] + 1e-5 * (abs(len(got_err) - len(ref_err)) + 1)
+
+
+def test_svd_init_statistically_equivalent():
+    """svd init depends on LAPACK sign / ordering conventions: compare the reached error, not the factors."""
+    x = lowrank((6, 40, 8, 8), 3, seed=13, noise=0.02)
+    from cell2cell_b200.tensor.factorization import non_negative_parafac
+    ref, ref_err = o.non_negative_parafac(x.astype(np.float64), 3, n_iter_max=60, init="svd", tol=-1.0)
+    got, got_err = non_negative_parafac(x, 3, n_iter_max=60, init="svd", tol=-1.0, return_errors=True)
+    assert abs(got_err[-1] - ref_err[-1]) < 0.05 * ref_err[-1] + 1e-3
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the public API end to end
+# ----------------------------------------------------------------------------------------------------------------------
+def test_api_interaction_tensor_to_factor_dataframes():
+    from cell2cell_b200.synthetic import synthetic_case
+    from cell2cell_b200.tensor import InteractionTensor
+    mats, ppi, kw = synthetic_case("toy", scale=0.2)
+    t = InteractionTensor(mats, ppi, **kw)
+    t.compute_tensor_factorization(rank=4, init="random", random_state=888, n_iter_max=50, tol=-1.0)
+    ref_in = interaction_tensor_oracle([m.astype(np.float64) for m in mats], ppi, **{k: v for k, v in kw.items() if k != "verbose"})
+    x64 = ref_in["tensor"].astype(np.float32).astype(np.float64)
+    cp, errs = o.non_negative_parafac(x64, 4, n_iter_max=50, init="random", tol=-1.0, random_state=888)
+    w, nf = o.cp_normalize(cp.weights, cp.factors)
+    order = np.argsort(w)[::-1]
+    assert list(t.factors.keys()) == ["Contexts", "Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
+    for (label, df), f, names in zip(t.factors.items(), nf, ref_in["order_names"]):
+        assert list(df.index) == list(names) and list(df.columns) == ["Factor %d" % i for i in range(1, 5)]
+        assert rel_err(df.values, f[:, order]) < FACTOR_RTOL
+    np.testing.assert_allclose(t.explained_variance_ratio_, w[order] / w.sum(), rtol=1e-4)
+    rec = cp.to_tensor()
+    d = x64 - rec
+    ev = 1 - np.linalg.norm(d - d.mean()) / np.linalg.norm(x64 - x64.mean())
+    assert abs(t.explained_variance_ - ev) < 1e-4
+    assert t.rank == 4
+    # best-of-runs picks the lowest error and is reproducible
+    t.compute_tensor_factorization(rank=3, init="random", random_state=0, runs=3, n_iter_max=20, tol=-1.0)
+    errs = [o.non_negative_parafac(x64, 3, n_iter_max=20, init="random", tol=-1.0, random_state=s)[1][-1] for s in range(3)]
+    best = int(np.argmin(errs))
+    cp = o.non_negative_parafac(x64, 3, n_iter_max=20, init="random", tol=-1.0, random_state=best)[0]
+    for a, b in zip(t.tl_object.factors, cp.factors):
+        assert rel_err(a, b) < FACTOR_RTOL
+
+
+def test_api_elbow_matches_oracle_losses():
+    from cell2cell_b200.tensor import PreBuiltTensor
+    shape = (5, 40, 6, 6)
+    x = lowrank(shape, 4, seed=21, noise=0.1)
+    names = [["n%d_%d" % (k, i) for i in range(s)] for k, s in enumerate(shape)]
+    t = PreBuiltTensor(x, order_names=names)
+    fig, loss = t.elbow_rank_selection(upper_rank=6, runs=2, init="random", random_state=5, n_iter_max=30, tol=-1.0,
+                                       output_fig=False)
+    assert fig is None and t.elbow_metric_raw.shape == (2, 6)
+    want = np.array([[o.non_negative_parafac(x.astype(np.float64), r, n_iter_max=30, init="random", tol=-1.0,
+                                             random_state=5 + run)[1][-1] for r in range(1, 7)] for run in range(2)])
+    np.testing.assert_allclose(t.elbow_metric_raw, want, rtol=ERROR_RTOL)
+    assert [l[0] for l in loss] == list(range(1, 7)) and isinstance(t.rank, int)
+    # runs == 1 path, masked: loss is the masked normalized error (factorization.py:263-267)
+    mask = (np.random.RandomState(1).rand(*shape) > 0.1).astype(np.uint8)
+    t2 = PreBuiltTensor(x * mask, order_names=names, mask=mask)
+    fig, loss = t2.elbow_rank_selection(upper_rank=3, runs=1, init="random", random_state=2, n_iter_max=20, tol=-1.0,
+                                        output_fig=False, automatic_elbow=False, manual_elbow=2)
+    for r, l in loss:
+        cp = o.non_negative_parafac((x * mask).astype(np.float64), r, n_iter_max=20, init="random", tol=-1.0,
+                                    random_state=2, mask=mask.astype(np.float64))[0]
+        assert abs(l - o.masked_norm_error((x * mask).astype(np.float64), cp, mask.astype(np.float64))) < ERROR_RTOL * l
+    assert t2.rank == 2 and t2.explained_variance_ is None
+    # similarity metric
+    fig, loss = t.elbow_rank_selection(upper_rank=3, runs=3, metric="similarity", init="random", random_state=5,
+                                       n_iter_max=30, tol=-1.0, output_fig=False, automatic_elbow=False, manual_elbow=2)
+    assert t.elbow_metric_raw.shape == (3, 3)
+
+
+def test_prebuilt_tensor_nan_handling_and_pickle(tmp_path):
+    import pickle
+    from cell2cell_b200.tensor import PreBuiltTensor
+    x = lowrank((3, 6, 4, 4), 2, seed=1).astype(np.float64)
+    x[0, 0, 0, 0] = np.nan
+    x[1, 1, 1, 1] = 0.0
+    names = [["n%d_%d" % (k, i) for i in range(s)] for k, s in enumerate(x.shape)]
+    t = PreBuiltTensor(x, order_names=names)
+    assert t.loc_nans.sum().item() == 1 and t.loc_zeros.sum().item() == 1 and t.tensor[0, 0, 0, 0].item() == 0.0
+    assert t.order_labels == ["Dimension-1", "Dimension-2", "Dimension-3", "Dimension-4"]
+    t.compute_tensor_factorization(rank=2, init="random", random_state=0, n_iter_max=10)
+    p = tmp_path / "t.pkl"
+    t.write_file(str(p))
+    t2 = pickle.load(open(p, "rb"))
+    assert t2.tensor.is_cuda and torch.equal(t2.tensor, t.tensor) and list(t2.factors) == list(t.factors)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE full sizes: size-independent properties (the numpy oracle would take minutes per iteration here)
+# ----------------------------------------------------------------------------------------------------------------------
+def _device_lowrank(shape, rank, seed, noise):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    fs = [torch.rand((s, rank), generator=g, device="cuda") + 0.1 for s in shape]
+    x = torch.einsum("ar,br,cr,dr->abcd", *fs)
+    if noise:
+        x += noise * x.mean() * torch.rand(x.shape, generator=g, device="cuda")
+    return x.contiguous(), fs
+
+
+@pytest.mark.parametrize("shape,rank", [((60, 2000, 40, 40), 10), ((12, 1054, 6, 6), 10), ((13, 1900, 17, 17), 10)])
+def test_full_size_properties(shape, rank):
+    from cell2cell_b200 import engine
+    X, fs = _device_lowrank(shape, rank, 1, 0.0)
+    # (1) exact low-rank tensor + true factors: a fixed point of the multiplicative update, error ~ 0
+    dfs = [engine.pack_factor(f, rank, X.device) for f in fs]
+    errs, n_it, conv = engine.ncp_run(X, None, dfs, rank, n_iter_max=3, tol=-1.0)
+    assert n_it == 3 and errs[-1] < 5e-3
+    for a, b in zip(dfs, fs):
+        assert float((a[:, :rank] - b).norm() / b.norm()) < 1e-4
+    # (2) MTTKRP is linear in X and matches einsum on a mode
+    M1 = engine.mttkrp(X, None, dfs, rank, 1)
+    M2 = engine.mttkrp(X * 2.0, None, dfs, rank, 1)
+    assert float((M2 - 2 * M1).norm() / M1.norm()) < 1e-6
+    want = torch.einsum("abcd,ar,cr,dr->br", X.double(), dfs[0][:, :rank].double(), dfs[2][:, :rank].double(),
+                        dfs[3][:, :rank].double())
+    assert float((M1[:, :rank].double() - want).norm() / want.norm()) < 2e-6
+    # (3) noisy tensor, random start: error sequence monotone non-increasing, Gram-form error == direct masked-sum error
+    X, _ = _device_lowrank(shape, 5, 2, 0.2)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dfs = [engine.pack_factor(torch.rand((s, rank), generator=g, device="cuda"), rank, X.device) for s in shape]
+    errs, n_it, conv = engine.ncp_run(X, None, dfs, rank, n_iter_max=12, tol=-1.0)
+    assert all(errs[i + 1] <= errs[i] * (1 + 1e-6) for i in range(len(errs) - 1))
+    s = engine.recon_sums(X, None, dfs, rank)
+    direct = np.sqrt(s[1]) / np.sqrt(s[3])
+    assert abs(direct - errs[-1]) < 1e-4 * direct
+    assert all(bool((f >= 0).all()) for f in dfs)
+    # (4) masked path with an all-ones mask reproduces the unmasked run
+    ones = torch.ones(shape, dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dfs2 = [engine.pack_factor(torch.rand((s, rank), generator=g, device="cuda"), rank, X.device) for s in shape]
+    errs2, _, _ = engine.ncp_run(X, ones, dfs2, rank, n_iter_max=12, tol=-1.0)
+    np.testing.assert_allclose(errs2, errs, rtol=1e-5)
+
+
+def test_full_size_build_roundtrip():
+    """Config 4 size build (60 x 2000 x 40 x 40): sampled planes against a numpy recomputation, mask all ones under 'outer'
+    when nothing is missing, checksum stable across two builds."""
+    from cell2cell_b200.synthetic import synthetic_contexts, synthetic_ppi
+    from cell2cell_b200.tensor import InteractionTensor
+    L, K, C = 2000, 40, 60
+    ppi = synthetic_ppi(L, 2 * L)
+    mats = synthetic_contexts(C, 2 * L, K)
+    t = InteractionTensor(mats, ppi, how="outer", communication_score="expression_gmean", complex_sep="&", verbose=False)
+    assert t.tensor.shape == (C, L, K, K) and bool((t.mask == 1).all())
+    rs = np.random.RandomState(0)
+    for _ in range(20):
+        c, l = rs.randint(C), rs.randint(L)
+        a, b = ppi["A"][l], ppi["B"][l]
+        v = mats[c].loc[a].values.astype(np.float64)
+        w = np.min([mats[c].loc[p].values for p in b.split("&")], axis=0).astype(np.float64)
+        want = np.sqrt(v[:, None] * w[None, :]).astype(np.float32)
+        assert ulp_distance(t.tensor[c, l].cpu().numpy(), want).max() <= 1
+    t2 = InteractionTensor(mats, ppi, how="inner", communication_score="expression_gmean", complex_sep="&", verbose=False)
+    assert t2.mask is None and torch.equal(t.tensor, t2.tensor)

@@ -1,0 +1,83 @@
+"""Self-consistency of the NCP oracle (oracle/ncp_oracle.py).  The arithmetic it restates lives in tensorly (not
+installable here; the reference holds no golden vectors for it -- parity unpinned, see the oracle's header), so these are
+the properties the algorithm must have, plus an independent einsum restatement of the same update."""
+import numpy as np
+import pytest
+
+from oracle import ncp_oracle as o
+
+
+def lowrank(shape, rank, seed=0, noise=0.0):
+    rs = np.random.RandomState(seed)
+    fs = [rs.gamma(1.0, 1.0, size=(s, rank)) for s in shape]
+    x = o.cp_to_tensor(None, fs)
+    if noise:
+        x = x + noise * rs.random_sample(x.shape)
+    return x, fs
+
+
+def test_mttkrp_equals_einsum():
+    x, fs = lowrank((4, 7, 3, 5), 3, noise=0.1)
+    ref = [np.einsum("abcd,br,cr,dr->ar", x, fs[1], fs[2], fs[3]), np.einsum("abcd,ar,cr,dr->br", x, fs[0], fs[2], fs[3]),
+           np.einsum("abcd,ar,br,dr->cr", x, fs[0], fs[1], fs[3]), np.einsum("abcd,ar,br,cr->dr", x, fs[0], fs[1], fs[2])]
+    for m in range(4):
+        np.testing.assert_allclose(o.mttkrp(x, None, fs, m), ref[m], rtol=1e-12)
+
+
+def test_random_init_is_numpy_mt19937_stream():
+    fs = o.random_init((3, 4, 2), 2, random_state=5)
+    rs = np.random.RandomState(5)
+    for f, s in zip(fs, (3, 4, 2)):
+        np.testing.assert_array_equal(f, rs.random_sample((s, 2)))
+
+
+def test_mu_errors_monotone_and_match_direct_error():
+    x, _ = lowrank((5, 9, 4, 4), 3, noise=0.3)
+    cp, errs = o.non_negative_parafac(x, 3, n_iter_max=40, init="random", tol=-1.0, random_state=1)
+    assert len(errs) == 40
+    assert all(errs[i + 1] <= errs[i] + 1e-12 for i in range(len(errs) - 1))
+    assert all((f >= 0).all() for f in cp.factors)
+    direct = np.linalg.norm(x - cp.to_tensor()) / np.linalg.norm(x)
+    assert abs(direct - errs[-1]) < 1e-10
+
+
+def test_fixed_point_stays():
+    x, fs = lowrank((4, 6, 3, 3), 2)
+    cp, errs = o.non_negative_parafac(x, 2, n_iter_max=5, init=(np.ones(2), fs), tol=-1.0)
+    for a, b in zip(cp.factors, fs):
+        np.testing.assert_allclose(a, b, rtol=1e-9)
+    assert errs[-1] < 1e-7
+
+
+def test_tol_stops_early_and_masked_runs():
+    x, _ = lowrank((5, 8, 4, 4), 2, noise=0.05)
+    cp, errs = o.non_negative_parafac(x, 2, n_iter_max=500, init="random", tol=1e-6, random_state=0)
+    assert 2 <= len(errs) < 500 and abs(errs[-2] - errs[-1]) < 1e-6
+    rs = np.random.RandomState(3)
+    mask = (rs.rand(*x.shape) > 0.1).astype(float)
+    cp, errs = o.non_negative_parafac(x * mask, 2, n_iter_max=80, init="random", tol=-1.0, random_state=0, mask=mask)
+    assert o.masked_norm_error(x * mask, cp, mask) < 0.2
+
+
+def test_hals_decreases_and_nonneg():
+    x, _ = lowrank((5, 9, 4, 4), 3, noise=0.3)
+    cp, errs = o.non_negative_parafac_hals(x, 3, n_iter_max=20, init="random", tol=-1.0, random_state=2)
+    assert errs[-1] < errs[0]
+    assert all((f >= 0).all() for f in cp.factors)
+    direct = np.linalg.norm(x - cp.to_tensor()) / np.linalg.norm(x)
+    assert abs(direct - errs[-1]) < 1e-8
+
+
+def test_cp_normalize_roundtrip():
+    x, fs = lowrank((4, 6, 3, 3), 3)
+    w, nf = o.cp_normalize(None, fs)
+    for f in nf:
+        np.testing.assert_allclose(np.linalg.norm(f, axis=0), 1.0, rtol=1e-12)
+    np.testing.assert_allclose(o.cp_to_tensor(w, nf), x, rtol=1e-10)
+
+
+def test_svd_init_shapes_nonneg():
+    x, _ = lowrank((3, 8, 4, 4), 2, noise=0.1)
+    fs = o.initialize_cp(x, 5, init="svd", random_state=0)       # rank > I_0 -> random padding columns
+    assert [f.shape for f in fs] == [(3, 5), (8, 5), (4, 5), (4, 5)]
+    assert all((f >= 0).all() for f in fs)
