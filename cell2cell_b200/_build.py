@@ -30,7 +30,7 @@ def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _digest():
+def _digest(extra=()):
     h = hashlib.sha256()
     for f in sorted(os.listdir(CSRC)) + ["../../include/c2c_b200.h"]:
         p = os.path.join(CSRC, f)
@@ -38,17 +38,20 @@ def _digest():
             h.update(f.encode())
             with open(p, "rb") as fh:
                 h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra)).encode())
     return h.hexdigest()[:16]
 
 
-def build(force=False, verbose=False, jobs=None):
-    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library.  Returns its path."""
-    tag = _digest()
+def build(force=False, verbose=False, jobs=None, extra_flags=(), out_path=None):
+    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library.  Returns its path.
+    ``extra_flags`` / ``out_path`` build a tuning variant (e.g. ``-DC2C_PC_UNROLL=8``) beside the product library."""
+    extra_flags = list(extra_flags)
+    lib_path = out_path or LIB_PATH
+    tag = _digest(extra_flags)
     obj_dir = os.path.join(ROOT, "build", tag)
     stamp = os.path.join(obj_dir, "linked")
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
-        return LIB_PATH
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == tag + lib_path:
+        return lib_path
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
 
@@ -56,7 +59,7 @@ def build(force=False, verbose=False, jobs=None):
         obj = os.path.join(obj_dir, src[:-3] + ".o")
         if os.path.exists(obj) and not force:
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj + ".tmp"]
+        cmd = [nvcc] + NVCC_FLAGS + extra_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj + ".tmp"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if verbose:
             with open(obj[:-2] + ".ptxas.log", "w") as fh:
@@ -68,14 +71,14 @@ def build(force=False, verbose=False, jobs=None):
 
     with ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH + ".tmp"] + objs
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", lib_path + ".tmp"] + objs
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s" % res.stderr[-4000:])
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(lib_path + ".tmp", lib_path)
     with open(stamp, "w") as fh:
-        fh.write(tag)
-    return LIB_PATH
+        fh.write(tag + lib_path)
+    return lib_path
 
 
 if __name__ == "__main__":

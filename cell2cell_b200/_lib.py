@@ -9,7 +9,8 @@ import threading
 
 __all__ = ["lib", "check", "C2CError", "LIB_PATH", "SCORE", "AGG", "ALGO", "CVG", "MAX_RANK", "MAX_NDIM"]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libc2c_b200.so")
+# C2C_B200_LIB selects another build of the same library (kernel tuning variants); the default is the in-tree product build
+LIB_PATH = os.environ.get("C2C_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libc2c_b200.so")
 
 SCORE = {"expression_product": 0, "expression_mean": 1, "expression_gmean": 2}
 AGG = {"min": 0, "mean": 1, "gmean": 2, "sum": 3}

@@ -32,8 +32,15 @@ template <> __device__ __forceinline__ unsigned ld_m<4>(const uint8_t* p) { retu
 template <> __device__ __forceinline__ unsigned ld_m<2>(const uint8_t* p) { return __ldcs(reinterpret_cast<const unsigned short*>(p)); }
 template <> __device__ __forceinline__ unsigned ld_m<1>(const uint8_t* p) { return __ldcs(p); }
 
+#ifndef C2C_PC_THREADS
 #define C2C_PC_THREADS 256      // plane_contract / recon_sums block size
+#endif
+#ifndef C2C_PC_UNROLL
 #define C2C_PC_UNROLL 4         // rows of a plane loaded ahead per thread
+#endif
+#ifndef C2C_PC_MINB
+#define C2C_PC_MINB 1           // resident CTAs per SM the register allocation must allow
+#endif
 
 // --------------------------------------------------------------------------------------------------------------------
 // plane_contract: a group of G = min(I3/VEC, 32) lanes owns one plane; lane `lig` owns the VEC-wide column strips
@@ -43,7 +50,7 @@ template <> __device__ __forceinline__ unsigned ld_m<1>(const uint8_t* p) { retu
 // Shared memory: A2 duplicated [I2][4*NP2] + A3 [I3][2*NP2].
 // --------------------------------------------------------------------------------------------------------------------
 template <int VEC, int NP2, bool MASKED, bool SUMS>
-__global__ void __launch_bounds__(C2C_PC_THREADS)
+__global__ void __launch_bounds__(C2C_PC_THREADS, C2C_PC_MINB)
 plane_contract_kernel(const ContractArgs a)
 {
     if (run_done(a.done)) return;
@@ -237,13 +244,22 @@ plane_contract_kernel(const ContractArgs a)
 // written once to the partials buffer [gridDim.x * nslots][E][ldr]; fiber_reduce sums the partials in a fixed order
 // (deterministic, no atomics).
 // --------------------------------------------------------------------------------------------------------------------
+#ifndef C2C_FC_TILE
 #define C2C_FC_TILE 32          // planes per shared-memory tile of lead weights
+#endif
+#ifndef C2C_FC_UNROLL
 #define C2C_FC_UNROLL 4
-
-#define C2C_FC_MAXTHREADS(NP2) ((NP2) > 8 ? 256 : 512)
+#endif
+#ifndef C2C_FC_THREADS_LO
+#define C2C_FC_THREADS_LO 512   // block size for NP2 <= 8
+#endif
+#ifndef C2C_FC_MINB
+#define C2C_FC_MINB 1
+#endif
+#define C2C_FC_MAXTHREADS(NP2) ((NP2) > 8 ? 256 : C2C_FC_THREADS_LO)
 
 template <int VEC, int NP2, bool MASKED>
-__global__ void __launch_bounds__(C2C_FC_MAXTHREADS(NP2))
+__global__ void __launch_bounds__(C2C_FC_MAXTHREADS(NP2), C2C_FC_MINB)
 fiber_contract_kernel(const ContractArgs a, const int nvec, const int nvec_total, const int nslots,
                       const long long planes_per_cta)
 {
