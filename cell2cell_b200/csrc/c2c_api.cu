@@ -13,12 +13,14 @@
 // with the factors as they stand when mode n is updated -- with 2 reads of X per iteration instead of N * R.
 // Masked: the imputed entries follow the current factors, so T (resp. U) is recomputed before every mode: N passes.
 #include "c2c_contract.cuh"
+#include "c2c_stream.cuh"
 #include "c2c_small.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #define C2C_VERSION 100
@@ -73,7 +75,107 @@ struct Geo {
     int fc_block, fc_nvec, fc_nvec_total, fc_nslots, fc_gx, fc_gy; long long fc_ppc; long long fc_nparts;
     int np2;     // rank pairs per chunk
     int nchunk;  // rank chunks
+    // shared-memory-staged (bulk-copy) passes; *_ok = 0 -> the register-staged kernels do the whole pass
+    int ps_ok, ps_ns, ps_spw, ps_rs, ps_ring, ps_nwarps, ps_rp, ps_pitch, ps_grid; long long ps_nstage; size_t ps_smem;
+    int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
+    long long max_parts;
 };
+
+#define C2C_SMEM_BUDGET (200 * 1024)
+
+static long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+static bool use_stream()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("C2C_B200_NO_STREAM"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v != 0;
+}
+
+// launch geometry of plane_stream / fiber_stream (see c2c_stream.cuh); both need the whole rank in one chunk
+static void stream_geometry(Geo& g, int rank)
+{
+    g.ps_ok = g.fs_ok = 0;
+    g.max_parts = g.fc_nparts;
+    if (g.nchunk != 1 || !use_stream()) return;
+    const int nsm = sm_count();
+    const long long plane_bytes = g.E * 4;
+    const long long align_unit = 4 / gcd_ll(g.E, 4);                 // planes per stage must keep stages 16-byte sized
+    {   // ---- plane_stream ----
+        const int vec = g.vec_plane;
+        const int ns = (vec == 4 && g.np2 <= C2C_NS2_MAXNP2 && (g.I3 / 4) % 2 == 0) ? 2 : 1;
+        const int nsets = g.I3 / (vec * ns);
+        const int G = nsets < 32 ? nsets : 32;
+        const int ppw = 32 / G;
+        g.ps_ns = ns;
+        g.ps_rp = (2 * g.np2 + 3) / 4 * 4;
+        const size_t fixed = align_up((size_t)(g.I2 + g.I3) * g.ps_rp * sizeof(float) + (size_t)C2C_ST_MAXWARPS * C2C_ST_MAXRING * 8, 128);
+        const long long target = 10 * 1024;                          // bytes per stage
+        long long spw = 0, rs = 1, pitch = g.E;
+        if (ppw * plane_bytes > target && nsets <= 32) {
+            // large planes: a stage is a row slab of ppw planes; the slab must stay 16-byte sized and aligned
+            for (rs = 1; rs <= g.I2; ++rs)
+                if (g.I2 % rs == 0 && ((g.I2 / rs) * (long long)g.I3) % 4 == 0 && ppw * (plane_bytes / rs) <= target) break;
+            if (rs <= g.I2 && g.E % 4 == 0) {
+                spw = ppw;
+                pitch = (g.I2 / rs) * (long long)g.I3;
+                if (ppw > 1 && (G * vec) % 4 == 0)                   // consecutive planes -> consecutive banks
+                    while (pitch % 32 != (G * vec) % 32) pitch += 4;
+            } else rs = 1;
+        }
+        if (spw == 0) {
+            rs = 1; pitch = g.E;
+            const long long unit = (long long)ppw / gcd_ll(ppw, align_unit) * align_unit;
+            long long mult = target / (unit * plane_bytes);
+            if (mult < 1) mult = 1;
+            spw = unit * mult;
+            // small tensors: shrink the stages until every warp of the machine gets at least two plane groups
+            while (mult > 1 && g.P / spw < 2LL * nsm * C2C_ST_MAXWARPS) { mult /= 2; spw = unit * mult; }
+        }
+        const size_t stage_bytes = (size_t)(spw * pitch * 4);
+        if (fixed < C2C_SMEM_BUDGET / 2 && stage_bytes <= 24 * 1024) {
+            long long nw = C2C_ST_MAXWARPS;
+            long long ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed) / (nw * (long long)stage_bytes);
+            if (ring < 2) { nw = 4; ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed) / (nw * (long long)stage_bytes); }
+            if (ring > C2C_ST_MAXRING) ring = C2C_ST_MAXRING;
+            const long long ngroups = g.P / spw;
+            if (ring >= 2 && ngroups >= 2LL * nsm * nw) {
+                g.ps_ok = 1; g.ps_spw = (int)spw; g.ps_rs = (int)rs; g.ps_ring = (int)ring; g.ps_nwarps = (int)nw;
+                g.ps_pitch = (int)pitch; g.ps_nstage = ngroups; g.ps_grid = nsm;
+                g.ps_smem = fixed + (size_t)nw * ring * stage_bytes;
+            }
+        }
+    }
+    {   // ---- fiber_stream ----
+        const int vec = g.vec_fiber;
+        const long long nvec = g.E / vec;
+        const int ns = (vec == 4 && g.np2 <= C2C_NS2_MAXNP2 && nvec % 2 == 0) ? 2 : 1;
+        const long long nthr = nvec / ns;
+        const int maxthr = (ns == 2 ? g.np2 <= 5 : g.np2 <= 12) ? 512 : 256;
+        long long nslots = (maxthr - 32) / nthr;
+        if (nslots > 4) nslots = 4;
+        if (nthr >= 64 && nslots >= 1) {
+            const int ldr = ldr_of(rank);
+            const long long per_trip = 2 * nslots;                           // planes consumed per trip of the unrolled loop
+            long long unit = align_unit / gcd_ll(align_unit, per_trip) * per_trip;   // ... and stages stay 16-byte sized
+            long long mult = (52 * 1024) / (unit * plane_bytes);
+            if (mult < 1) mult = 1;
+            const long long tp = unit * mult;
+            const size_t stage_floats = ((size_t)tp * g.E + (size_t)tp * ldr + 31) / 32 * 32;
+            const size_t smem = 128 + (size_t)C2C_FS_STAGES * stage_floats * sizeof(float);
+            const long long nstage = g.P / tp;
+            if (smem <= C2C_SMEM_BUDGET && nstage >= 4LL * nsm) {
+                g.fs_ok = 1; g.fs_tp = (int)tp; g.fs_ns = ns; g.fs_nthr = (int)nthr; g.fs_nslots = (int)nslots;
+                g.fs_ncw = (int)((nthr * nslots + 31) / 32);
+                g.fs_nstage = nstage; g.fs_smem = smem;
+                g.fs_spc = (nstage + nsm - 1) / nsm;
+                g.fs_grid = (int)((nstage + g.fs_spc - 1) / g.fs_spc);
+                const long long parts = (long long)g.fs_grid * nslots + g.fc_nslots;
+                if (parts > g.max_parts) g.max_parts = parts;
+            }
+        }
+    }
+}
 
 static int fiber_geometry(Geo& g, int np2_chunk)
 {
@@ -125,14 +227,16 @@ static int make_geo(Geo& g, int ndim, const int64_t* shape, int rank)
     if (smem > 200 * 1024)
         return fail(-4, "trailing modes %d x %d at rank %d need %zu B of shared memory (> 200 KiB): put the two smallest modes last",
                     g.I2, g.I3, rank, smem);
-    return fiber_geometry(g, g.np2);
+    fiber_geometry(g, g.np2);
+    stream_geometry(g, rank);
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------------------------------------
 struct Ws {
-    float* T; float* part; float* U; float* M; float* G; float* Bmat; float* Xh;
+    float* T; float* part; float* U; float* M; float* G; float* Bmat; float* Xh; float* W;
     double* S; double* gram_part; double* iprod_part; double* normX2; double* sums_part; double* scratch_d;
     int* flags;
     size_t bytes;
@@ -148,7 +252,8 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
     const long long nblk = (g.maxI + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS;
     w.T = (float*)take((size_t)g.P * ldr * sizeof(float));
-    w.part = (float*)take((size_t)g.fc_nparts * g.E * ldr * sizeof(float));
+    w.part = (float*)take((size_t)g.max_parts * g.E * ldr * sizeof(float));
+    w.W = (float*)take(g.fs_ok ? (size_t)g.P * ldr * sizeof(float) : 0);
     w.U = (float*)take((size_t)g.E * ldr * sizeof(float));
     w.M = (float*)take((size_t)g.maxI * ldr * sizeof(float));
     w.G = (float*)take((size_t)ldr * ldr * sizeof(float));
@@ -199,7 +304,7 @@ static ContractArgs base_args(const Geo& g, const float* X, const uint8_t* mask,
 {
     ContractArgs a;
     memset(&a, 0, sizeof(a));
-    a.X = X; a.mask = mask; a.P = g.P; a.I2 = g.I2; a.I3 = g.I3; a.R = rank; a.ldr = ldr; a.r0 = 0;
+    a.X = X; a.mask = mask; a.P = g.P; a.p0 = 0; a.I2 = g.I2; a.I3 = g.I3; a.R = rank; a.ldr = ldr; a.r0 = 0;
     a.A2 = A[g.ndim - 2]; a.A3 = A[g.ndim - 1];
     fill_lead(a.lead, g, A);
     a.done = done;
@@ -221,9 +326,25 @@ static int plane_grid(const Geo& g, int vec)
 // T[P x ldr] = plane contraction of Xh with the two trailing factors
 static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cudaStream_t st)
 {
+    if (!masked && g.ps_ok) {
+        StreamArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.c = a; sa.c.out = T; sa.W = nullptr; sa.spw = g.ps_spw; sa.rs = g.ps_rs; sa.nring = g.ps_ring; sa.nstage = g.ps_nstage; sa.rp = g.ps_rp; sa.nwarps = g.ps_nwarps;
+        const int block = 32 * g.ps_nwarps;
+        sa.pitch = g.ps_pitch;
+        const cudaError_t e = g.vec_plane == 4 ? (g.ps_ns == 2 ? c2c_launch_plane_stream_v4_s2(g.np2, sa, g.ps_grid, block, g.ps_smem, st)
+                                                               : c2c_launch_plane_stream_v4_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st))
+                            : g.vec_plane == 2 ? c2c_launch_plane_stream_v2_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st)
+                                               : c2c_launch_plane_stream_v1_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st);
+        if (e != cudaSuccess) return cuda_fail(e, "plane_stream launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        a.p0 = g.ps_nstage * g.ps_spw;                 // the tail (< one stage of planes) goes to the register-staged kernel
+        if (a.p0 >= g.P) return 0;
+    }
     const int vec = g.vec_plane;
     const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);
-    const int grid = plane_grid(g, vec);
+    int grid = plane_grid(g, vec);
+    if (a.p0 > 0) { const long long tail = g.P - a.p0; if (grid > tail) grid = (int)tail; }
     a.out = T;
     for (int c = 0; c < g.nchunk; ++c) {
         a.r0 = c * 2 * g.np2;
@@ -247,32 +368,62 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
 {
     const int vec = g.vec_fiber;
     a.out = w.part;
-    if (masked) {
-        const long long n = g.E * a.ldr;
-        bmat_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(a.A2, a.A3, g.I2, g.I3, a.ldr, w.Bmat, a.done);
-        CKL("bmat launch");
-        a.Bmat = w.Bmat;
-    }
-    const dim3 grid(g.fc_gx, g.fc_gy);
-    for (int c = 0; c < g.nchunk; ++c) {
-        a.r0 = c * 2 * g.np2;
-        if (a.r0 >= a.R) break;
-        cudaError_t e;
-        if (masked) {
-            e = vec == 4 ? c2c_launch_fiber_v4_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
-              : vec == 2 ? c2c_launch_fiber_v2_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
-                         : c2c_launch_fiber_v1_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st);
-        } else {
-            e = vec == 4 ? c2c_launch_fiber_v4_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
-              : vec == 2 ? c2c_launch_fiber_v2_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st)
-                         : c2c_launch_fiber_v1_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, g.fc_ppc, st);
-        }
-        if (e != cudaSuccess) return cuda_fail(e, "fiber_contract launch");
+    long long nparts = g.fc_nparts;
+    dim3 grid(g.fc_gx, g.fc_gy);
+    long long ppc = g.fc_ppc;
+    bool legacy = true;
+    if (!masked && g.fs_ok) {
+        LeadInfo li = a.lead;
+        const long long n = g.P * (a.ldr / 4);
+        long long kb = (n + 255) / 256; if (kb > sm_count() * 8) kb = sm_count() * 8;
+        kr_rows_kernel<<<(int)kb, C2C_SMALL_THREADS, 0, st>>>(li, g.P, a.R, a.ldr, w.W, a.done);
+        CKL("kr_rows launch");
+        StreamArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.c = a; sa.W = w.W; sa.spw = g.fs_tp; sa.nstage = g.fs_nstage; sa.nwarps = g.fs_ncw; sa.stages_per_cta = g.fs_spc;
+        const int block = 32 * (g.fs_ncw + 1);
+        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st)
+                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st))
+                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st)
+                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        nparts = (long long)g.fs_grid * g.fs_nslots;
+        a.p0 = g.fs_nstage * g.fs_tp;
+        legacy = a.p0 < g.P;
+        if (legacy) {                                  // tail planes: one CTA row of the register-staged kernel, extra partials
+            a.out = w.part + (size_t)nparts * g.E * a.ldr;
+            grid = dim3(1, g.fc_gy);
+            ppc = g.P - a.p0;
+            nparts += g.fc_nslots;
+        }
     }
-    const long long n = g.E * a.ldr;
-    int rb = (int)((n + 255) / 256);
-    fiber_reduce_kernel<<<rb, 256, 0, st>>>(w.part, (int)g.fc_nparts, g.E, a.R, a.ldr, w.U, a.done);
+    if (legacy) {
+        if (masked) {
+            const long long n = g.E * a.ldr;
+            bmat_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(a.A2, a.A3, g.I2, g.I3, a.ldr, w.Bmat, a.done);
+            CKL("bmat launch");
+            a.Bmat = w.Bmat;
+        }
+        for (int c = 0; c < g.nchunk; ++c) {
+            a.r0 = c * 2 * g.np2;
+            if (a.r0 >= a.R) break;
+            cudaError_t e;
+            if (masked) {
+                e = vec == 4 ? c2c_launch_fiber_v4_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st)
+                  : vec == 2 ? c2c_launch_fiber_v2_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st)
+                             : c2c_launch_fiber_v1_m1(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st);
+            } else {
+                e = vec == 4 ? c2c_launch_fiber_v4_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st)
+                  : vec == 2 ? c2c_launch_fiber_v2_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st)
+                             : c2c_launch_fiber_v1_m0(g.np2, a, grid, g.fc_block, g.fc_nvec, g.fc_nvec_total, g.fc_nslots, ppc, st);
+            }
+            if (e != cudaSuccess) return cuda_fail(e, "fiber_contract launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+    }
+    const long long n4 = g.E * a.ldr / 4;
+    fiber_reduce2_kernel<<<(int)((n4 + 31) / 32), 256, 0, st>>>(w.part, (int)nparts, n4, a.R, a.ldr, w.U, a.done);
     CKL("fiber_reduce launch");
     return 0;
 }

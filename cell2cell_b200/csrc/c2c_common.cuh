@@ -22,6 +22,7 @@ struct ContractArgs {
     const float* X;            // [P, I2, I3]
     const uint8_t* mask;       // same shape, 1 = observed, 0 = missing (imputed with the current reconstruction); may be null
     long long P;               // number of planes
+    long long p0;              // first plane this launch handles (the register-staged kernels finish the tail of a streamed pass)
     int I2, I3;                // trailing mode sizes
     int R;                     // rank
     int ldr;                   // factor pitch (floats), multiple of 4, >= R

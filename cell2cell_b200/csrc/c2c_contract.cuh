@@ -82,7 +82,7 @@ plane_contract_kernel(const ContractArgs a)
 
     double s_d = 0, s_dd = 0, s_x = 0, s_xx = 0, s_n = 0;   // SUMS only
 
-    for (long long base = wg * ppw; base < a.P; base += nw * ppw) {
+    for (long long base = a.p0 + wg * ppw; base < a.P; base += nw * ppw) {
         const long long p = base + grp;
         const bool on = lane_on && p < a.P;
         float out[RC];
@@ -272,7 +272,7 @@ fiber_contract_kernel(const ContractArgs a, const int nvec, const int nvec_total
     const int slot = threadIdx.x / nvec;
     const int pos = blockIdx.y * nvec + (threadIdx.x - slot * nvec);
     const bool on = slot < nslots && pos < nvec_total;
-    const long long pb = (long long)blockIdx.x * planes_per_cta;
+    const long long pb = a.p0 + (long long)blockIdx.x * planes_per_cta;
     long long pe = pb + planes_per_cta; if (pe > a.P) pe = a.P;
 
     float2 acc[(VEC + 1) / 2][RC];

@@ -1,0 +1,3 @@
+#define C2C_INST_VEC 4
+#define C2C_INST_NS 1
+#include "c2c_stream_inst.cuh"
