@@ -15,6 +15,7 @@
 #include "c2c_contract.cuh"
 #include "c2c_stream.cuh"
 #include "c2c_small.cuh"
+#include "c2c_update.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -77,7 +78,7 @@ struct Geo {
     int nchunk;  // rank chunks
     // shared-memory-staged (bulk-copy) passes; *_ok = 0 -> the register-staged kernels do the whole pass
     int ps_ok, ps_ns, ps_spw, ps_rs, ps_ring, ps_nwarps, ps_rp, ps_pitch, ps_grid; long long ps_nstage; size_t ps_smem;
-    int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
+    int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_merge, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
     long long max_parts;
 };
 
@@ -170,7 +171,9 @@ static void stream_geometry(Geo& g, int rank)
                 g.fs_nstage = nstage; g.fs_smem = smem;
                 g.fs_spc = (nstage + nsm - 1) / nsm;
                 g.fs_grid = (int)((nstage + g.fs_spc - 1) / g.fs_spc);
-                const long long parts = (long long)g.fs_grid * nslots + g.fc_nslots;
+                const size_t acc_bytes = (size_t)ns * vec * g.np2 * 8;                 // accumulators of one thread
+                g.fs_merge = (nslots - 1) * nthr * (long long)acc_bytes <= (long long)(smem - 128) ? 1 : 0;
+                const long long parts = (long long)g.fs_grid * (g.fs_merge ? 1 : nslots) + g.fc_nslots;
                 if (parts > g.max_parts) g.max_parts = parts;
             }
         }
@@ -253,20 +256,21 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     const long long nblk = (g.maxI + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS;
     w.T = (float*)take((size_t)g.P * ldr * sizeof(float));
     w.part = (float*)take((size_t)g.max_parts * g.E * ldr * sizeof(float));
-    w.W = (float*)take(g.fs_ok ? (size_t)g.P * ldr * sizeof(float) : 0);
+    w.W = nullptr;
     w.U = (float*)take((size_t)g.E * ldr * sizeof(float));
     w.M = (float*)take((size_t)g.maxI * ldr * sizeof(float));
     w.G = (float*)take((size_t)ldr * ldr * sizeof(float));
     w.Bmat = (float*)take(masked ? (size_t)g.E * ldr * sizeof(float) : 0);
     // ranks beyond one chunk: the masked passes need the full-rank reconstruction, so the imputed tensor is materialised
     w.Xh = (float*)take((masked && g.nchunk > 1) ? (size_t)g.P * g.E * sizeof(float) : 0);
-    w.S = (double*)take((size_t)g.ndim * ldr * ldr * sizeof(double));
-    w.gram_part = (double*)take((size_t)nblk * ldr * ldr * sizeof(double));
+    w.S = (double*)take((size_t)2 * g.ndim * ldr * ldr * sizeof(double));        // two banks (c2c_update.cuh)
+    const long long nblk_g = nblk > 512 ? nblk : 512;             // lead_update runs at most 2 CTAs per SM, capped at 512
+    w.gram_part = (double*)take((size_t)nblk_g * ldr * ldr * sizeof(double));
     w.iprod_part = (double*)take((size_t)nblk * sizeof(double));
     w.normX2 = (double*)take(sizeof(double));
     w.sums_part = (double*)take((size_t)C2C_SUMS_BLOCKS * 5 * sizeof(double));
     w.scratch_d = (double*)take(16 * sizeof(double));
-    w.flags = (int*)take(4 * sizeof(int));
+    w.flags = (int*)take(4 * sizeof(int));       // [0]: lead_update arrival counter (zero between launches)
     w.bytes = off;
 }
 
@@ -373,22 +377,17 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
     long long ppc = g.fc_ppc;
     bool legacy = true;
     if (!masked && g.fs_ok) {
-        LeadInfo li = a.lead;
-        const long long n = g.P * (a.ldr / 4);
-        long long kb = (n + 255) / 256; if (kb > sm_count() * 8) kb = sm_count() * 8;
-        kr_rows_kernel<<<(int)kb, C2C_SMALL_THREADS, 0, st>>>(li, g.P, a.R, a.ldr, w.W, a.done);
-        CKL("kr_rows launch");
         StreamArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.c = a; sa.W = w.W; sa.spw = g.fs_tp; sa.nstage = g.fs_nstage; sa.nwarps = g.fs_ncw; sa.stages_per_cta = g.fs_spc;
         const int block = 32 * (g.fs_ncw + 1);
-        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st)
-                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st))
-                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st)
-                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_grid, block, g.fs_smem, st);
+        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st)
+                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st))
+                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st)
+                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        nparts = (long long)g.fs_grid * g.fs_nslots;
+        nparts = (long long)g.fs_grid * (g.fs_merge ? 1 : g.fs_nslots);
         a.p0 = g.fs_nstage * g.fs_tp;
         legacy = a.p0 < g.P;
         if (legacy) {                                  // tail planes: one CTA row of the register-staged kernel, extra partials
@@ -809,6 +808,76 @@ static int update_mode(const RunCtx& c, int mode, bool last)
     return 0;
 }
 
+// fused MU update of leading mode `mode` from T (c2c_update.cuh)
+static int launch_lead_update(const RunCtx& c, int mode)
+{
+    const Geo& g = c.g;
+    LeadUpdArgs u;
+    memset(&u, 0, sizeof(u));
+    u.T = c.w.T; fill_lead(u.lead, g, (const float* const*)c.A); u.k = mode; u.P = g.P; u.R = c.R; u.ldr = c.ldr; u.N = g.ndim;
+    u.A = c.A[mode]; u.S = c.w.S; u.state = c.state; u.eps = c.eps; u.done = c.state + 1;
+    const long long I = g.shape[mode];
+    const long long cnt = g.P / I;                                   // planes carrying one index of this mode
+    const int block = cnt >= 1024 ? 1024 : 256;
+    const int tpr = cnt >= 512 ? block : 32;                         // CTA per row / warp per row
+    const int nrc = block / tpr;
+    long long rows = (I + 2LL * sm_count() - 1) / (2LL * sm_count());
+    rows = (rows + nrc - 1) / nrc * nrc;
+    u.rows_per_cta = (int)rows;
+    const long long grid = (I + rows - 1) / rows;
+    const int njr = tpr / (c.ldr / 4);
+    if (njr < 1) return fail(-30, "rank too large for the fused update");
+    const size_t smem = (((size_t)(c.R * c.R + nrc * c.ldr) * sizeof(float) + 7) & ~(size_t)7) + (size_t)nrc * njr * c.ldr * sizeof(double);
+    lead_update_kernel<<<(int)grid, block, smem, c.st>>>(u, tpr);
+    CKL("lead_update launch");
+    return 0;
+}
+
+static size_t trail_update_smem(const Geo& g, int R, int ldr, int* u_in_smem)
+{
+    const size_t Imax = g.I2 > g.I3 ? g.I2 : g.I3;
+    size_t base = ((size_t)g.ndim * R * R + 32) * sizeof(double) + ((size_t)R * R + (size_t)(g.I2 + g.I3 + Imax) * R) * sizeof(float) + 16;
+    const size_t ub = (size_t)g.E * ldr * sizeof(float);
+    *u_in_smem = (base + ub <= 200 * 1024) ? 1 : 0;
+    return base + (*u_in_smem ? ub : 0);
+}
+
+// fused MU update of the trailing modes [which_begin, which_end) from U, + error / stop rule after the last one
+static int launch_trail_update(const RunCtx& c, int which_begin, int which_end)
+{
+    const Geo& g = c.g;
+    TrailUpdArgs u;
+    memset(&u, 0, sizeof(u));
+    u.U = c.w.U; u.A2 = c.A[g.ndim - 2]; u.A3 = c.A[g.ndim - 1]; u.I2 = g.I2; u.I3 = g.I3; u.R = c.R; u.ldr = c.ldr; u.N = g.ndim;
+    u.S = c.w.S; u.eps = c.eps; u.which_begin = which_begin; u.which_end = which_end;
+    u.normX2 = c.normX2; u.errors = c.errors; u.state = c.state; u.n_iter_max = c.n_iter_max; u.tol = c.tol; u.cvg = c.cvg;
+    u.done = c.state + 1;
+    const size_t smem = trail_update_smem(g, c.R, c.ldr, &u.u_in_smem);
+    if (smem > 48 * 1024) {
+        static thread_local size_t set_for = 0;
+        if (set_for < smem) {
+            CK(cudaFuncSetAttribute(trail_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "trail_update smem attribute");
+            set_for = 200 * 1024;
+        }
+    }
+    trail_update_kernel<<<1, C2C_TU_THREADS, smem, c.st>>>(u);
+    CKL("trail_update launch");
+    return 0;
+}
+
+static bool fused_updates(const RunCtx& c)
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("C2C_B200_NO_FUSED"); v = (e && e[0] == '1') ? 0 : 1; }
+    if (!v || c.algo != C2C_ALGO_MU || c.g.nchunk != 1) return false;
+    int dummy;
+    const size_t Imax = c.g.I2 > c.g.I3 ? c.g.I2 : c.g.I3;
+    (void)dummy;
+    // the single-CTA trailing update keeps both trailing factors (+ one M) in shared memory, two new entries per thread
+    return ((size_t)(c.g.I2 + c.g.I3 + Imax) * c.R * sizeof(float)) <= 96 * 1024 && Imax * c.R <= 2 * C2C_TU_THREADS &&
+           c.g.P < (1LL << 31);
+}
+
 static int enqueue_iteration(const RunCtx& c)
 {
     const Geo& g = c.g; int rc;
@@ -825,7 +894,11 @@ static int enqueue_iteration(const RunCtx& c)
             if (mode < nlead) { if ((rc = launch_plane(g, a, masked, c.w.T, c.st)) != 0) return rc; }
             else              { if ((rc = launch_fiber(g, a, masked, c.w, c.st)) != 0) return rc; }
         }
-        if ((rc = update_mode(c, mode, mode == g.ndim - 1)) != 0) return rc;
+        if (fused_updates(c)) {
+            if (mode < nlead) { if ((rc = launch_lead_update(c, mode)) != 0) return rc; }
+            else if (!has_mask) { if (mode == nlead) { if ((rc = launch_trail_update(c, 0, 2)) != 0) return rc; } }
+            else { if ((rc = launch_trail_update(c, mode - nlead, mode - nlead + 1)) != 0) return rc; }
+        } else if ((rc = update_mode(c, mode, mode == g.ndim - 1)) != 0) return rc;
     }
     return 0;
 }
@@ -852,15 +925,20 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
     const Geo& g = c.g;
 
     CK(cudaMemsetAsync(state, 0, 2 * sizeof(int), st), "memset state");
+    CK(cudaMemsetAsync(c.w.flags, 0, 4 * sizeof(int), st), "memset flags");
     if (normX2) c.normX2 = normX2;
     else {
         if ((rc = sumsq_into(X, g.P * g.E, c.w.normX2, c.w.sums_part, st)) != 0) return rc;
         c.normX2 = c.w.normX2;
     }
-    // Grams of the initial factors; G for mode 0
+    // Grams of the initial factors (fused updates: into bank 1, bank 0 cleared for iteration 0); G for mode 0
+    const bool fused = fused_updates(c);
+    const size_t bank = (size_t)ndim * ldr * ldr;
+    if (fused) CK(cudaMemsetAsync(c.w.S, 0, bank * sizeof(double), st), "memset Gram bank");
     for (int k = 0; k < ndim; ++k) {
         if ((rc = launch_gram_partial(A[k], nullptr, g.shape[k], rank, ldr, c.w, false, nullptr, st)) != 0) return rc;
         FinalizeArgs f = fin_args(g, rank, ldr, c.w, nullptr);
+        if (fused) f.S = c.w.S + bank;
         f.k = k; f.gram_part = c.w.gram_part; f.nblk = (int)((g.shape[k] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
         if (k == ndim - 1) { f.next = 0; f.G = c.w.G; }
         gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);

@@ -264,7 +264,7 @@ plane_stream_kernel(const StreamArgs sa)
 #define C2C_FS_MAXTHREADS(NS, NP2) (((NS) == 2 ? (NP2) <= 5 : (NP2) <= 12) ? 512 : 256)
 template <int VEC, int NS, int NP2>
 __global__ void __launch_bounds__(C2C_FS_MAXTHREADS(NS, NP2), 1)
-fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, const int nslots)
+fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, const int nslots, const int merge)
 {
     const ContractArgs& a = sa.c;
     if (run_done(a.done)) return;
@@ -284,24 +284,41 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
     long long se = sb + sa.stages_per_cta; if (se > sa.nstage) se = sa.nstage;
     if (sb > se) sb = se;
     if (threadIdx.x == 0) {
-        for (int j = 0; j < S; ++j) { mbar_init(full + j, 1); mbar_init(empty + j, ncw); }
+        for (int j = 0; j < S; ++j) { mbar_init(full + j, 2); mbar_init(empty + j, ncw); }
         mbar_init_fence();
     }
     __syncthreads();
 
     if (warp == ncw) {
-        // ---- producer ----
-        if (lane == 0) {
-            const unsigned xb = (unsigned)(x_floats * sizeof(float)), wb = (unsigned)(w_floats * sizeof(float));
-            int slot = 0; unsigned phase = 0; bool wrapped = false;
-            for (long long g = sb; g < se; ++g) {
-                if (wrapped) mbar_wait(empty + slot, phase ^ 1u);
-                float* dst = stage0 + (size_t)slot * stage_floats;
-                mbar_expect_tx(full + slot, xb + wb);
+        // ---- producer: bulk copy of the stage's planes, then its Khatri-Rao rows W[p, :] = prod_k A_k[i_k(p), :] built
+        // in place by the 32 lanes ("full" takes two arrivals: the copy's expect_tx and the one that publishes W) ----
+        const unsigned xb = (unsigned)(x_floats * sizeof(float));
+        const int q4 = ldr >> 2, nitems = tp * q4;
+        int slot = 0; unsigned phase = 0; bool wrapped = false;
+        for (long long g = sb; g < se; ++g) {
+            if (wrapped) mbar_wait(empty + slot, phase ^ 1u);
+            float* dst = stage0 + (size_t)slot * stage_floats;
+            if (lane == 0) {
+                mbar_expect_tx(full + slot, xb);
                 bulk_g2s(dst, a.X + (size_t)g * x_floats, xb, full + slot);
-                bulk_g2s(dst + x_floats, sa.W + (size_t)g * w_floats, wb, full + slot);
-                if (++slot == S) { slot = 0; phase ^= 1u; wrapped = true; }
             }
+            for (int it = lane; it < nitems; it += 32) {
+                const int pl = it / q4, quad = it - pl * q4;
+                long long rem = g * tp + pl;
+                float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int k = a.lead.nl - 1; k >= 0; --k) {
+                    const int d = a.lead.dim[k];
+                    const long long qq = rem / d;
+                    const int i = (int)(rem - qq * d);
+                    rem = qq;
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(a.lead.fac[k] + (size_t)i * ldr) + quad);
+                    w.x *= f.x; w.y *= f.y; w.z *= f.z; w.w *= f.w;
+                }
+                *reinterpret_cast<float4*>(dst + x_floats + (size_t)pl * ldr + quad * 4) = w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + slot);
+            if (++slot == S) { slot = 0; phase ^= 1u; wrapped = true; }
         }
         return;
     }
@@ -349,10 +366,41 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
         if (lane == 0) mbar_arrive(empty + cslot);
         if (++cslot == S) { cslot = 0; cphase ^= 1u; }
     }
-    if (on) {
+    // the slots' accumulators are combined through shared memory (the ring is drained), slot 0 writes the CTA's partial
+    const int nout = merge ? 1 : nslots;
+    if (merge && nslots > 1) {
+        constexpr int PER = NS * VEC * NP2;                          // float2 per thread
+        float2* sacc = reinterpret_cast<float2*>(stage0);
+        asm volatile("bar.sync 1, %0;" ::"r"(ncw * 32) : "memory");
+        if (on && slot_id > 0) {
+            float2* dst = sacc + ((size_t)(slot_id - 1) * nthr + pos) * PER;
+#pragma unroll
+            for (int n = 0; n < NS; ++n)
+#pragma unroll
+                for (int j = 0; j < VEC; ++j)
+#pragma unroll
+                    for (int q = 0; q < NP2; ++q) dst[(n * VEC + j) * NP2 + q] = acc[n][j][q];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncw * 32) : "memory");
+        if (on && slot_id == 0) {
+            for (int sl = 1; sl < nslots; ++sl) {
+                const float2* src = sacc + ((size_t)(sl - 1) * nthr + pos) * PER;
+#pragma unroll
+                for (int n = 0; n < NS; ++n)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j)
+#pragma unroll
+                        for (int q = 0; q < NP2; ++q) {
+                            const float2 t = src[(n * VEC + j) * NP2 + q];
+                            acc[n][j][q].x += t.x; acc[n][j][q].y += t.y;
+                        }
+            }
+        }
+    }
+    if (on && (slot_id == 0 || !merge)) {
 #pragma unroll
         for (int n = 0; n < NS; ++n) {
-            float* o = a.out + (((size_t)blockIdx.x * nslots + slot_id) * E + ((size_t)n * nthr + pos) * VEC) * ldr;
+            float* o = a.out + (((size_t)blockIdx.x * nout + (merge ? 0 : slot_id)) * E + ((size_t)n * nthr + pos) * VEC) * ldr;
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
 #pragma unroll
@@ -368,5 +416,5 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
 #define C2C_NS2_MAXNP2 10
 #define C2C_DECL_STREAM(V, N)                                                                                       \
     cudaError_t c2c_launch_plane_stream_v##V##_s##N(int np2, const StreamArgs& a, int grid, int block, size_t smem, cudaStream_t st); \
-    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int grid, int block, size_t smem, cudaStream_t st);
+    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int merge, int grid, int block, size_t smem, cudaStream_t st);
 C2C_DECL_STREAM(4, 1) C2C_DECL_STREAM(4, 2) C2C_DECL_STREAM(2, 1) C2C_DECL_STREAM(1, 1)
