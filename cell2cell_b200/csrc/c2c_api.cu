@@ -78,7 +78,7 @@ struct Geo {
     int nchunk;  // rank chunks
     // shared-memory-staged (bulk-copy) passes; *_ok = 0 -> the register-staged kernels do the whole pass
     int ps_ok, ps_ns, ps_spw, ps_rs, ps_ring, ps_nwarps, ps_rp, ps_pitch, ps_grid; long long ps_nstage; size_t ps_smem;
-    int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_merge, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
+    int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_merge, fs_wall, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
     long long max_parts;
 };
 
@@ -162,17 +162,22 @@ static void stream_geometry(Geo& g, int rank)
             long long mult = (52 * 1024) / (unit * plane_bytes);
             if (mult < 1) mult = 1;
             const long long tp = unit * mult;
-            const size_t stage_floats = ((size_t)tp * g.E + (size_t)tp * ldr + 31) / 32 * 32;
-            const size_t smem = 128 + (size_t)C2C_FS_STAGES * stage_floats * sizeof(float);
             const long long nstage = g.P / tp;
-            if (smem <= C2C_SMEM_BUDGET && nstage >= 4LL * nsm) {
-                g.fs_ok = 1; g.fs_tp = (int)tp; g.fs_ns = ns; g.fs_nthr = (int)nthr; g.fs_nslots = (int)nslots;
+            const long long spc = (nstage + nsm - 1) / nsm;
+            // Khatri-Rao rows: all of a CTA's planes up front in shared memory when they fit, else per stage by the producer
+            const size_t x_stage = ((size_t)tp * g.E + 31) / 32 * 32;
+            const size_t wall_bytes = (size_t)spc * tp * ldr * sizeof(float);
+            int w_all = 128 + (size_t)C2C_FS_STAGES * x_stage * sizeof(float) + wall_bytes <= (size_t)C2C_SMEM_BUDGET + 16 * 1024;
+            const size_t stage_floats = w_all ? x_stage : ((size_t)tp * g.E + (size_t)tp * ldr + 31) / 32 * 32;
+            const size_t smem = 128 + (size_t)C2C_FS_STAGES * stage_floats * sizeof(float) + (w_all ? wall_bytes : 0);
+            if (smem <= (size_t)C2C_SMEM_BUDGET + 16 * 1024 && nstage >= 4LL * nsm) {
+                g.fs_ok = 1; g.fs_tp = (int)tp; g.fs_ns = ns; g.fs_nthr = (int)nthr; g.fs_nslots = (int)nslots; g.fs_wall = w_all;
                 g.fs_ncw = (int)((nthr * nslots + 31) / 32);
                 g.fs_nstage = nstage; g.fs_smem = smem;
-                g.fs_spc = (nstage + nsm - 1) / nsm;
+                g.fs_spc = spc;
                 g.fs_grid = (int)((nstage + g.fs_spc - 1) / g.fs_spc);
                 const size_t acc_bytes = (size_t)ns * vec * g.np2 * 8;                 // accumulators of one thread
-                g.fs_merge = (nslots - 1) * nthr * (long long)acc_bytes <= (long long)(smem - 128) ? 1 : 0;
+                g.fs_merge = (nslots - 1) * nthr * (long long)acc_bytes <= (long long)((size_t)C2C_FS_STAGES * stage_floats * sizeof(float)) ? 1 : 0;
                 const long long parts = (long long)g.fs_grid * (g.fs_merge ? 1 : nslots) + g.fc_nslots;
                 if (parts > g.max_parts) g.max_parts = parts;
             }
@@ -381,10 +386,10 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         memset(&sa, 0, sizeof(sa));
         sa.c = a; sa.W = w.W; sa.spw = g.fs_tp; sa.nstage = g.fs_nstage; sa.nwarps = g.fs_ncw; sa.stages_per_cta = g.fs_spc;
         const int block = 32 * (g.fs_ncw + 1);
-        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st)
-                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st))
-                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st)
-                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_grid, block, g.fs_smem, st);
+        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st)
+                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st))
+                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st)
+                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         nparts = (long long)g.fs_grid * (g.fs_merge ? 1 : g.fs_nslots);

@@ -264,7 +264,8 @@ plane_stream_kernel(const StreamArgs sa)
 #define C2C_FS_MAXTHREADS(NS, NP2) (((NS) == 2 ? (NP2) <= 5 : (NP2) <= 12) ? 512 : 256)
 template <int VEC, int NS, int NP2>
 __global__ void __launch_bounds__(C2C_FS_MAXTHREADS(NS, NP2), 1)
-fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, const int nslots, const int merge)
+fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, const int nslots, const int merge,
+                    const int w_all /* 1: the CTA's Khatri-Rao rows are built once, up front, into shared memory */)
 {
     const ContractArgs& a = sa.c;
     if (run_done(a.done)) return;
@@ -275,16 +276,17 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
     const int tp = sa.spw;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw);      // [S]
     unsigned long long* empty = full + S;                                            // [S]
-    const size_t x_floats = (size_t)tp * E, w_floats = (size_t)tp * ldr;
+    const size_t x_floats = (size_t)tp * E, w_floats = w_all ? 0 : (size_t)tp * ldr;
     const size_t stage_floats = (x_floats + w_floats + 31) / 32 * 32;
     float* stage0 = reinterpret_cast<float*>(smem_raw + 128);
+    float* wall = stage0 + (size_t)S * stage_floats;                 // [stages_per_cta * tp][ldr] when w_all
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ncw = sa.nwarps;
     long long sb = (long long)blockIdx.x * sa.stages_per_cta;
     long long se = sb + sa.stages_per_cta; if (se > sa.nstage) se = sa.nstage;
     if (sb > se) sb = se;
     if (threadIdx.x == 0) {
-        for (int j = 0; j < S; ++j) { mbar_init(full + j, 2); mbar_init(empty + j, ncw); }
+        for (int j = 0; j < S; ++j) { mbar_init(full + j, w_all ? 1 : 2); mbar_init(empty + j, ncw); }
         mbar_init_fence();
     }
     __syncthreads();
@@ -302,7 +304,7 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
                 mbar_expect_tx(full + slot, xb);
                 bulk_g2s(dst, a.X + (size_t)g * x_floats, xb, full + slot);
             }
-            for (int it = lane; it < nitems; it += 32) {
+            for (int it = lane; it < (w_all ? 0 : nitems); it += 32) {
                 const int pl = it / q4, quad = it - pl * q4;
                 long long rem = g * tp + pl;
                 float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -317,7 +319,7 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
                 *reinterpret_cast<float4*>(dst + x_floats + (size_t)pl * ldr + quad * 4) = w;
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(full + slot);
+            if (lane == 0 && !w_all) mbar_arrive(full + slot);
             if (++slot == S) { slot = 0; phase ^= 1u; wrapped = true; }
         }
         return;
@@ -333,13 +335,34 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
 #pragma unroll
             for (int q = 0; q < NP2; ++q) acc[n][j][q] = make_float2(0.0f, 0.0f);
     const int e_i = (int)E, step = nslots * e_i, wstep = nslots * ldr, noff = nthr * VEC;
+    if (w_all) {
+        // Khatri-Rao rows of this CTA's planes, built by the consumer warps while the first stages are in flight
+        const int q4 = ldr >> 2;
+        const long long nitems = (se - sb) * tp * q4;
+        for (long long it = threadIdx.x; it < nitems; it += (long long)ncw * 32) {
+            const long long pl = it / q4; const int quad = (int)(it - pl * q4);
+            long long rem = sb * tp + pl;
+            float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+            for (int k = a.lead.nl - 1; k >= 0; --k) {
+                const int d = a.lead.dim[k];
+                const long long qq = rem / d;
+                const int i = (int)(rem - qq * d);
+                rem = qq;
+                const float4 f = __ldg(reinterpret_cast<const float4*>(a.lead.fac[k] + (size_t)i * ldr) + quad);
+                w.x *= f.x; w.y *= f.y; w.z *= f.z; w.w *= f.w;
+            }
+            *reinterpret_cast<float4*>(wall + (size_t)pl * ldr + quad * 4) = w;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(ncw * 32) : "memory");
+    }
     int cslot = 0; unsigned cphase = 0;
+    const float* wrow_cta = wall + slot_id * ldr;                    // w_all: advances tp rows per stage
     for (long long g = sb; g < se; ++g) {
         mbar_wait(full + cslot, cphase);
         const float* xs = stage0 + (size_t)cslot * stage_floats;
         if (on) {
             const float* xp = xs + slot_id * e_i + pos * VEC;
-            const float* wp = xs + x_floats + slot_id * ldr;
+            const float* wp = w_all ? wrow_cta : xs + x_floats + slot_id * ldr;
             auto plane = [&](const float* xr, const float* wr) {
                 float x[NS][VEC];
 #pragma unroll
@@ -362,6 +385,7 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
                 xp += 2 * step; wp += 2 * wstep;
             }
         }
+        wrow_cta += (size_t)tp * ldr;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + cslot);
         if (++cslot == S) { cslot = 0; cphase ^= 1u; }
@@ -416,5 +440,5 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
 #define C2C_NS2_MAXNP2 10
 #define C2C_DECL_STREAM(V, N)                                                                                       \
     cudaError_t c2c_launch_plane_stream_v##V##_s##N(int np2, const StreamArgs& a, int grid, int block, size_t smem, cudaStream_t st); \
-    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int merge, int grid, int block, size_t smem, cudaStream_t st);
+    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st);
 C2C_DECL_STREAM(4, 1) C2C_DECL_STREAM(4, 2) C2C_DECL_STREAM(2, 1) C2C_DECL_STREAM(1, 1)

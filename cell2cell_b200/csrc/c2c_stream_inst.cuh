@@ -17,7 +17,7 @@
         e = cudaFuncSetAttribute(fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N>,                                 \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
         if (e != cudaSuccess) return e;                                                                             \
-        fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N><<<grid, block, smem, st>>>(a, nthr, nslots, merge);               \
+        fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N><<<grid, block, smem, st>>>(a, nthr, nslots, merge, w_all);               \
         break;
 
 #if C2C_INST_NS == 2
@@ -38,7 +38,7 @@ cudaError_t C2C_SCAT(c2c_launch_plane_stream_v, C2C_INST_VEC, _s, C2C_INST_NS)(i
 }
 
 cudaError_t C2C_SCAT(c2c_launch_fiber_stream_v, C2C_INST_VEC, _s, C2C_INST_NS)(int np2, const StreamArgs& a, int nthr, int nslots,
-                                                                               int merge, int grid, int block, size_t smem, cudaStream_t st)
+                                                                               int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st)
 {
     cudaError_t e = cudaSuccess;
     switch (np2) {
