@@ -276,6 +276,51 @@ def run_ours(args, rank_id, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, rank_id, local_rank, world):
+    """One factorization of the workload tensor sharded along mode 0 over the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    from cell2cell_b200.sharded import shard_bounds, sharded_non_negative_parafac
+    from cell2cell_b200.tensor.cp import random_factors
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = WORKLOADS[args.workload]
+    shape, rank, iters = wl["shape"], wl["rank"], args.iters
+    lo, hi = shard_bounds(shape[0], world, rank_id)
+    x_host = synth_host(shape, 1, pinned=False)
+    X = x_host[lo:hi].contiguous().to(dev)
+    del x_host
+    init = random_factors(shape, rank, 888)
+    for _ in range(max(1, args.warmup // 3)):
+        sharded_non_negative_parafac(X, shape, rank, init, n_iter_max=10, tol=-1.0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 3))
+    e0.record()
+    for _ in range(steps):
+        cp, errs = sharded_non_negative_parafac(X, shape, rank, init, n_iter_max=iters, tol=-1.0)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank_id != 0:
+        return
+    sec = float(t[0])
+    print(json.dumps({"metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": steps * iters / sec,
+                      "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": max(1, args.warmup // 3),
+                      "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "%s %s rank %d, ONE factorization sharded along the context mode" % (
+                          args.workload, "x".join(map(str, shape)), rank), "iterations_per_step": iters,
+                          "collectives_per_iteration": len(shape) - 1},
+                      "final_rec_error": errs[-1]}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -287,6 +332,9 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=2, help="CPU iterations per step of the reference arm / cpu_baseline")
     ap.add_argument("--ref-warm", action="store_true", help="also run the warm-up steps on the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="N > 1: independent factorizations per GPU (weak scaling, default) or ONE factorization sharded along "
+                         "the context mode with NCCL all-reduces of the MTTKRP / Gram partials (strong scaling)")
     args = ap.parse_args()
     rank_id = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -300,7 +348,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank_id, local_rank, world)
+        if args.mode == "sharded":
+            run_sharded(args, rank_id, local_rank, world)
+        else:
+            run_ours(args, rank_id, local_rank, world)
     finally:
         if world > 1:
             dist.destroy_process_group()

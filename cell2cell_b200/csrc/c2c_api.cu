@@ -690,6 +690,22 @@ extern "C" int c2c_fiber_contract(const float* X, const uint8_t* mask, int ndim,
     return 0;
 }
 
+// M for one mode from an already computed T (leading modes) or U (trailing modes): the second half of c2c_mttkrp, exposed
+// so that a sharded factorization can all-reduce T-derived / U partial sums between the two halves.
+extern "C" int c2c_mttkrp_from_contraction(const float* TU, int ndim, const int64_t* shape, const float* const* A, int ldr, int rank,
+                                           int mode, float* M, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(TU, A, ndim, ldr, rank)) != 0) return rc;
+    if (mode < 0 || mode >= ndim) return fail(-13, "mode %d out of range", mode);
+    if (!M) return fail(-14, "M is NULL");
+    Ws w; memset(&w, 0, sizeof(w));
+    w.T = const_cast<float*>(TU); w.U = const_cast<float*>(TU);
+    return launch_mode_mttkrp(g, A, mode, rank, ldr, w, M, nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int c2c_gram_hadamard(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank, int skip_mode,
                                  float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream)
 {

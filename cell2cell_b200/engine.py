@@ -12,7 +12,7 @@ import torch
 from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, lib
 
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
-           "plane_contract", "fiber_contract", "launch_count",
+           "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count",
            "mu_update", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "build_ccc", "group_aggregate"]
 
 _vp = ctypes.c_void_p
@@ -146,13 +146,23 @@ def fiber_contract(X, mask, factors, rank, ws=None, out=None):
         return U
 
 
+def mttkrp_from_contraction(TU, shape, factors, rank, mode):
+    """M of ``mode`` from T (leading modes) or U (trailing modes) -- the L2-resident half of the MTTKRP."""
+    with torch.cuda.device(TU.device):
+        M = torch.empty((int(shape[mode]), ldr_of(rank)), dtype=torch.float32, device=TU.device)
+        check(lib().c2c_mttkrp_from_contraction(_ptr(TU), len(shape), _shape_arr(shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                                mode, _ptr(M), _stream()), "c2c_mttkrp_from_contraction")
+        return M
+
+
 def launch_count():
     """Kernels enqueued by libc2c_b200.so so far in this process."""
     return int(lib().c2c_launch_count())
 
 
-def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None):
-    """(G, cp_norm^2): Hadamard product of the factor Grams, skipping ``skip_mode`` (-1: none)."""
+def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None, as_tensor=False):
+    """(G, cp_norm^2): Hadamard product of the factor Grams, skipping ``skip_mode`` (-1: none).  ``as_tensor`` returns the
+    norm as a 1-element fp64 CUDA tensor without synchronising."""
     dev = factors[0].device
     with torch.cuda.device(dev):
         if ws is None:
@@ -162,7 +172,7 @@ def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None):
         n2 = torch.zeros(1, dtype=torch.float64, device=dev)
         check(lib().c2c_gram_hadamard(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr, rank, skip_mode, _ptr(G),
                                       _ptr(n2), ws.ptr, ws.nbytes, _stream()), "c2c_gram_hadamard")
-        return G, float(n2.item())
+        return (G, n2) if as_tensor else (G, float(n2.item()))
 
 
 def mu_update(A, M, G, rank, eps=float(np.finfo(np.float32).eps)):

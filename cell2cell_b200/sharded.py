@@ -1,0 +1,137 @@
+"""One factorization sharded over the GPUs of a box along the first (context) mode  (SURVEY.md section 8e).
+
+Every rank holds a slab ``X[c0:c1]`` of the tensor (contiguous in C order) and the matching rows of the first factor; the
+other factors are replicated.  Per NCP iteration (same Gauss-Seidel order and update as the single-GPU path):
+
+    T      = plane contraction of the local slab                         (local pass 1)
+    mode 0 : M_0 rows of the local contexts are complete locally -> local update; the full A_0 (C x R, tiny) is re-assembled
+             with one all-reduce of a zero-padded buffer so every rank can form the Gram-Hadamard products
+    mode k : (other leading modes) M_k = all-reduce of the per-slab partials (I_k x R fp32, <= 240 KB), replicated update
+    U      = all-reduce of the per-slab fiber contractions (K*K x R fp32)   (local pass 2)
+    trailing modes: replicated updates from the global U; error scalar from the global Grams
+
+i.e. ``N - 1`` small NCCL all-reduces per iteration over NVLink; the tensor itself never moves.  Summation order differs from
+the single-GPU run, so results agree to rounding (well inside the 1e-4 parity budget), not bit for bit.
+
+The orchestration is written against a small ``ops`` interface so that the multi-process logic is testable on CPU
+(gloo) with numpy stand-ins for the kernels (tests/test_sharded.py); ``DeviceOps`` is the product implementation
+(libc2c_b200.so through ``engine``).
+"""
+import numpy as np
+import torch
+
+from . import engine
+from .tensor.cp import CPTensor
+
+__all__ = ["shard_bounds", "DeviceOps", "sharded_non_negative_parafac"]
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous, near-equal split of ``range(n)``: [lo, hi) of ``rank``."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+class DeviceOps:
+    """Kernels of libc2c_b200.so behind the interface the sharded driver needs."""
+
+    def __init__(self, rank_r):
+        self.R = int(rank_r)
+        self._gws = {}
+
+    def pack(self, f, device):
+        return engine.pack_factor(f, self.R, device)
+
+    def unpack(self, a):
+        return engine.unpack_factor(a, self.R)
+
+    def sumsq(self, X):
+        return engine.sumsq(X)
+
+    def plane(self, X, factors, ws):
+        return engine.plane_contract(X, None, factors, self.R, ws=ws)
+
+    def fiber(self, X, factors, ws):
+        return engine.fiber_contract(X, None, factors, self.R, ws=ws)
+
+    def m_from(self, TU, shape, factors, mode):
+        return engine.mttkrp_from_contraction(TU, shape, factors, self.R, mode)
+
+    def gram_hadamard(self, factors, shape, skip):
+        key = (tuple(shape), factors[0].device)
+        if key not in self._gws:
+            self._gws[key] = engine.Workspace(shape, self.R, False, factors[0].device)
+        return engine.gram_hadamard(factors, shape, self.R, skip, ws=self._gws[key], as_tensor=True)
+
+    def mu_update(self, A, M, G):
+        return engine.mu_update(A, M, G, self.R)
+
+    def workspace(self, shape, device):
+        return engine.Workspace(shape, self.R, False, device)
+
+
+def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter_max=100, tol=1e-6, group=None, ops=None,
+                                 cvg_criterion="abs_rec_error"):
+    """MU NCP of a tensor whose first mode is split over the ranks of ``group``.
+
+    X_local: this rank's slab ``[c1 - c0, I_1, ...]`` (``shard_bounds(full_shape[0], world, rank)``), fp32, on the compute
+    device.  init_factors: the FULL initial factors (host arrays, identical on every rank -- e.g. host-seeded random_cp).
+    Returns ``(CPTensor with the full factors, errors)`` on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    me = dist.get_rank(group) if dist.is_initialized() else 0
+    ops = ops or DeviceOps(rank)
+    nd = len(full_shape)
+    dev = X_local.device
+    lo, hi = shard_bounds(full_shape[0], world, me)
+    if X_local.shape[0] != hi - lo:
+        raise ValueError("X_local has %d slices of mode 0, expected %d" % (X_local.shape[0], hi - lo))
+    local_shape = (hi - lo,) + tuple(int(s) for s in full_shape[1:])
+    full_shape = tuple(int(s) for s in full_shape)
+
+    def allreduce(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t
+
+    A_full0 = ops.pack(np.abs(np.asarray(init_factors[0], dtype=np.float64)), dev)         # [C, ldr], replicated
+    A = [None] + [ops.pack(np.abs(np.asarray(f, dtype=np.float64)), dev) for f in init_factors[1:]]
+    A_loc0 = A_full0[lo:hi].clone().contiguous()
+    ws = ops.workspace(local_shape, dev)
+
+    nx2 = torch.tensor([ops.sumsq(X_local)], dtype=torch.float64, device=dev)
+    allreduce(nx2)
+    norm_x2 = float(nx2.item())
+    errors = []
+    eps_rule = (lambda d: abs(d) < tol) if cvg_criterion == "abs_rec_error" else (lambda d: d < tol)
+    for it in range(int(n_iter_max)):
+        loc = [A_loc0] + A[1:]
+        T = ops.plane(X_local, loc, ws)
+        # ---- mode 0: rows of the local contexts ----
+        M0 = ops.m_from(T, local_shape, loc, 0)
+        G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, 0)
+        ops.mu_update(A_loc0, M0, G)
+        A_full0.zero_()
+        A_full0[lo:hi] = A_loc0
+        allreduce(A_full0)
+        # ---- other leading modes: partial M all-reduced, update replicated ----
+        for k in range(1, nd - 2):
+            Mk = ops.m_from(T, local_shape, [A_loc0] + A[1:], k)
+            allreduce(Mk)
+            G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, k)
+            ops.mu_update(A[k], Mk, G)
+        # ---- trailing modes from the all-reduced fiber contraction ----
+        U = ops.fiber(X_local, [A_loc0] + A[1:], ws)
+        allreduce(U)
+        M = None
+        for mode in (nd - 2, nd - 1):
+            M = ops.m_from(U, full_shape, [A_full0] + A[1:], mode)
+            G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, mode)
+            ops.mu_update(A[mode], M, G)
+        _, rn2 = ops.gram_hadamard([A_full0] + A[1:], full_shape, -1)
+        iprod = (ops.unpack(M).double() * ops.unpack(A[nd - 1]).double()).sum()
+        err = float(torch.sqrt(torch.abs(norm_x2 + rn2 - 2.0 * iprod)).item()) / np.sqrt(norm_x2)
+        errors.append(err)
+        if it >= 1 and eps_rule(errors[-2] - errors[-1]):
+            break
+    factors = [ops.unpack(A_full0).cpu().numpy()] + [ops.unpack(a).cpu().numpy() for a in A[1:]]
+    return CPTensor(np.ones(rank, dtype=np.float32), factors, device=dev if dev.type == "cuda" else None), errors

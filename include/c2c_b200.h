@@ -107,6 +107,11 @@ int c2c_fiber_contract(const float* X, const uint8_t* mask, int ndim, const int6
                        const float* const* A /*host array*/, int ldr, int rank, float* U,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* Second half of c2c_mttkrp on its own: M of `mode` from T (mode < ndim - 2) or from U (the two trailing modes).  A sharded
+ * factorization (shards along a leading mode) all-reduces the partial M / U between the halves. */
+int c2c_mttkrp_from_contraction(const float* TU, int ndim, const int64_t* shape /*host*/, const float* const* A /*host array*/,
+                                int ldr, int rank, int mode, float* M, void* stream);
+
 /* ---- K3: Gram / Hadamard ------------------------------------------------------------------------------------------
  * G = prod_{k != skip_mode} A_k^T A_k  (fp32 [ldr x ldr]); rec_norm2 (device double, may be NULL) receives
  * sum_{r,s} prod_{all k} (A_k^T A_k)[r,s] = cp_norm^2.  skip_mode = -1 skips nothing.
