@@ -529,9 +529,16 @@ extern "C" int c2c_build_ccc(const float* expr, const int64_t* expr_off, const i
     const long long ntiles = (P + C2C_BUILD_TILE - 1) / C2C_BUILD_TILE;
     const size_t smem = (size_t)C2C_BUILD_TILE * 2 * K * sizeof(double);
     if (smem > 48 * 1024) return fail(-6, "K = %d too large for the build tile", K);
-    long long grid = ntiles; const long long cap = (long long)sm_count() * 16;
+    long long grid = ntiles; const long long cap = (long long)sm_count() * 8;
     if (grid > cap) grid = cap;
-    build_ccc_kernel<<<(int)grid, C2C_SMALL_THREADS, smem, (cudaStream_t)stream>>>(a);
+    // 'min' aggregates (and plain genes) are exact fp32 values: fp32 staging and scores.  'mean' / 'gmean' keep the fp64 value
+    // the reference would carry into the score (only complexes differ, but the flag is per launch).
+    a.exact = agg_kind == C2C_AGG_MIN ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K % 4 == 0) { if (a.exact) build_ccc_kernel<true, true><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a);
+                      else         build_ccc_kernel<true, false><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a); }
+    else            { if (a.exact) build_ccc_kernel<false, true><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a);
+                      else         build_ccc_kernel<false, false><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a); }
     CKL("build_ccc launch");
     return 0;
 }

@@ -364,9 +364,11 @@ def _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction, communication
     expr = np.concatenate([m.reshape(-1) for m in mats]) if pos else np.zeros(1, np.float32)
     grouped = group_ppi_by is not None
     with_mask = how != "inner" or grouped
+    # no multi-subunit partner in this build -> the aggregation method is irrelevant: take the exact-fp32 ('min') path
+    multi = (idx["a_count"].max(initial=0) > 1) or (idx["b_count"].max(initial=0) > 1)
     X, mask = engine.build_ccc(expr, off, ld, idx["cell_col"], idx["a_first"], idx["a_count"], idx["b_first"],
-                               idx["b_count"], idx["sub_rows"], C, L, K, communication_score, complex_agg_method,
-                               with_mask, dev)
+                               idx["b_count"], idx["sub_rows"], C, L, K, communication_score,
+                               complex_agg_method if multi else "min", with_mask, dev)
     if grouped:
         keys, g_off, g_rows = bi.group_rows(ppi, group_ppi_by)
         X, mask = engine.group_aggregate(X, mask, g_off, g_rows, group_ppi_method)
