@@ -14,6 +14,7 @@
 // Masked: the imputed entries follow the current factors, so T (resp. U) is recomputed before every mode: N passes.
 #include "c2c_contract.cuh"
 #include "c2c_stream.cuh"
+#include "c2c_mma.cuh"
 #include "c2c_small.cuh"
 #include "c2c_update.cuh"
 #include "../../include/c2c_b200.h"
@@ -25,6 +26,9 @@
 #include <cstring>
 
 #define C2C_VERSION 100
+#ifndef C2C_MMA_DEFAULT_MIN_RANK
+#define C2C_MMA_DEFAULT_MIN_RANK 13
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -80,6 +84,10 @@ struct Geo {
     int ps_ok, ps_ns, ps_spw, ps_rs, ps_ring, ps_nwarps, ps_rp, ps_pitch, ps_grid; long long ps_nstage; size_t ps_smem;
     int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_merge, fs_wall, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
     long long max_parts;
+    // tensor-core (TMA + tcgen05) passes, c2c_mma.cuh; mma_ok = 0 -> the FFMA kernels do the pass
+    int mma_ok, mma_n;
+    int pm_nstages, pm_grid, pm_nkb; long long pm_ntiles; size_t pm_smem;
+    int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack; long long fm_nst; size_t fm_smem;
 };
 
 #define C2C_SMEM_BUDGET (200 * 1024)
@@ -185,6 +193,102 @@ static void stream_geometry(Geo& g, int rank)
     }
 }
 
+
+// launch geometry of plane_mma / fiber_mma (c2c_mma.cuh).  Conditions: whole rank in one MMA (R <= 32 here, so that the
+// fused updates apply), in-plane size a multiple of 32 floats (whole swizzle atoms; TMA needs 16-byte row pitches), enough
+// planes to give every SM at least one 128-plane tile.  C2C_B200_NO_MMA=1 turns the path off, C2C_B200_MMA_MIN_RANK sets
+// the smallest rank that takes it.
+#define C2C_MMA_SMEM_BUDGET (225 * 1024)
+static std::atomic<int> g_mma_min_rank{-1};
+static int mma_min_rank()
+{
+    int v = g_mma_min_rank.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* off = getenv("C2C_B200_NO_MMA");
+        const char* e = getenv("C2C_B200_MMA_MIN_RANK");
+        v = (off && off[0] == '1') ? 1 << 30 : (e ? atoi(e) : C2C_MMA_DEFAULT_MIN_RANK);
+        if (v < 1) v = 1;
+        g_mma_min_rank.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+extern "C" int c2c_set_mma_min_rank(int rank)
+{
+    const int prev = mma_min_rank();
+    g_mma_min_rank.store(rank < 1 ? 1 : rank, std::memory_order_relaxed);
+    return prev;
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static int mma_lring() { static int v = -1; if (v < 0) { v = env_int("C2C_B200_MMA_LRING", 3); if (v < 2) v = 2; } return v; }
+static int mma_dbg() { static int v = -1; if (v < 0) v = env_int("C2C_B200_MMA_DBG", 0); return v; }
+
+static int mma_epoch()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("C2C_B200_MMA_EPOCH"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+static void mma_geometry(Geo& g, int rank)
+{
+    g.mma_ok = 0;
+    const int nsm = sm_count();
+    if (rank < mma_min_rank() || rank > 32 || g.nchunk != 1) return;
+    if (g.E % 32 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
+    const int n = rank <= 16 ? 16 : 32;
+    g.mma_n = n;
+    const int ldr = ldr_of(rank);
+    {   // plane_mma: B ring and the factor copies are fixed, the rest of shared memory is the X ring
+        const size_t xb = 128 * 128;
+        const size_t fixed = c2c_plane_mma_smem(n, g.I2, g.I3, 0);
+        if (fixed + 3 * xb > C2C_MMA_SMEM_BUDGET) return;
+        int nx = (int)((C2C_MMA_SMEM_BUDGET - fixed) / (xb + 16));
+        if (nx > 12) nx = 12;
+        g.pm_nstages = nx;
+        g.pm_nkb = (int)(g.E / 32);
+        g.pm_ntiles = (g.P + 127) / 128;
+        g.pm_grid = nsm;                                 // P >= 128 * nsm: a CTA's share spans at least one whole tile
+        g.pm_smem = c2c_plane_mma_smem(n, g.I2, g.I3, nx);
+    }
+    {   // fiber_mma: split the in-plane positions into `es` parts (es divides the SM count when it can) so that the CTA's
+        // running sums and >= 5 X slots of 8 planes fit in shared memory and its accumulators + lo(X) ring in TMEM --
+        // preferably with the stacked B tile (2N accumulator columns per tile)
+        const int na_total = (int)(g.E / 32);
+        int best_es = 0, best_nx = 0, best_stack = 0;
+        // pass 0: stacked B tile with whole-machine splits of <= 2 parts (big stages amortise the per-stage hand-offs);
+        // pass 1: unstacked, >= 5 X slots; pass 2: whatever fits (>= 3 X slots)
+        for (int pass = 0; pass < 3 && best_es == 0; ++pass) {
+            for (int cand = 1; cand <= 8; ++cand) {
+                if (nsm % cand != 0) continue;
+                const int na = (na_total + cand - 1) / cand;
+                if (na < 4) break;
+                const int ntile = (na + 3) / 4;
+                const int stack = ntile * (2 * n + 8 * C2C_MMA_RING2) <= 512;
+                if (pass == 0 && (!stack || cand > 2)) continue;
+                if (ntile > C2C_FM_MAXTILE || ntile * (n + 8 * C2C_MMA_RING2) > 512) continue;
+                const size_t fixed = c2c_fiber_mma_smem(n, na, ldr, 0);
+                if (fixed > C2C_MMA_SMEM_BUDGET) continue;
+                const int fit = (int)((C2C_MMA_SMEM_BUDGET - fixed) / ((size_t)na * 1024 + 16));
+                if (fit >= 5 || (pass == 2 && fit >= 3)) { best_es = cand; best_nx = fit > 12 ? 12 : fit; best_stack = stack; break; }
+            }
+        }
+        if (best_es == 0) return;
+        g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
+        g.fm_nstages = best_nx; g.fm_stack = best_stack;
+        g.fm_nj = nsm / best_es; if (g.fm_nj < 1) return;
+        g.fm_grid = g.fm_nj * best_es;
+        g.fm_nst = (g.P + 7) / 8;
+        g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, ldr, best_nx);
+        if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
+    }
+    g.mma_ok = 1;
+}
+
 static int fiber_geometry(Geo& g, int np2_chunk)
 {
     const int maxT = C2C_FC_MAXTHREADS(np2_chunk);
@@ -237,6 +341,7 @@ static int make_geo(Geo& g, int ndim, const int64_t* shape, int rank)
                     g.I2, g.I3, rank, smem);
     fiber_geometry(g, g.np2);
     stream_geometry(g, rank);
+    mma_geometry(g, rank);
     return 0;
 }
 
@@ -335,6 +440,20 @@ static int plane_grid(const Geo& g, int vec)
 // T[P x ldr] = plane contraction of Xh with the two trailing factors
 static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cudaStream_t st)
 {
+    if (!masked && g.mma_ok && a.p0 == 0 && a.r0 == 0) {
+        CUtensorMap map;
+        const int rc = c2c_make_plane_map(&map, a.X, g.P, g.E);
+        if (rc != 0) return fail(-40, "cuTensorMapEncodeTiled (plane map) failed: %d", rc);
+        PlaneMmaArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.P = g.P; pa.E = (int)g.E; pa.I2 = g.I2; pa.I3 = g.I3; pa.R = a.R; pa.ldr = a.ldr; pa.A2 = a.A2; pa.A3 = a.A3; pa.T = T;
+        pa.done = a.done; pa.nkb = g.pm_nkb; pa.ntiles = g.pm_ntiles; pa.nx = g.pm_nstages; pa.dbg = mma_dbg();
+        CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
+        const cudaError_t e = c2c_launch_plane_mma(g.mma_n, map, pa, g.pm_grid, g.pm_smem, st);
+        if (e != cudaSuccess) return cuda_fail(e, "plane_mma launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     if (!masked && g.ps_ok) {
         StreamArgs sa;
         memset(&sa, 0, sizeof(sa));
@@ -381,7 +500,20 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
     dim3 grid(g.fc_gx, g.fc_gy);
     long long ppc = g.fc_ppc;
     bool legacy = true;
-    if (!masked && g.fs_ok) {
+    if (!masked && g.mma_ok) {
+        CUtensorMap map;
+        const int rc = c2c_make_fiber_map(&map, a.X, g.P, g.E, g.fm_na);
+        if (rc != 0) return fail(-41, "cuTensorMapEncodeTiled (fiber map) failed: %d", rc);
+        FiberMmaArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.P = g.P; fa.E = (int)g.E; fa.R = a.R; fa.ldr = a.ldr; fa.lead = a.lead; fa.part = w.part; fa.done = a.done;
+        fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : (g.fm_stack ? 16 : 8);
+        const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st);
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_mma launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        nparts = g.fm_nj;
+        legacy = false;
+    } else if (!masked && g.fs_ok) {
         StreamArgs sa;
         memset(&sa, 0, sizeof(sa));
         sa.c = a; sa.W = w.W; sa.spw = g.fs_tp; sa.nstage = g.fs_nstage; sa.nwarps = g.fs_ncw; sa.stages_per_cta = g.fs_spc;

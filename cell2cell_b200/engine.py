@@ -12,7 +12,7 @@ import torch
 from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, lib
 
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
-           "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count",
+           "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
            "mu_update", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "build_ccc", "group_aggregate"]
 
 _vp = ctypes.c_void_p
@@ -153,6 +153,11 @@ def mttkrp_from_contraction(TU, shape, factors, rank, mode):
         check(lib().c2c_mttkrp_from_contraction(_ptr(TU), len(shape), _shape_arr(shape), _ptr_arr(factors), ldr_of(rank), rank,
                                                 mode, _ptr(M), _stream()), "c2c_mttkrp_from_contraction")
         return M
+
+
+def set_mma_min_rank(rank):
+    """Smallest rank that takes the tensor-pipe (tcgen05) streaming passes; returns the previous value."""
+    return int(lib().c2c_set_mma_min_rank(int(rank)))
 
 
 def launch_count():

@@ -48,6 +48,11 @@ int c2c_version(void);
 const char* c2c_last_error(void);
 /* kernels this library has enqueued so far in the process (graph replays count every kernel they run) */
 long long c2c_launch_count(void);
+/* Smallest rank whose two streaming passes run on the tensor pipe (TMA + tcgen05.mma kind::tf32, three-term split for
+ * fp32 accuracy) instead of the FFMA kernels; below it the contraction is cheap enough for the CUDA cores to hide under
+ * the HBM stream.  Returns the previous value; a value > 32 turns the tensor-pipe path off.  No counterpart in the
+ * reference (its arithmetic is tensorly's numpy / torch dot, cell2cell/tensor/factorization.py:91-104). */
+int c2c_set_mma_min_rank(int rank);
 
 /* ---- K1: context-wise ligand-receptor score build --------------------------------------------------------------
  * Replaces add_complexes_to_expression (cell2cell/preprocessing/rnaseq.py:176-196), the generate_ccc_tensor loop

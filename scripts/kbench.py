@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--tag", default=os.environ.get("C2C_B200_LIB", "product"))
+    ap.add_argument("--quick", action="store_true", help="only time the two streaming passes (no reference check, no iteration)")
     args = ap.parse_args()
     shape = tuple(args.shape)
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -48,6 +49,12 @@ def main():
         ws = engine.Workspace(shape, R, args.masked, X.device)
         T = engine.plane_contract(X, mask, fs, R, ws=ws)
         U = engine.fiber_contract(X, mask, fs, R, ws=ws)
+        if args.quick:
+            tp = timeit(lambda: engine.plane_contract(X, mask, fs, R, ws=ws, out=T), args.reps)
+            tf = timeit(lambda: engine.fiber_contract(X, mask, fs, R, ws=ws, out=U), args.reps)
+            print(json.dumps({"tag": args.tag, "rank": R, "plane_ms": round(tp, 4), "fiber_ms": round(tf, 4),
+                              "plane_gbs": round(n_x * 4 / tp / 1e6, 1), "fiber_gbs": round(n_x * 4 / tf / 1e6, 1)}), flush=True)
+            continue
         Xh = X.double()
         if args.masked:
             rec = torch.einsum(",".join(l + "r" for l in letters) + "->" + letters, *[f[:, :R].double() for f in fs])

@@ -163,6 +163,66 @@ __global__ void __launch_bounds__(128) mma_kernel(const MmaArgs a)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u));
 }
 
+// ---- A operand from TMEM: lane = row, column = k (32-bit each); written with tcgen05.st by the thread that owns the lane ----
+__global__ void __launch_bounds__(128) mma_ts_kernel(const float* A /*[128][8]*/, const float* B /*[32][32], k < 8 used*/, float* D)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_base_s;
+    unsigned char* sB = smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 4096 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < 32 * 32; i += blockDim.x) {
+        const int r = i >> 5, k = i & 31;
+        const unsigned off = r * 128 + ((((k >> 2) ^ (r & 7))) << 4) + (k & 3) * 4;
+        *reinterpret_cast<float*>(sB + off) = B[i];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(64u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_base_s;
+    {
+        unsigned v[8];
+        for (int k = 0; k < 8; ++k) v[k] = __float_as_uint(A[tid * 8 + k]);
+        const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + 32u;
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const unsigned long long db = make_desc(smem_u32(sB), 16, 1024, 2);
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
+                     ::"r"(tmem), "r"(tmem + 32u), "l"(db), "r"(idesc), "r"(0u) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    unsigned v[32];
+    const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                   "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 32; ++j) D[(warp * 32 + lane) * 32 + j] = __uint_as_float(v[j]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64u));
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -322,6 +382,30 @@ int main()
                 printf("   (want %d..%d)\n", m * 8 + 1, m * 8 + 8);
             }
         }
+    }
+    // ---------------- A from TMEM ----------------
+    {
+        std::vector<float> A8(128 * 8), B(32 * 32, 0.f);
+        for (auto& v : A8) v = (float)(rand() % 17 - 8);
+        for (int n = 0; n < 32; ++n) for (int k = 0; k < 8; ++k) B[n * 32 + k] = (float)(rand() % 17 - 8);
+        float *dA, *dB, *dD;
+        CK(cudaMalloc(&dA, A8.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, 128 * 32 * 4));
+        CK(cudaMemcpy(dA, A8.data(), A8.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(dD, 0xff, 128 * 32 * 4));
+        mma_ts_kernel<<<1, 128, 4096 + 1024>>>(dA, dB, dD);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("{\"test\": \"mma_ts\", \"error\": \"%s\"}\n", cudaGetErrorString(e)); return 2; }
+        std::vector<float> D(128 * 32);
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < 32; ++n) {
+                double ref = 0;
+                for (int k = 0; k < 8; ++k) ref += (double)A8[m * 8 + k] * B[n * 32 + k];
+                if (fabs(ref - D[m * 32 + n]) > 1e-3) { if (bad < 4) printf("  mma_ts mismatch m=%d n=%d got %g want %g\n", m, n, D[m * 32 + n], ref); ++bad; }
+            }
+        printf("{\"test\": \"mma_ts_a_from_tmem\", \"bad\": %d}\n", bad);
     }
     // ---------------- trunc ----------------
     {

@@ -477,3 +477,56 @@ def test_full_size_build_roundtrip():
         assert ulp_distance(t.tensor[c, l].cpu().numpy(), want).max() <= 1
     t2 = InteractionTensor(mats, ppi, how="inner", communication_score="expression_gmean", complex_sep="&", verbose=False)
     assert t2.mask is None and torch.equal(t.tensor, t2.tensor)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensor-pipe streaming passes (TMA + tcgen05.mma kind::tf32 with the three-term split, c2c_mma.cuh): taken when the rank
+# reaches c2c_set_mma_min_rank, the in-plane size is a multiple of 32 and there are >= 128 planes per SM
+# ----------------------------------------------------------------------------------------------------------------------
+MMA_SHAPES = [(40, 500, 16, 8), (25, 801, 8, 32), (19000, 16, 16), (10, 1900, 40, 40)]
+
+
+@pytest.fixture
+def mma_from_rank_1():
+    from cell2cell_b200 import engine
+    prev = engine.set_mma_min_rank(1)
+    yield
+    engine.set_mma_min_rank(prev)
+
+
+@pytest.mark.parametrize("shape", MMA_SHAPES)
+@pytest.mark.parametrize("rank", [1, 5, 16, 20, 32])
+def test_mma_passes_match_einsum(shape, rank, mma_from_rank_1):
+    """T and U of the tensor-pipe passes against float64 einsum (every mode's MTTKRP is derived from them)."""
+    from cell2cell_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    X = torch.rand(shape, generator=g, device="cuda") * (torch.rand(shape, generator=g, device="cuda") > 0.3)
+    fs = [engine.pack_factor(torch.rand((s, rank), generator=g, device="cuda"), rank, X.device) for s in shape]
+    n0 = engine.launch_count()
+    T = engine.plane_contract(X, None, fs, rank)
+    U = engine.fiber_contract(X, None, fs, rank)
+    assert engine.launch_count() - n0 == 3            # plane_mma, fiber_mma, fiber_reduce: no FFMA tail kernels
+    letters = "abcdefgh"[: len(shape)]
+    lead, tr = letters[:-2], letters[-2:]
+    f64 = [f[:, :rank].double() for f in fs]
+    Tw = torch.einsum(letters + "," + tr[0] + "r," + tr[1] + "r->" + lead + "r", X.double(), f64[-2], f64[-1]).reshape(-1, rank)
+    Uw = torch.einsum(letters + "," + ",".join(l + "r" for l in lead) + "->" + tr + "r", X.double(), *f64[:-2]).reshape(-1, rank)
+    eT = float((T[:, :rank].double() - Tw).norm() / Tw.norm())
+    eU = float((U[:, :rank].double() - Uw).norm() / Uw.norm())
+    assert eT < 2e-6 and eU < 2e-6, (eT, eU)
+    # padding columns of T / U stay zero (the factor updates read whole float4 rows)
+    ldr = engine.ldr_of(rank)
+    if ldr > rank:
+        assert float(T[:, rank:].abs().max()) == 0.0 and float(U[:, rank:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape,rank,n_iter", [((40, 500, 16, 8), 16, 30), ((40, 500, 16, 8), 20, 30), ((25, 801, 8, 32), 5, 30),
+                                               ((19000, 16, 16), 32, 15)])
+def test_mma_ncp_matches_oracle(shape, rank, n_iter, mma_from_rank_1):
+    """Whole factorization through the tensor-pipe passes against the float64 oracle: factors and error within 1e-4."""
+    _compare_run(lowrank(shape, 6, seed=11), rank, n_iter)
+
+
+def test_mma_full_size_rank20():
+    """BASELINE config 4 at its named rank (60 x 2000 x 40 x 40, rank 20): default dispatch takes the tensor-pipe passes."""
+    test_full_size_properties((60, 2000, 40, 40), 20)
