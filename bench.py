@@ -40,6 +40,15 @@ WORKLOADS = {
 METRIC = "NCP iterations/s at 60x2000x40x40 rank 10"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh).get(kernel)
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -165,7 +174,7 @@ def run_ours(args, rank_id, local_rank, world):
     wl = WORKLOADS[args.workload]
     shape, rank, iters = wl["shape"], wl["rank"], args.iters
     n_x = int(np.prod(shape))
-    x_host = synth_host(shape, 1 + rank_id)
+    x_host = synth_host(shape, 1)                  # the tensor is replicated: every GPU holds the same data, seeds differ
     X = x_host.to(dev, non_blocking=True)
     torch.cuda.synchronize()
     ws = engine.Workspace(shape, rank, False, dev)
@@ -221,6 +230,40 @@ def run_ours(args, rank_id, local_rank, world):
     e2e_sec = e0.elapsed_time(e1) * 1e-3
     d2h = sum(s * rank * 4 for s in shape) * 2 + iters * 8
 
+    # ---- second metric of BASELINE.json: elbow sweep wall seconds (ranks 1..25 x 10 runs, 100 fixed iterations each) ------
+    elbow = None
+    if args.elbow:
+        t = PreBuiltTensor(X, order_names=names)
+        t.elbow_rank_selection(upper_rank=2, runs=2, init="random", random_state=1, n_iter_max=5, tol=-1.0, output_fig=False,
+                               automatic_elbow=False)
+        barrier()
+        t0 = time.perf_counter()
+        _, loss = t.elbow_rank_selection(upper_rank=args.elbow_ranks, runs=args.elbow_runs, init="random", random_state=888,
+                                         n_iter_max=iters, tol=-1.0, output_fig=False, automatic_elbow=False, manual_elbow=None)
+        barrier()
+        elbow = {"wall_s": time.perf_counter() - t0, "upper_rank": args.elbow_ranks, "runs": args.elbow_runs,
+                 "iterations_per_run": iters, "n_gpus": world,
+                 "loss_rank1": float(loss[0][1]), "loss_last": float(loss[-1][1]),
+                 "note": "independent (rank, seed) factorizations spread over the GPUs, fixed iteration count (tol = -1)"}
+        del t
+
+    # ---- config 4's own rank (20): the tensor-pipe passes --------------------------------------------------------------------
+    r20 = None
+    if args.workload == "atlas":
+        ws20 = engine.Workspace(shape, 20, False, dev)
+        f20 = [[engine.pack_factor(np.random.RandomState(7 + k).random_sample((s, 20)).astype(np.float32), 20, dev) for s in shape]
+               for k in range(2)]
+        engine.ncp_run(X, None, f20[0], 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        engine.ncp_run(X, None, f20[1], 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20, sync=False)
+        a1.record()
+        torch.cuda.synchronize()
+        r20 = {"rank": 20, "iterations_per_s_per_gpu": iters / (a0.elapsed_time(a1) * 1e-3),
+               "passes": "plane_mma / fiber_mma (TMA + tcgen05.mma kind::tf32, 3-term split)"}
+        del ws20, f20
+
     # ---- per-kernel roofline (rank 0 only reports) ---------------------------------------------------------------------
     f = fresh_factors(1)
     T = torch.empty((int(np.prod(shape[:-2])), engine.ldr_of(rank)), dtype=torch.float32, device=dev)
@@ -239,7 +282,7 @@ def run_ours(args, rank_id, local_rank, world):
     total_iters = world * args.steps * iters
     value = total_iters / sec
     worst = max(t_plane, t_fiber)
-    name = "plane_contract" if t_plane >= t_fiber else "fiber_contract (+ partial reduce)"
+    name = "plane_stream" if t_plane >= t_fiber else "fiber_stream"
     line = {
         "metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
@@ -256,7 +299,7 @@ def run_ours(args, rank_id, local_rank, world):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": name, "achieved": n_x * 4 / worst / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": n_x * 4 / worst / 1e9 / peak, "traffic": None, "peak_kind": "of " + peak_kind,
+                     "frac": n_x * 4 / worst / 1e9 / peak, "traffic": ncu_traffic(name), "peak_kind": "of " + peak_kind,
                      "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
                      "plane_contract_gbs": n_x * 4 / t_plane / 1e9, "fiber_contract_gbs": n_x * 4 / t_fiber / 1e9,
                      "iteration": {"algorithmic_bytes": 4 * n_x * 4, "achieved_gbs": 4 * n_x * 4 * value / world / 1e9,
@@ -264,6 +307,10 @@ def run_ours(args, rank_id, local_rank, world):
                                    "passes_made": 2}},
         "final_rec_error": final_err,
     }
+    if elbow is not None:
+        line["elbow_sweep"] = elbow
+    if r20 is not None:
+        line["rank20"] = r20
     if not args.no_cpu:
         from threadpoolctl import threadpool_info
         threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
@@ -332,6 +379,9 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=2, help="CPU iterations per step of the reference arm / cpu_baseline")
     ap.add_argument("--ref-warm", action="store_true", help="also run the warm-up steps on the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-elbow", dest="elbow", action="store_false", help="skip the elbow-sweep wall time (second BASELINE metric)")
+    ap.add_argument("--elbow-ranks", type=int, default=25)
+    ap.add_argument("--elbow-runs", type=int, default=10)
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="N > 1: independent factorizations per GPU (weak scaling, default) or ONE factorization sharded along "
                          "the context mode with NCCL all-reduces of the MTTKRP / Gram partials (strong scaling)")

@@ -67,12 +67,13 @@ def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, ver
     errors, n_iter, converged = engine.ncp_run(X, M, factors, rank, tf_type=algo, n_iter_max=int(n_iter_max),
                                                tol=float(tol) if tol else -1.0, cvg_criterion=cvg_criterion,
                                                check_every=check_every)
+    sums = None
     if M is None and n_iter > 0:
         # The per-iteration errors are tensorly's Gram form sqrt(|nx2 + rn2 - 2 ip|) / sqrt(nx2): in fp32 it cancels once
         # the error is small.  The last one -- the value cell2cell keeps (tensor.py:311-315, factorization.py:262,356) --
         # is replaced by the directly accumulated ||X - rec|| / ||X|| (one extra fused pass, fp64 sums), which is what the
         # fp64 reference's Gram form equals.
-        s = engine.recon_sums(X, None, factors, rank)
+        s = sums = engine.recon_sums(X, None, factors, rank)
         errors = np.array(errors, dtype=np.float64)
         errors[-1] = np.sqrt(s[1]) / np.sqrt(s[3])
     if verbose:
@@ -82,6 +83,8 @@ def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, ver
             print("PARAFAC converged after {} iterations".format(n_iter))
     out = [engine.unpack_factor(f, rank).cpu().numpy() for f in factors]
     cp = CPTensor(np.ones(rank, dtype=np.float32), out, device=X.device)
+    if sums is not None:
+        cp.recon_sums_ = sums          # [sum d, sum d^2, sum x, sum x^2, n] of this tensor and these factors (explained_variance)
     if return_errors:
         return cp, [np.float64(e) for e in errors]
     return cp

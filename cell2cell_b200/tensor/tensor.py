@@ -292,13 +292,15 @@ class BaseTensor:
         assert self.tl_object is not None, "Must run compute_tensor_factorization before using this method."
         weights, factors = self.tl_object
         rank = int(np.asarray(factors[0]).shape[1])
-        fs = []
-        for i, f in enumerate(factors):
-            f = np.asarray(f, dtype=np.float64)
-            if i == 0:
-                f = f * np.asarray(weights, dtype=np.float64)[None, :]
-            fs.append(engine.pack_factor(f.astype(np.float32), rank, self.tensor.device))
-        s = engine.recon_sums(self.tensor, self.mask, fs, rank)
+        s = getattr(self.tl_object, "recon_sums_", None)        # left by the factorization's own final pass over this tensor
+        if s is None or self.mask is not None:
+            fs = []
+            for i, f in enumerate(factors):
+                f = np.asarray(f, dtype=np.float64)
+                if i == 0:
+                    f = f * np.asarray(weights, dtype=np.float64)[None, :]
+                fs.append(engine.pack_factor(f.astype(np.float32), rank, self.tensor.device))
+            s = engine.recon_sums(self.tensor, self.mask, fs, rank)
         n = float(self.tensor.numel())
         sum_d, sum_dd, sum_x, sum_xx = s[0], s[1], s[2], s[3]
         if self.mask is not None:
@@ -443,13 +445,21 @@ class PreBuiltTensor(BaseTensor):
         if device is None and isinstance(t, torch.Tensor) and t.is_cuda:
             device = t.device
         X = as_device_tensor(t, device)                  # NaN / inf survive the cast to fp32; scanned on the device
-        nan = torch.isnan(X)
-        if loc_nans is not None:
-            assert tuple(loc_nans.shape) == tuple(X.shape), "`loc_nans` and `tensor` must be of the same shape"
-            nan = nan | (torch.as_tensor(np.asarray(loc_nans)).to(X.device) > 0)
-        self._loc_nans = nan.to(torch.uint8)
-        self._loc_zeros = ((X == 0) & ~nan).to(torch.uint8)
-        self.tensor = torch.nan_to_num(X)
+        # one reduction pass decides whether the clean-up passes (loc_nans, nan_to_num: tensor.py:933-946) are needed at all
+        finite = bool(torch.isfinite(X).all())
+        if finite and loc_nans is None:
+            self._loc_nans = None                         # derived on first use: all zeros
+            self._loc_zeros = None                        # derived on first use: (tensor == 0)
+            self._no_nans = True
+            self.tensor = X
+        else:
+            nan = torch.isnan(X)
+            if loc_nans is not None:
+                assert tuple(loc_nans.shape) == tuple(X.shape), "`loc_nans` and `tensor` must be of the same shape"
+                nan = nan | (torch.as_tensor(np.asarray(loc_nans)).to(X.device) > 0)
+            self._loc_nans = nan.to(torch.uint8)
+            self._loc_zeros = ((X == 0) & ~nan).to(torch.uint8)
+            self.tensor = torch.nan_to_num(X)
         self.mask = as_device_mask(mask, self.tensor)
         self.order_names = order_names
         if order_labels is None:
@@ -461,6 +471,8 @@ class PreBuiltTensor(BaseTensor):
 
     @property
     def loc_nans(self):
+        if self._loc_nans is None and getattr(self, "_no_nans", False):
+            self._loc_nans = torch.zeros(self.tensor.shape, dtype=torch.uint8, device=self.tensor.device)
         return self._loc_nans
 
     @loc_nans.setter
