@@ -376,6 +376,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="atlas", choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=100, help="NCP iterations per step (the reference's n_iter_max)")
+    ap.add_argument("--rank", type=int, default=None, help="override the workload's rank (side experiments; the metric is quoted at its default)")
     ap.add_argument("--ref-iters", type=int, default=2, help="CPU iterations per step of the reference arm / cpu_baseline")
     ap.add_argument("--ref-warm", action="store_true", help="also run the warm-up steps on the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -386,6 +387,8 @@ def main():
                     help="N > 1: independent factorizations per GPU (weak scaling, default) or ONE factorization sharded along "
                          "the context mode with NCCL all-reduces of the MTTKRP / Gram partials (strong scaling)")
     args = ap.parse_args()
+    if args.rank is not None:
+        WORKLOADS[args.workload] = dict(WORKLOADS[args.workload], rank=args.rank)
     rank_id = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

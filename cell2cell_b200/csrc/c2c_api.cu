@@ -906,7 +906,7 @@ extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, con
     if (g.nchunk > 1) {
         recon_sums_generic_kernel<<<C2C_SUMS_BLOCKS, 256, 0, st>>>(X, mask, g.P, g.I2, g.I3, a.lead, a.A2, a.A3, rank, ldr, w.sums_part);
         CKL("recon_sums (generic) launch");
-        sum_partials_kernel<<<1, 32, 0, st>>>(w.sums_part, C2C_SUMS_BLOCKS, 5, 5, out);
+        sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, C2C_SUMS_BLOCKS, 5, 5, out);
         CKL("recon_sums reduce launch");
         return 0;
     }
@@ -918,7 +918,7 @@ extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, con
                   : vec == 2 ? c2c_launch_sums_v2(g.np2, a, grid, smem, st) : c2c_launch_sums_v1(g.np2, a, grid, smem, st);
     if (e != cudaSuccess) return cuda_fail(e, "recon_sums launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    sum_partials_kernel<<<1, 32, 0, st>>>(w.sums_part, grid, 5, 5, out);
+    sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, grid, 5, 5, out);
     CKL("recon_sums reduce launch");
     return 0;
 }

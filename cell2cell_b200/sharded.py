@@ -101,9 +101,11 @@ def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter
     nx2 = torch.tensor([ops.sumsq(X_local)], dtype=torch.float64, device=dev)
     allreduce(nx2)
     norm_x2 = float(nx2.item())
-    errors = []
     eps_rule = (lambda d: abs(d) < tol) if cvg_criterion == "abs_rec_error" else (lambda d: d < tol)
-    for it in range(int(n_iter_max)):
+    err_dev = torch.zeros(1, dtype=torch.float64, device=dev)            # this iteration's error, written by `iteration`
+    errors_dev = torch.zeros(max(int(n_iter_max), 1), dtype=torch.float64, device=dev)
+
+    def iteration():
         loc = [A_loc0] + A[1:]
         T = ops.plane(X_local, loc, ws)
         # ---- mode 0: rows of the local contexts ----
@@ -129,9 +131,48 @@ def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter
             ops.mu_update(A[mode], M, G)
         _, rn2 = ops.gram_hadamard([A_full0] + A[1:], full_shape, -1)
         iprod = (ops.unpack(M).double() * ops.unpack(A[nd - 1]).double()).sum()
-        err = float(torch.sqrt(torch.abs(norm_x2 + rn2 - 2.0 * iprod)).item()) / np.sqrt(norm_x2)
-        errors.append(err)
-        if it >= 1 and eps_rule(errors[-2] - errors[-1]):
-            break
+        err_dev.copy_((torch.sqrt(torch.abs(norm_x2 + rn2 - 2.0 * iprod)) / np.sqrt(norm_x2)).reshape(1))
+
+    # On CUDA the iteration (kernels + the N - 1 NCCL all-reduces) is captured once into a CUDA graph and replayed: no
+    # per-iteration host work besides the replay; the error history stays on the device.  With a real stop rule (tol > 0)
+    # the history is read back after every iteration so that the run ends on the iteration the reference ends on; with a
+    # fixed iteration count (tol <= 0) it is read once at the end.  Off-device (the gloo tests with numpy stand-ins) it
+    # runs eagerly.
+    graph = None
+    check_every = 1 if tol > 0 else int(n_iter_max)
+    n_done = 0
+    if dev.type == "cuda" and int(n_iter_max) >= 3:
+        iteration()                                                    # eager first iteration: lazy initialisations happen here
+        errors_dev[0].copy_(err_dev[0])
+        n_done = 1
+        torch.cuda.synchronize(dev)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                iteration()
+        except Exception:                                              # capture not possible here: stay eager
+            graph = None
+            torch.cuda.synchronize(dev)
+    errors = []
+    it = n_done
+    stop = False
+    if n_done:
+        errors = errors_dev[:n_done].cpu().numpy().tolist()
+    while it < int(n_iter_max) and not stop:
+        if graph is not None:
+            graph.replay()
+        else:
+            iteration()
+        errors_dev[it].copy_(err_dev[0])
+        it += 1
+        if graph is None or it % check_every == 0 or it == int(n_iter_max):
+            hist = errors_dev[:it].cpu().numpy().tolist()
+            for k in range(max(len(errors), 1), it):
+                if eps_rule(hist[k - 1] - hist[k]):
+                    hist = hist[:k + 1]
+                    stop = True
+                    break
+            errors = hist
     factors = [ops.unpack(A_full0).cpu().numpy()] + [ops.unpack(a).cpu().numpy() for a in A[1:]]
     return CPTensor(np.ones(rank, dtype=np.float32), factors, device=dev if dev.type == "cuda" else None), errors

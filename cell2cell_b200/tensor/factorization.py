@@ -66,7 +66,7 @@ def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, ver
     # tensorly records no errors when tol is falsy; the reference would then fail on errors[-1] -- we always record them.
     errors, n_iter, converged = engine.ncp_run(X, M, factors, rank, tf_type=algo, n_iter_max=int(n_iter_max),
                                                tol=float(tol) if tol else -1.0, cvg_criterion=cvg_criterion,
-                                               check_every=check_every)
+                                               check_every=check_every, norm_x2=getattr(X, "_c2c_norm_x2", None))
     sums = None
     if M is None and n_iter > 0:
         # The per-iteration errors are tensorly's Gram form sqrt(|nx2 + rn2 - 2 ip|) / sqrt(nx2): in fp32 it cancels once

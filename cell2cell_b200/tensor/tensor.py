@@ -445,8 +445,12 @@ class PreBuiltTensor(BaseTensor):
         if device is None and isinstance(t, torch.Tensor) and t.is_cuda:
             device = t.device
         X = as_device_tensor(t, device)                  # NaN / inf survive the cast to fp32; scanned on the device
-        # one reduction pass decides whether the clean-up passes (loc_nans, nan_to_num: tensor.py:933-946) are needed at all
-        finite = bool(torch.isfinite(X).all())
+        # one reduction pass decides whether the clean-up passes (loc_nans, nan_to_num: tensor.py:933-946) are needed at all:
+        # sum(x^2) is finite only if every entry is (it is also the ||X||^2 the factorization needs, so it is kept)
+        nx2 = engine.sumsq(X)
+        finite = bool(np.isfinite(nx2))
+        if finite:
+            X._c2c_norm_x2 = nx2
         if finite and loc_nans is None:
             self._loc_nans = None                         # derived on first use: all zeros
             self._loc_zeros = None                        # derived on first use: (tensor == 0)
