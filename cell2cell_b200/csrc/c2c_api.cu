@@ -437,8 +437,18 @@ static int plane_grid(const Geo& g, int vec)
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// how a pass is launched inside the captured iteration
+struct PassOpts {
+    int pdl;                   // programmatic dependent launch: the pass may start under its predecessor (it waits before reading factors)
+    bool t_zeroed;             // plane_mma: T was cleared by the previous fiber_mma (else a memset is enqueued)
+    float* zero_T;             // fiber_mma: buffer to clear for the next plane_mma, `zero_n` floats
+    long long zero_n;
+};
+static const PassOpts kPlainPass = {0, false, nullptr, 0};
+static int use_pdl() { static int v = -1; if (v < 0) v = env_int("C2C_B200_NO_PDL", 0) ? 0 : 1; return v; }
+
 // T[P x ldr] = plane contraction of Xh with the two trailing factors
-static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cudaStream_t st)
+static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cudaStream_t st, const PassOpts& po = kPlainPass)
 {
     if (!masked && g.mma_ok && a.p0 == 0 && a.r0 == 0) {
         CUtensorMap map;
@@ -448,8 +458,8 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
         memset(&pa, 0, sizeof(pa));
         pa.P = g.P; pa.E = (int)g.E; pa.I2 = g.I2; pa.I3 = g.I3; pa.R = a.R; pa.ldr = a.ldr; pa.A2 = a.A2; pa.A3 = a.A3; pa.T = T;
         pa.done = a.done; pa.nkb = g.pm_nkb; pa.ntiles = g.pm_ntiles; pa.nx = g.pm_nstages; pa.dbg = mma_dbg();
-        CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
-        const cudaError_t e = c2c_launch_plane_mma(g.mma_n, map, pa, g.pm_grid, g.pm_smem, st);
+        if (!po.t_zeroed) CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
+        const cudaError_t e = c2c_launch_plane_mma(g.mma_n, map, pa, g.pm_grid, g.pm_smem, st, po.t_zeroed ? po.pdl : 0);
         if (e != cudaSuccess) return cuda_fail(e, "plane_mma launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;
@@ -460,10 +470,10 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
         sa.c = a; sa.c.out = T; sa.W = nullptr; sa.spw = g.ps_spw; sa.rs = g.ps_rs; sa.nring = g.ps_ring; sa.nstage = g.ps_nstage; sa.rp = g.ps_rp; sa.nwarps = g.ps_nwarps;
         const int block = 32 * g.ps_nwarps;
         sa.pitch = g.ps_pitch;
-        const cudaError_t e = g.vec_plane == 4 ? (g.ps_ns == 2 ? c2c_launch_plane_stream_v4_s2(g.np2, sa, g.ps_grid, block, g.ps_smem, st)
-                                                               : c2c_launch_plane_stream_v4_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st))
-                            : g.vec_plane == 2 ? c2c_launch_plane_stream_v2_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st)
-                                               : c2c_launch_plane_stream_v1_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st);
+        const cudaError_t e = g.vec_plane == 4 ? (g.ps_ns == 2 ? c2c_launch_plane_stream_v4_s2(g.np2, sa, g.ps_grid, block, g.ps_smem, st, po.pdl)
+                                                               : c2c_launch_plane_stream_v4_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st, po.pdl))
+                            : g.vec_plane == 2 ? c2c_launch_plane_stream_v2_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st, po.pdl)
+                                               : c2c_launch_plane_stream_v1_s1(g.np2, sa, g.ps_grid, block, g.ps_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "plane_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         a.p0 = g.ps_nstage * g.ps_spw;                 // the tail (< one stage of planes) goes to the register-staged kernel
@@ -492,7 +502,7 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
 }
 
 // U[E x ldr] = fiber contraction of Xh with the Khatri-Rao rows of the leading factors (partials + fixed-order reduce)
-static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, cudaStream_t st)
+static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, cudaStream_t st, const PassOpts& po = kPlainPass)
 {
     const int vec = g.vec_fiber;
     a.out = w.part;
@@ -508,7 +518,8 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         memset(&fa, 0, sizeof(fa));
         fa.P = g.P; fa.E = (int)g.E; fa.R = a.R; fa.ldr = a.ldr; fa.lead = a.lead; fa.part = w.part; fa.done = a.done;
         fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : (g.fm_stack ? 16 : 8);
-        const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st);
+        fa.zero_ptr = reinterpret_cast<float4*>(po.zero_T); fa.zero_n4 = po.zero_n / 4;
+        const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_mma launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         nparts = g.fm_nj;
@@ -518,10 +529,10 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         memset(&sa, 0, sizeof(sa));
         sa.c = a; sa.W = w.W; sa.spw = g.fs_tp; sa.nstage = g.fs_nstage; sa.nwarps = g.fs_ncw; sa.stages_per_cta = g.fs_spc;
         const int block = 32 * (g.fs_ncw + 1);
-        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st)
-                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st))
-                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st)
-                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st);
+        const cudaError_t e = vec == 4 ? (g.fs_ns == 2 ? c2c_launch_fiber_stream_v4_s2(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st, po.pdl)
+                                                       : c2c_launch_fiber_stream_v4_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st, po.pdl))
+                            : vec == 2 ? c2c_launch_fiber_stream_v2_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st, po.pdl)
+                                       : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         nparts = (long long)g.fs_grid * (g.fs_merge ? 1 : g.fs_nslots);
@@ -559,8 +570,12 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         }
     }
     const long long n4 = g.E * a.ldr / 4;
-    fiber_reduce2_kernel<<<(int)((n4 + 31) / 32), 256, 0, st>>>(w.part, (int)nparts, n4, a.R, a.ldr, w.U, a.done);
-    CKL("fiber_reduce launch");
+    {
+        const cudaError_t e = c2c_launch_ex(fiber_reduce2_kernel, dim3((unsigned)((n4 + 31) / 32)), dim3(256), 0, st, legacy ? 0 : po.pdl,
+                                            (const float*)w.part, (int)nparts, n4, a.R, a.ldr, w.U, a.done);
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_reduce launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return 0;
 }
 
@@ -942,6 +957,8 @@ extern "C" int c2c_cp_normalize(float* const* A, int ndim, const int64_t* shape,
 struct RunCtx {
     Geo g; Ws w; const float* X; const uint8_t* mask; float* const* A; int ldr, R, algo, n_iter_max; double tol; int cvg;
     const double* normX2; double* errors; int* state; cudaStream_t st; float eps;
+    int pdl;                   // launch the fused unmasked iteration's kernels as programmatic dependents
+    bool mma_zero;             // plane_mma / fiber_mma: T is kept cleared by the fiber pass
 };
 
 static int update_mode(const RunCtx& c, int mode, bool last)
@@ -988,8 +1005,11 @@ static int launch_lead_update(const RunCtx& c, int mode)
     const int njr = tpr / (c.ldr / 4);
     if (njr < 1) return fail(-30, "rank too large for the fused update");
     const size_t smem = (((size_t)(c.R * c.R + nrc * c.ldr) * sizeof(float) + 7) & ~(size_t)7) + (size_t)nrc * njr * c.ldr * sizeof(double);
-    lead_update_kernel<<<(int)grid, block, smem, c.st>>>(u, tpr);
-    CKL("lead_update launch");
+    {
+        const cudaError_t e = c2c_launch_ex(lead_update_kernel, dim3((unsigned)grid), dim3(block), smem, c.st, c.pdl, u, tpr);
+        if (e != cudaSuccess) return cuda_fail(e, "lead_update launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return 0;
 }
 
@@ -1020,8 +1040,11 @@ static int launch_trail_update(const RunCtx& c, int which_begin, int which_end)
             set_for = 200 * 1024;
         }
     }
-    trail_update_kernel<<<1, C2C_TU_THREADS, smem, c.st>>>(u);
-    CKL("trail_update launch");
+    {
+        const cudaError_t e = c2c_launch_ex(trail_update_kernel, dim3(1), dim3(C2C_TU_THREADS), smem, c.st, c.pdl, u);
+        if (e != cudaSuccess) return cuda_fail(e, "trail_update launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return 0;
 }
 
@@ -1051,8 +1074,11 @@ static int enqueue_iteration(const RunCtx& c)
             ContractArgs a = base_args(g, c.X, c.mask, A, c.ldr, c.R, done);
             bool masked = has_mask;
             if ((rc = maybe_impute(g, a, masked, c.w, c.st)) != 0) return rc;
-            if (mode < nlead) { if ((rc = launch_plane(g, a, masked, c.w.T, c.st)) != 0) return rc; }
-            else              { if ((rc = launch_fiber(g, a, masked, c.w, c.st)) != 0) return rc; }
+            PassOpts po = kPlainPass;
+            po.pdl = c.pdl;
+            if (c.mma_zero) { po.t_zeroed = true; po.zero_T = c.w.T; po.zero_n = g.P * c.ldr; }
+            if (mode < nlead) { if ((rc = launch_plane(g, a, masked, c.w.T, c.st, po)) != 0) return rc; }
+            else              { if ((rc = launch_fiber(g, a, masked, c.w, c.st, po)) != 0) return rc; }
         }
         if (fused_updates(c)) {
             if (mode < nlead) { if ((rc = launch_lead_update(c, mode)) != 0) return rc; }
@@ -1106,16 +1132,28 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
     }
     if (n_iter_max == 0) return 0;
 
-    // one iteration is captured once and replayed: ~15 launches per iteration become one graph launch
+    // The fused unmasked iteration is a chain of kernels only: they are launched as programmatic dependents (every kernel
+    // waits for its predecessor before it touches that predecessor's results, so a streaming pass fills its ring while the
+    // update kernel before it is still running).  On the tensor-pipe path T is cleared once here and then by every fiber pass.
+    c.pdl = (use_pdl() && fused && mask == nullptr) ? 1 : 0;
+    c.mma_zero = g.mma_ok && mask == nullptr;
+    if (c.mma_zero) CK(cudaMemsetAsync(c.w.T, 0, (size_t)g.P * ldr * sizeof(float), st), "memset T");
+
+    // `unroll` iterations are captured once and replayed: ~6 launches per iteration become a fraction of a graph launch, and
+    // the dependent launches also link one iteration to the next
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     bool use_graph = n_iter_max >= 3;
-    long long per_iter = 0;
+    int unroll = 1;
+    if (use_graph && n_iter_max >= 10 && (check_every <= 0 || check_every >= 5))
+        for (int u = 5; u >= 2; --u) if (n_iter_max % u == 0 && (check_every <= 0 || check_every % u == 0)) { unroll = u; break; }
+    long long per_graph = 0;
     if (use_graph) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
             (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone))
             use_graph = false;                                        // the caller is capturing: just enqueue
     }
+    if (!use_graph) unroll = 1;
     if (use_graph) {
         // captured on a private stream (the caller's may be the legacy default stream, which cannot capture) and replayed
         // on the caller's stream
@@ -1125,9 +1163,10 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
         if (e != cudaSuccess) { cudaStreamDestroy(cap); return cuda_fail(e, "begin capture"); }
         const long long before = g_launches.load(std::memory_order_relaxed);
         RunCtx cc = c; cc.st = cap;
-        rc = enqueue_iteration(cc);
-        per_iter = g_launches.load(std::memory_order_relaxed) - before;
-        g_launches.fetch_sub(per_iter, std::memory_order_relaxed);     // captured, not executed
+        rc = 0;
+        for (int u = 0; u < unroll && rc == 0; ++u) rc = enqueue_iteration(cc);
+        per_graph = g_launches.load(std::memory_order_relaxed) - before;
+        g_launches.fetch_sub(per_graph, std::memory_order_relaxed);    // captured, not executed
         e = cudaStreamEndCapture(cap, &graph);
         cudaStreamDestroy(cap);
         if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1137,13 +1176,14 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
     }
     int host_state[2] = {0, 0};
     rc = 0;
-    for (int it = 0; it < n_iter_max; ++it) {
+    for (int it = 0; it < n_iter_max; it += unroll) {
         if (use_graph) {
             cudaError_t e = cudaGraphLaunch(exec, st);
             if (e != cudaSuccess) { rc = cuda_fail(e, "graph launch"); break; }
-            g_launches.fetch_add(per_iter, std::memory_order_relaxed);
+            g_launches.fetch_add(per_graph, std::memory_order_relaxed);
         } else if ((rc = enqueue_iteration(c)) != 0) break;
-        if (check_every > 0 && (it + 1) % check_every == 0 && it + 1 < n_iter_max) {
+        const int done_it = it + unroll;
+        if (check_every > 0 && done_it % check_every == 0 && done_it < n_iter_max) {
             cudaError_t e = cudaMemcpyAsync(host_state, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) { rc = cuda_fail(e, "poll state"); break; }

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define C2C_MAX_DIMS 8
 #define C2C_MAX_LEAD (C2C_MAX_DIMS - 2)
@@ -40,6 +41,12 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     // packed fp32x2 FMA (sm_100 FFMA2): half the issue slots of two FFMAs
     return __ffma2_rn(a, b, c);
 }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and its
+// writes are visible (a no-op without the attribute), pdl_trigger() lets the successor's CTAs be scheduled from now on.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ bool run_done(const int* done) {
     return done != nullptr && *reinterpret_cast<const volatile int*>(done) != 0;
@@ -90,4 +97,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// host: launch with (pdl != 0) or without the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t c2c_launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }

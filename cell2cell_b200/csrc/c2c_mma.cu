@@ -2,37 +2,35 @@
 #include "c2c_mma.cuh"
 
 template <int N>
-static cudaError_t launch_plane_n(const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st)
+static cudaError_t launch_plane_n(const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
     cudaError_t e = cudaFuncSetAttribute(plane_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    plane_mma_kernel<N><<<grid, C2C_MMA_THREADS, smem, st>>>(map, a);
-    return cudaGetLastError();
+    return c2c_launch_ex(plane_mma_kernel<N>, dim3(grid), dim3(C2C_MMA_THREADS), smem, st, pdl, map, a);
 }
 
 template <int N, bool STACK>
-static cudaError_t launch_fiber_n(const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st)
+static cudaError_t launch_fiber_n(const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
     cudaError_t e = cudaFuncSetAttribute(fiber_mma_kernel<N, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fiber_mma_kernel<N, STACK><<<grid, C2C_MMA_THREADS, smem, st>>>(map, a);
-    return cudaGetLastError();
+    return c2c_launch_ex(fiber_mma_kernel<N, STACK>, dim3(grid), dim3(C2C_MMA_THREADS), smem, st, pdl, map, a);
 }
 
-cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st)
+cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
     switch (n) {
-        case 16: return launch_plane_n<16>(map, a, grid, smem, st);
-        case 32: return launch_plane_n<32>(map, a, grid, smem, st);
+        case 16: return launch_plane_n<16>(map, a, grid, smem, st, pdl);
+        case 32: return launch_plane_n<32>(map, a, grid, smem, st, pdl);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st)
+cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
     switch (n) {
-        case 16: return stack ? launch_fiber_n<16, true>(map, a, grid, smem, st) : launch_fiber_n<16, false>(map, a, grid, smem, st);
-        case 32: return stack ? launch_fiber_n<32, true>(map, a, grid, smem, st) : launch_fiber_n<32, false>(map, a, grid, smem, st);
+        case 16: return stack ? launch_fiber_n<16, true>(map, a, grid, smem, st, pdl) : launch_fiber_n<16, false>(map, a, grid, smem, st, pdl);
+        case 32: return stack ? launch_fiber_n<32, true>(map, a, grid, smem, st, pdl) : launch_fiber_n<32, false>(map, a, grid, smem, st, pdl);
         default: return cudaErrorInvalidValue;
     }
 }

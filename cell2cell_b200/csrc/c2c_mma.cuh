@@ -161,8 +161,6 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + NR);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < I2 * N; i += blockDim.x) { const int s = i / N, n = i - s * N; A2s[i] = n < R ? a.A2[(size_t)s * ldr + n] : 0.0f; }
-    for (int i = tid; i < I3 * N; i += blockDim.x) { const int s = i / N, n = i - s * N; A3s[i] = n < R ? a.A3[(size_t)s * ldr + n] : 0.0f; }
     if (tid == 0) {
         for (int s = 0; s < DX; ++s) { mbar_init(fullx + s, 1); mbar_init(emptyx + s, 1); }
         for (int s = 0; s < D2; ++s) { mbar_init(ready + s, 4); mbar_init(empty2 + s, 1); }
@@ -242,6 +240,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
         const int lg = warp & 3;
         int r = 0; unsigned phr = 0;
         long long g = g0;
+        pdl_wait();
         while (g < g1) {
             const long long tile = g / nkb;
             const long long tile_end = (tile + 1) * nkb;
@@ -284,6 +283,14 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
         const int q = (warp - C2C_MMA_PREP_WARP0) >> 2, lq = warp & 3;
         const int tg = ((warp - C2C_MMA_PREP_WARP0) & 3) * 32 + lane;          // thread index inside the group, 0..127
         const long long nitem = g1 - g0;
+        // the trailing factors come from the previous kernel (the TMA producer is already filling the X ring)
+        pdl_wait();
+        {
+            const int tp = tid - 32 * C2C_MMA_PREP_WARP0, np = 128 * C2C_MMA_PREP_GROUPS;
+            for (int i = tp; i < I2 * N; i += np) { const int s = i / N, n = i - s * N; A2s[i] = n < R ? a.A2[(size_t)s * ldr + n] : 0.0f; }
+            for (int i = tp; i < I3 * N; i += np) { const int s = i / N, n = i - s * N; A3s[i] = n < R ? a.A3[(size_t)s * ldr + n] : 0.0f; }
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * C2C_MMA_PREP_GROUPS) : "memory");
+        }
         for (long long t = q; t < nitem; t += C2C_MMA_PREP_GROUPS) {
             const long long g = g0 + t;
             const long long tile = g / nkb; const int kb = (int)(g - tile * nkb);
@@ -354,6 +361,8 @@ struct FiberMmaArgs {
     int dbg;                   // timing experiments only (see PlaneMmaArgs)
     int epoch;                 // stages per accumulator chain
     long long nst_total;       // 8-plane stages: ceil(P / 8)
+    float4* zero_ptr;          // optional: buffer this pass clears for the next plane_mma (T, no longer read once the leading
+    long long zero_n4;         // modes are updated), in float4 units; the epilogue warps do it while the stream runs
 };
 
 // STACK: hi(x) hi(w) and hi(x) lo(w) in one MMA over the stacked B tile (needs 2N accumulator columns per tile)
@@ -468,6 +477,12 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
         const int lg = warp & 3;
         unsigned phe = 0;
         bool first = true;
+        pdl_wait();
+        if (a.zero_ptr != nullptr) {
+            const long long per = (a.zero_n4 + gridDim.x - 1) / gridDim.x;
+            const long long z0 = (long long)blockIdx.x * per, z1 = z0 + per < a.zero_n4 ? z0 + per : a.zero_n4;
+            for (long long i = z0 + (warp - 2) * 32 + lane; i < z1; i += 128) a.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (long long g = sb; g < se; ) {
             const long long ep_end = g + F < se ? g + F : se;
             for (int i = 0; i < ntile; ++i) {
@@ -533,6 +548,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
         const int q = (warp - C2C_MMA_PREP_WARP0) >> 2, lq = warp & 3;
         const int tg = ((warp - C2C_MMA_PREP_WARP0) & 3) * 32 + lane;
         const long long nitem = se - sb;
+        pdl_wait();                          // the leading factors come from the previous kernel
         for (long long t = q; t < nitem; t += C2C_MMA_PREP_GROUPS) {
             const long long g = sb + t;
             const int sx = (int)(t % DX), s2 = (int)(t % D2);
@@ -586,8 +602,8 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
 }
 
 // launchers (c2c_mma.cu); n = MMA N in {16, 32}
-cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st);
-cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st);
+cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
+cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
 size_t c2c_plane_mma_smem(int n, int I2, int I3, int nx);
 size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);
 // tensor maps over X: [P][E] rows of 32 floats (128-byte swizzle) / {32, P, E/32} (32-byte-atom 128-byte swizzle)

@@ -116,14 +116,6 @@ plane_stream_kernel(const StreamArgs sa)
     float* stage0 = reinterpret_cast<float*>(smem_raw + off);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < I2 * rp; i += blockDim.x) {
-        const int s = i / rp, r = i - s * rp;
-        sA2[i] = r < R ? a.A2[(size_t)s * ldr + r] : 0.0f;
-    }
-    for (int i = threadIdx.x; i < I3 * rp; i += blockDim.x) {
-        const int s = i / rp, r = i - s * rp;
-        sA3[i] = r < R ? a.A3[(size_t)s * ldr + r] : 0.0f;
-    }
     unsigned long long* mybar = bars + warp * S;
     float* mystage = stage0 + (size_t)warp * S * stage_floats;
     const unsigned stage_bytes = (unsigned)((size_t)sa.spw * chunk_floats * sizeof(float));
@@ -155,6 +147,16 @@ plane_stream_kernel(const StreamArgs sa)
     }
     __syncwarp();
     for (int j = 0; j < S && pg < sa.nstage; ++j) issue();
+    // the tensor does not depend on the previous kernel: the ring is already filling while that kernel finishes
+    pdl_wait();
+    for (int i = threadIdx.x; i < I2 * rp; i += blockDim.x) {
+        const int s = i / rp, r = i - s * rp;
+        sA2[i] = r < R ? a.A2[(size_t)s * ldr + r] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < I3 * rp; i += blockDim.x) {
+        const int s = i / rp, r = i - s * rp;
+        sA3[i] = r < R ? a.A3[(size_t)s * ldr + r] : 0.0f;
+    }
     __syncthreads();                     // A2 / A3 copies visible; the only CTA-wide barrier
 
     const int nsets = I3 / (VEC * NS);   // strip sets per plane row
@@ -297,6 +299,7 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
         const unsigned xb = (unsigned)(x_floats * sizeof(float));
         const int q4 = ldr >> 2, nitems = tp * q4;
         int slot = 0; unsigned phase = 0; bool wrapped = false;
+        if (!w_all) pdl_wait();          // the per-stage Khatri-Rao rows read the factors the previous kernel wrote
         for (long long g = sb; g < se; ++g) {
             if (wrapped) mbar_wait(empty + slot, phase ^ 1u);
             float* dst = stage0 + (size_t)slot * stage_floats;
@@ -335,6 +338,7 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
 #pragma unroll
             for (int q = 0; q < NP2; ++q) acc[n][j][q] = make_float2(0.0f, 0.0f);
     const int e_i = (int)E, step = nslots * e_i, wstep = nslots * ldr, noff = nthr * VEC;
+    pdl_wait();                          // (the producer warp is already streaming the tensor)
     if (w_all) {
         // Khatri-Rao rows of this CTA's planes, built by the consumer warps while the first stages are in flight
         const int q4 = ldr >> 2;
@@ -439,6 +443,6 @@ fiber_stream_kernel(const StreamArgs sa, const int nthr /* threads per slot */, 
 // launchers: (VEC, NS) in {(4,1), (4,2), (2,1), (1,1)}; NS = 2 instances exist for NP2 <= C2C_NS2_MAXNP2 only
 #define C2C_NS2_MAXNP2 10
 #define C2C_DECL_STREAM(V, N)                                                                                       \
-    cudaError_t c2c_launch_plane_stream_v##V##_s##N(int np2, const StreamArgs& a, int grid, int block, size_t smem, cudaStream_t st); \
-    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st);
+    cudaError_t c2c_launch_plane_stream_v##V##_s##N(int np2, const StreamArgs& a, int grid, int block, size_t smem, cudaStream_t st, int pdl); \
+    cudaError_t c2c_launch_fiber_stream_v##V##_s##N(int np2, const StreamArgs& a, int nthr, int nslots, int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st, int pdl);
 C2C_DECL_STREAM(4, 1) C2C_DECL_STREAM(4, 2) C2C_DECL_STREAM(2, 1) C2C_DECL_STREAM(1, 1)

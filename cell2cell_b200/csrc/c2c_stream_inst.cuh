@@ -9,7 +9,8 @@
         e = cudaFuncSetAttribute(plane_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N>,                                 \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
         if (e != cudaSuccess) return e;                                                                             \
-        plane_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N><<<grid, block, smem, st>>>(a);                             \
+        e = c2c_launch_ex(plane_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N>, dim3(grid), dim3(block), smem, st, pdl, a); \
+        if (e != cudaSuccess) return e;                                                                             \
         break;
 
 #define C2C_FS_CASE(N)                                                                                              \
@@ -17,7 +18,8 @@
         e = cudaFuncSetAttribute(fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N>,                                 \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                           \
         if (e != cudaSuccess) return e;                                                                             \
-        fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N><<<grid, block, smem, st>>>(a, nthr, nslots, merge, w_all);               \
+        e = c2c_launch_ex(fiber_stream_kernel<C2C_INST_VEC, C2C_INST_NS, N>, dim3(grid), dim3(block), smem, st, pdl, a, nthr, nslots, merge, w_all); \
+        if (e != cudaSuccess) return e;                                                                             \
         break;
 
 #if C2C_INST_NS == 2
@@ -27,7 +29,7 @@
 #endif
 
 cudaError_t C2C_SCAT(c2c_launch_plane_stream_v, C2C_INST_VEC, _s, C2C_INST_NS)(int np2, const StreamArgs& a, int grid, int block,
-                                                                               size_t smem, cudaStream_t st)
+                                                                               size_t smem, cudaStream_t st, int pdl)
 {
     cudaError_t e = cudaSuccess;
     switch (np2) {
@@ -38,7 +40,7 @@ cudaError_t C2C_SCAT(c2c_launch_plane_stream_v, C2C_INST_VEC, _s, C2C_INST_NS)(i
 }
 
 cudaError_t C2C_SCAT(c2c_launch_fiber_stream_v, C2C_INST_VEC, _s, C2C_INST_NS)(int np2, const StreamArgs& a, int nthr, int nslots,
-                                                                               int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st)
+                                                                               int merge, int w_all, int grid, int block, size_t smem, cudaStream_t st, int pdl)
 {
     cudaError_t e = cudaSuccess;
     switch (np2) {

@@ -50,6 +50,8 @@ __device__ __forceinline__ void hadamard_to_smem(const double* Snew, const doubl
 __global__ void __launch_bounds__(1024)
 lead_update_kernel(const LeadUpdArgs a, const int tpr)
 {
+    pdl_trigger();
+    pdl_wait();
     if (run_done(a.done)) return;
     extern __shared__ __align__(16) unsigned char lu_smem[];
     const int R = a.R, ldr = a.ldr, q4 = ldr >> 2, LL = ldr * ldr;
@@ -200,6 +202,8 @@ __device__ __forceinline__ double block_sum_1024(double v, double* red /*[32]*/)
 __global__ void __launch_bounds__(C2C_TU_THREADS, 1)
 trail_update_kernel(const TrailUpdArgs a)
 {
+    pdl_trigger();
+    pdl_wait();
     if (run_done(a.done)) return;
     extern __shared__ __align__(16) unsigned char tu_smem[];
     const int R = a.R, ldr = a.ldr, I2 = a.I2, I3 = a.I3, N = a.N, LL = ldr * ldr, RR = R * R;
