@@ -958,6 +958,8 @@ struct RunCtx {
     Geo g; Ws w; const float* X; const uint8_t* mask; float* const* A; int ldr, R, algo, n_iter_max; double tol; int cvg;
     const double* normX2; double* errors; int* state; cudaStream_t st; float eps;
     int pdl;                   // launch the fused unmasked iteration's kernels as programmatic dependents
+    int rr, nruns;             // batched runs: nruns independent factorizations of rank rr side by side (R = rr * nruns)
+    int* run_flags; int* run_iters;
     bool mma_zero;             // plane_mma / fiber_mma: T is kept cleared by the fiber pass
 };
 
@@ -993,6 +995,7 @@ static int launch_lead_update(const RunCtx& c, int mode)
     memset(&u, 0, sizeof(u));
     u.T = c.w.T; fill_lead(u.lead, g, (const float* const*)c.A); u.k = mode; u.P = g.P; u.R = c.R; u.ldr = c.ldr; u.N = g.ndim;
     u.A = c.A[mode]; u.S = c.w.S; u.state = c.state; u.eps = c.eps; u.done = c.state + 1;
+    u.rr = c.rr; u.run_flags = c.nruns > 1 ? c.run_flags : nullptr;
     const long long I = g.shape[mode];
     const long long cnt = g.P / I;                                   // planes carrying one index of this mode
     const int block = cnt >= 1024 ? 1024 : 256;
@@ -1032,6 +1035,7 @@ static int launch_trail_update(const RunCtx& c, int which_begin, int which_end)
     u.S = c.w.S; u.eps = c.eps; u.which_begin = which_begin; u.which_end = which_end;
     u.normX2 = c.normX2; u.errors = c.errors; u.state = c.state; u.n_iter_max = c.n_iter_max; u.tol = c.tol; u.cvg = c.cvg;
     u.done = c.state + 1;
+    u.rr = c.rr; u.nruns = c.nruns; u.run_flags = c.nruns > 1 ? c.run_flags : nullptr; u.run_iters = c.run_iters;
     const size_t smem = trail_update_smem(g, c.R, c.ldr, &u.u_in_smem);
     if (smem > 48 * 1024) {
         static thread_local size_t set_for = 0;
@@ -1089,9 +1093,10 @@ static int enqueue_iteration(const RunCtx& c)
     return 0;
 }
 
-extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
-                           int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
-                           double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
+static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
+                        int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
+                        double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream,
+                        int rank_per_run, int nruns)
 {
     RunCtx c; int rc;
     if (!shape) return fail(-1, "shape is NULL");
@@ -1110,7 +1115,12 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
     cudaStream_t st = c.st;
     const Geo& g = c.g;
 
-    CK(cudaMemsetAsync(state, 0, 2 * sizeof(int), st), "memset state");
+    c.rr = rank_per_run; c.nruns = nruns; c.run_flags = state + 2; c.run_iters = state + 2 + nruns;
+    if (nruns > 1) {
+        if (nruns > 32 || rank_per_run * nruns != rank) return fail(-26, "batched runs: need rank = rank_per_run * nruns and nruns <= 32");
+        if (algo != C2C_ALGO_MU || mask != nullptr) return fail(-27, "batched runs: multiplicative updates without a mask only");
+    }
+    CK(cudaMemsetAsync(state, 0, (size_t)(nruns > 1 ? 2 + 2 * nruns : 2) * sizeof(int), st), "memset state");
     CK(cudaMemsetAsync(c.w.flags, 0, 4 * sizeof(int), st), "memset flags");
     if (normX2) c.normX2 = normX2;
     else {
@@ -1119,6 +1129,7 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
     }
     // Grams of the initial factors (fused updates: into bank 1, bank 0 cleared for iteration 0); G for mode 0
     const bool fused = fused_updates(c);
+    if (nruns > 1 && !fused) return fail(-28, "batched runs need the fused update kernels (rank <= 32, small trailing modes)");
     const size_t bank = (size_t)ndim * ldr * ldr;
     if (fused) CK(cudaMemsetAsync(c.w.S, 0, bank * sizeof(double), st), "memset Gram bank");
     for (int k = 0; k < ndim; ++k) {
@@ -1197,4 +1208,21 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
         if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
     }
     return rc;
+}
+
+extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
+                           int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
+                           double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
+{
+    return ncp_run_impl(X, mask, ndim, shape, A, ldr, rank, algo, n_iter_max, tol, cvg_criterion, normX2, errors, state,
+                        check_every, ws, ws_bytes, stream, rank, 1);
+}
+
+extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, int rank_per_run,
+                                   int nruns, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
+                                   double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
+{
+    if (rank_per_run < 1 || nruns < 1) return fail(-26, "batched runs: rank_per_run and nruns must be >= 1");
+    return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, rank_per_run * nruns, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
+                        normX2, errors, state, check_every, ws, ws_bytes, stream, rank_per_run, nruns);
 }

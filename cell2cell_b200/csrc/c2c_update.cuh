@@ -31,17 +31,21 @@ struct LeadUpdArgs {
     int rows_per_cta;
     float eps;
     const int* done;
+    // batched runs: the R columns are R / rr independent factorizations of rank rr each (rr = R: one run).  Columns of
+    // different runs do not interact (their Gram-Hadamard entries are taken as zero); a run whose flag is set is frozen.
+    int rr;
+    const int* run_flags;      // [R / rr] or null
 };
 
-// G[q][r] = prod_{j < k} Snew_j[q][r] * prod_{j > k} Sold_j[q][r] into shared memory (float), R x R
-__device__ __forceinline__ void hadamard_to_smem(const double* Snew, const double* Sold, int N, int k, int R, int ldr, float* sG)
+// G[q][r] = prod_{j < k} Snew_j[q][r] * prod_{j > k} Sold_j[q][r] into shared memory (float), R x R; zero across runs
+__device__ __forceinline__ void hadamard_to_smem(const double* Snew, const double* Sold, int N, int k, int R, int ldr, int rr, float* sG)
 {
     for (int t = threadIdx.x; t < R * R; t += blockDim.x) {
         const int q = t / R, r = t - q * R;
         double g = 1.0;
         for (int j = 0; j < N; ++j)
             if (j != k) g *= (j < k ? Snew : Sold)[(size_t)j * ldr * ldr + q * ldr + r];
-        sG[t] = (float)g;
+        sG[t] = (q / rr == r / rr) ? (float)g : 0.0f;
     }
 }
 
@@ -65,7 +69,7 @@ lead_update_kernel(const LeadUpdArgs a, const int tpr)
     double* Snew = a.S + (size_t)par * a.N * LL;
     const double* Sold = a.S + (size_t)(par ^ 1) * a.N * LL;
 
-    hadamard_to_smem(Snew, Sold, a.N, a.k, R, ldr, sG);
+    hadamard_to_smem(Snew, Sold, a.N, a.k, R, ldr, a.rr, sG);
 
     const int dk = a.lead.dim[a.k];
     int inner = 1;
@@ -151,6 +155,7 @@ lead_update_kernel(const LeadUpdArgs a, const int tpr)
                 float den = 0.0f;
                 for (int q = 0; q < R; ++q) den = fmaf(arow[q], sG[q * R + r], den);
                 nv = arow[r] * fmaxf((float)m, a.eps) / fmaxf(den, a.eps);
+                if (a.run_flags != nullptr && a.run_flags[r / a.rr]) nv = arow[r];          // this run has stopped
             }
             sNew[rslot * ldr + r] = nv;
         }
@@ -186,6 +191,9 @@ struct TrailUpdArgs {
     int which_begin, which_end; // trailing modes updated by this launch: [0, 2) = both (unmasked), [0, 1) / [1, 2) = one (masked)
     const double* normX2; double* errors; int* state; int n_iter_max; double tol; int cvg;
     const int* done;
+    // batched runs (see LeadUpdArgs): errors is [nruns][n_iter_max], run_flags / run_iters are [nruns]
+    int rr, nruns;
+    int* run_flags; int* run_iters;
 };
 
 __device__ __forceinline__ double block_sum_1024(double v, double* red /*[32]*/)
@@ -234,6 +242,9 @@ trail_update_kernel(const TrailUpdArgs a)
     for (int t = threadIdx.x; t < I2 * R; t += blockDim.x) sA2[t] = a.A2[(size_t)(t / R) * ldr + (t % R)];
     for (int t = threadIdx.x; t < I3 * R; t += blockDim.x) sA3[t] = a.A3[(size_t)(t / R) * ldr + (t % R)];
     double iprod = 0.0;
+    __shared__ double s_ip[32], s_rn[32];                      // per-run <M, A> and ||rec||^2 (batched runs)
+    if (threadIdx.x < 32) { s_ip[threadIdx.x] = 0.0; s_rn[threadIdx.x] = 0.0; }
+    const int rr = a.rr;
     __syncthreads();
 
     for (int which = a.which_begin; which < a.which_end; ++which) {
@@ -245,7 +256,7 @@ trail_update_kernel(const TrailUpdArgs a)
         for (int t = threadIdx.x; t < RR; t += blockDim.x) {
             double g = 1.0;
             for (int j = 0; j < N; ++j) if (j != mode) g *= sS[(size_t)j * RR + t];
-            sG[t] = (float)g;
+            sG[t] = ((t / R) / rr == (t % R) / rr) ? (float)g : 0.0f;
         }
         // M[i, r] = sum_j U[e(i, j), r] * O[j, r]
         for (int t = threadIdx.x; t < I * R; t += blockDim.x) {
@@ -274,8 +285,10 @@ trail_update_kernel(const TrailUpdArgs a)
             float den = 0.0f;
             for (int q = 0; q < R; ++q) den = fmaf(sA[i * R + q], sG[q * R + r], den);
             const float m = sM[t];
-            const float nv = sA[t] * fmaxf(m, a.eps) / fmaxf(den, a.eps);
+            float nv = sA[t] * fmaxf(m, a.eps) / fmaxf(den, a.eps);
+            if (a.run_flags != nullptr && a.run_flags[r / rr]) nv = sA[t];                    // this run has stopped
             ip += (double)m * (double)nv;
+            if (a.nruns > 1 && which == 1) atomicAdd(&s_ip[r / rr], (double)m * (double)nv);
             gA[(size_t)i * ldr + r] = nv;
             nv_keep[nk & 1] = nv;
         }
@@ -303,6 +316,39 @@ trail_update_kernel(const TrailUpdArgs a)
     // the bank the next iteration accumulates into
     for (int t = threadIdx.x; t < N * LL; t += blockDim.x) Sold[t] = 0.0;
     // reconstruction error (Gram form), stop rule, iteration counter
+    if (a.nruns > 1) {
+        // batched runs: one error / stop decision per run
+        for (int pr = threadIdx.x; pr < RR; pr += blockDim.x) {
+            const int q = pr / R, r = pr - q * R;
+            if (q / rr == r / rr) {
+                double g = 1.0;
+                for (int j = 0; j < N; ++j) g *= sS[(size_t)j * RR + pr];
+                atomicAdd(&s_rn[q / rr], g);
+            }
+        }
+        __syncthreads();
+        const int it = a.state[0];
+        if (threadIdx.x < a.nruns && a.errors && !a.run_flags[threadIdx.x]) {
+            const int b = threadIdx.x;
+            const double nx2 = *a.normX2;
+            const double err = sqrt(fabs(nx2 + s_rn[b] - 2.0 * s_ip[b])) / sqrt(nx2);
+            double* eb = a.errors + (size_t)b * a.n_iter_max;
+            if (it < a.n_iter_max) eb[it] = err;
+            a.run_iters[b] = it + 1;
+            if (it >= 1) {
+                const double dec = eb[it - 1] - err;
+                if (a.cvg == 0 ? (fabs(dec) < a.tol) : (dec < a.tol)) a.run_flags[b] = 1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int all = 1;
+            for (int b = 0; b < a.nruns; ++b) all &= (a.run_flags[b] != 0);
+            if (all) a.state[1] = 1;
+            a.state[0] = it + 1;
+        }
+        return;
+    }
     iprod = block_sum_1024(iprod, red);
     double t = 0.0;
     for (int pr = threadIdx.x; pr < RR; pr += blockDim.x) {

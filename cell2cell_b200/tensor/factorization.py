@@ -90,6 +90,32 @@ def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, ver
     return cp
 
 
+def _factorize_batch(X, rank, seeds, n_iter_max, tol, cvg_criterion="abs_rec_error", check_every=10):
+    """The runs ``seeds`` of one rank, as one batched device factorization (``c2c_ncp_run_batched``): one read of the tensor
+    per pass serves every run.  Same results as ``len(seeds)`` calls of ``non_negative_parafac(init='random')`` (the runs do
+    not interact; each has its own error history and stop iteration).  Returns ``[(CPTensor, errors), ...]``."""
+    rank, nruns = int(rank), len(seeds)
+    host = [initialize_factors(X, rank, init="random", random_state=sd) for sd in seeds]           # [run][mode]
+    packed = [engine.pack_factor(np.concatenate([host[b][m].astype(np.float32) for b in range(nruns)], axis=1), rank * nruns,
+                                 X.device) for m in range(X.dim())]
+    errors, iters = engine.ncp_run_batched(X, packed, rank, nruns, n_iter_max=int(n_iter_max), tol=float(tol) if tol else -1.0,
+                                           cvg_criterion=cvg_criterion, check_every=check_every,
+                                           norm_x2=getattr(X, "_c2c_norm_x2", None))
+    out = []
+    for b in range(nruns):
+        fs = [engine.pack_factor(p[:, b * rank:(b + 1) * rank], rank, X.device) for p in packed]
+        errs = np.array(errors[b, :int(iters[b])], dtype=np.float64)
+        sums = None
+        if len(errs):
+            sums = engine.recon_sums(X, None, fs, rank)                  # the kept error is the directly accumulated one
+            errs[-1] = np.sqrt(sums[1]) / np.sqrt(sums[3])
+        cp = CPTensor(np.ones(rank, dtype=np.float32), [engine.unpack_factor(f, rank).cpu().numpy() for f in fs], device=X.device)
+        if sums is not None:
+            cp.recon_sums_ = sums
+        out.append((cp, [np.float64(e) for e in errs]))
+    return out
+
+
 def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-7, random_state=None,
                          verbose=0, normalize_factors=False, return_errors=False, mask=None,
                          cvg_criterion="abs_rec_error", fixed_modes=None):
@@ -170,7 +196,7 @@ def _run_elbow_analysis(tensor, upper_rank=50, tf_type="non_negative_cp", init="
 
 def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_negative_cp", init="svd",
                                   svd="truncated_svd", metric="error", random_state=None, mask=None, n_iter_max=100,
-                                  tol=10e-7, verbose=False, **kwargs):
+                                  tol=10e-7, verbose=False, batch_runs=True, **kwargs):
     """``runs`` factorizations per rank; ndarray (runs x upper_rank) of losses (factorization.py:272-373).
 
     The ``upper_rank * runs`` units are independent; when ``torch.distributed`` is initialised they are spread over the
@@ -182,27 +208,53 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
     kwargs["return_errors"] = True
     X = as_device_tensor(tensor)
     M = as_device_mask(mask, X)
-    units = [(r, run) for r in range(1, upper_rank + 1) for run in range(runs)]
+    # Runs of one rank are independent; as many as fit 32 factor columns are factorized side by side, so one read of the
+    # tensor per pass serves all of them (MU, unmasked, host-seeded random init: what the elbow analysis uses by default).
+    batchable = (tf_type == "non_negative_cp" and M is None and init == "random" and random_state is not None and
+                 set(kwargs) <= {"return_errors", "cvg_criterion"} and X.dim() >= 3 and batch_runs)
+    units = []
+    for r in range(1, upper_rank + 1):
+        per = max(1, min(runs, 32 // r)) if batchable else 1
+        for b0 in range(0, runs, per):
+            units.append((r, list(range(b0, min(runs, b0 + per)))))
 
     def one(unit):
-        r, run = unit
-        seed = None if random_state is None else random_state + run
-        tl_object, errors = _compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=seed,
-                                                          mask=M, n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs)
+        r, idx = unit
+        res = None
+        if len(idx) > 1:
+            try:
+                res = _factorize_batch(X, r, [random_state + run for run in idx], n_iter_max, tol,
+                                       cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
+            except C2CError:
+                res = None                       # shape outside the fused update kernels: run by run on the device instead
+        if res is None and len(idx) > 1:
+            res = [_compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=random_state + run,
+                                                 mask=M, n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs) for run in idx]
+        elif res is None:
+            seed = None if random_state is None else random_state + idx[0]
+            res = [_compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=seed, mask=M,
+                                                 n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs)]
         if metric == "error":
-            return float(_loss_of(X, tl_object, errors, M))
-        return tl_object
+            return [float(_loss_of(X, tl, errs, M)) for tl, errs in res]
+        return [tl for tl, errs in res]
 
+    def cost(unit):
+        cols = unit[0] * len(unit[1])
+        return 1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)
+
+    parts = run_units(units, one, cost=cost, gather="object")
+    flat = {}
+    for (r, idx), vals in zip(units, parts):
+        for run, v in zip(idx, vals):
+            flat[(r, run)] = v
     if metric == "error":
-        vals = run_units(units, one, cost=lambda u: u[0], gather="float")
-        all_loss = np.asarray(vals, dtype=np.float64).reshape(upper_rank, runs)
+        all_loss = np.asarray([[flat[(r, run)] for run in range(runs)] for r in range(1, upper_rank + 1)], dtype=np.float64)
     else:
         from .metrics import pairwise_correlation_index
         from scipy.spatial.distance import squareform
-        objs = run_units(units, one, cost=lambda u: u[0], gather="object")
         rows = []
-        for i in range(upper_rank):
-            fs = [objs[i * runs + j].factors for j in range(runs)]
+        for r in range(1, upper_rank + 1):
+            fs = [flat[(r, run)].factors for run in range(runs)]
             rows.append((1.0 - squareform(pairwise_correlation_index(fs))).tolist())
         all_loss = np.asarray(rows, dtype=np.float64)
     return all_loss.T

@@ -530,3 +530,41 @@ def test_mma_ncp_matches_oracle(shape, rank, n_iter, mma_from_rank_1):
 def test_mma_full_size_rank20():
     """BASELINE config 4 at its named rank (60 x 2000 x 40 x 40, rank 20): default dispatch takes the tensor-pipe passes."""
     test_full_size_properties((60, 2000, 40, 40), 20)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# batched runs (c2c_ncp_run_batched): the runs of one rank side by side, one read of the tensor per pass for all of them
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,rank,nruns", [((6, 50, 8, 8), 3, 5), ((12, 1054, 6, 6), 4, 8), ((40, 500, 16, 8), 6, 5),
+                                              ((40, 500, 16, 8), 16, 2), ((5, 7, 3, 3), 1, 10)])
+@pytest.mark.parametrize("tol", [-1.0, 2e-4])
+def test_batched_runs_match_single_runs(shape, rank, nruns, tol):
+    """Every run of a batch equals the same run factorized alone: factors, error history, stop iteration."""
+    from cell2cell_b200.tensor.factorization import _factorize_batch, as_device_tensor, non_negative_parafac
+    x = lowrank(shape, 4, seed=21)
+    X = as_device_tensor(x)
+    seeds = [300 + 7 * b for b in range(nruns)]
+    n_iter = 40
+    batch = _factorize_batch(X, rank, seeds, n_iter, tol, check_every=5)
+    assert len(batch) == nruns
+    n_its = set()
+    for (cp_b, err_b), seed in zip(batch, seeds):
+        cp_s, err_s = non_negative_parafac(X, rank, n_iter_max=n_iter, init="random", tol=tol, random_state=seed, return_errors=True)
+        assert len(err_b) == len(err_s), (len(err_b), len(err_s))
+        n_its.add(len(err_b))
+        # the per-iteration values are the fp32 Gram form (cancels at the 1e-6 level, see _compare_run); the kept last one is direct
+        np.testing.assert_allclose(err_b, err_s, rtol=2e-5, atol=5e-6)
+        assert abs(err_b[-1] - err_s[-1]) <= 2e-5 * err_s[-1]
+        for a, b in zip(cp_b.factors, cp_s.factors):
+            assert a.shape == b.shape and rel_err(a, b) < FACTOR_RTOL, rel_err(a, b)
+    if tol < 0:
+        assert n_its == {n_iter}
+
+
+def test_batched_elbow_equals_unbatched_elbow():
+    from cell2cell_b200.tensor.factorization import _multiple_runs_elbow_analysis
+    x = lowrank((12, 300, 6, 6), 4, seed=5)
+    a = _multiple_runs_elbow_analysis(x, upper_rank=7, runs=4, init="random", random_state=11, n_iter_max=25, tol=-1.0)
+    b = _multiple_runs_elbow_analysis(x, upper_rank=7, runs=4, init="random", random_state=11, n_iter_max=25, tol=-1.0, batch_runs=False)
+    assert a.shape == b.shape == (4, 7)
+    np.testing.assert_allclose(a, b, rtol=2e-5)
