@@ -85,7 +85,8 @@ struct Geo {
     int fs_ok, fs_ns, fs_tp, fs_nthr, fs_nslots, fs_merge, fs_wall, fs_ncw, fs_grid; long long fs_nstage, fs_spc; size_t fs_smem;
     long long max_parts;
     // tensor-core (TMA + tcgen05) passes, c2c_mma.cuh; mma_ok = 0 -> the FFMA kernels do the pass
-    int mma_ok, mma_n;
+    int mma_ok, mma_n;         // mma_ok: plane_mma applies;  mma_fiber_ok: fiber_mma applies too
+    int mma_fiber_ok;
     int pm_nstages, pm_grid, pm_nkb; long long pm_ntiles; size_t pm_smem;
     int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack; long long fm_nst; size_t fm_smem;
 };
@@ -195,7 +196,8 @@ static void stream_geometry(Geo& g, int rank)
 
 
 // launch geometry of plane_mma / fiber_mma (c2c_mma.cuh).  Conditions: whole rank in one MMA (R <= 32 here, so that the
-// fused updates apply), in-plane size a multiple of 32 floats (whole swizzle atoms; TMA needs 16-byte row pitches), enough
+// fused updates apply), in-plane size a multiple of 4 floats (TMA needs 16-byte row pitches; a ragged last 32-float atom is
+// zero-filled by the TMA unit), enough
 // planes to give every SM at least one 128-plane tile.  C2C_B200_NO_MMA=1 turns the path off, C2C_B200_MMA_MIN_RANK sets
 // the smallest rank that takes it.
 #define C2C_MMA_SMEM_BUDGET (225 * 1024)
@@ -236,10 +238,12 @@ static int mma_epoch()
 
 static void mma_geometry(Geo& g, int rank)
 {
-    g.mma_ok = 0;
+    g.mma_ok = 0; g.mma_fiber_ok = 0;
     const int nsm = sm_count();
-    if (rank < mma_min_rank() || rank > 32 || g.nchunk != 1) return;
-    if (g.E % 32 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
+    // shapes the FFMA kernels only take with narrow (< 128-bit) loads go to the tensor pipe at every rank
+    const int min_rank = g.vec_plane < 4 ? 1 : mma_min_rank();
+    if (rank < min_rank || rank > 32 || g.nchunk != 1 || mma_min_rank() > 32) return;
+    if (g.E % 4 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
     const int n = rank <= 16 ? 16 : 32;
     g.mma_n = n;
     const int ldr = ldr_of(rank);
@@ -250,7 +254,7 @@ static void mma_geometry(Geo& g, int rank)
         int nx = (int)((C2C_MMA_SMEM_BUDGET - fixed) / (xb + 16));
         if (nx > 12) nx = 12;
         g.pm_nstages = nx;
-        g.pm_nkb = (int)(g.E / 32);
+        g.pm_nkb = (int)((g.E + 31) / 32);
         g.pm_ntiles = (g.P + 127) / 128;
         g.pm_grid = nsm;                                 // P >= 128 * nsm: a CTA's share spans at least one whole tile
         g.pm_smem = c2c_plane_mma_smem(n, g.I2, g.I3, nx);
@@ -258,7 +262,7 @@ static void mma_geometry(Geo& g, int rank)
     {   // fiber_mma: split the in-plane positions into `es` parts (es divides the SM count when it can) so that the CTA's
         // running sums and >= 5 X slots of 8 planes fit in shared memory and its accumulators + lo(X) ring in TMEM --
         // preferably with the stacked B tile (2N accumulator columns per tile)
-        const int na_total = (int)(g.E / 32);
+        const int na_total = (int)((g.E + 31) / 32);
         int best_es = 0, best_nx = 0, best_stack = 0;
         // pass 0: stacked B tile with whole-machine splits of <= 2 parts (big stages amortise the per-stage hand-offs);
         // pass 1: unstacked, >= 5 X slots; pass 2: whatever fits (>= 3 X slots)
@@ -277,14 +281,19 @@ static void mma_geometry(Geo& g, int rank)
                 if (fit >= 5 || (pass == 2 && fit >= 3)) { best_es = cand; best_nx = fit > 12 ? 12 : fit; best_stack = stack; break; }
             }
         }
-        if (best_es == 0) return;
-        g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
-        g.fm_nstages = best_nx; g.fm_stack = best_stack;
-        g.fm_nj = nsm / best_es; if (g.fm_nj < 1) return;
-        g.fm_grid = g.fm_nj * best_es;
-        g.fm_nst = (g.P + 7) / 8;
-        g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, ldr, best_nx);
-        if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
+        // a ragged last atom (in-plane size not a multiple of 32 floats) needs one small TMA box per atom: slower than the
+        // FFMA pass below the rank where that pass leaves the HBM roof
+        const bool fiber_worth = (g.E % 32 == 0) || rank >= mma_min_rank();
+        if (best_es != 0 && nsm / best_es >= 1 && fiber_worth) {
+            g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
+            g.fm_nstages = best_nx; g.fm_stack = best_stack;
+            g.fm_nj = nsm / best_es;
+            g.fm_grid = g.fm_nj * best_es;
+            g.fm_nst = (g.P + 7) / 8;
+            g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, ldr, best_nx);
+            if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
+            g.mma_fiber_ok = 1;
+        }
     }
     g.mma_ok = 1;
 }
@@ -510,14 +519,16 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
     dim3 grid(g.fc_gx, g.fc_gy);
     long long ppc = g.fc_ppc;
     bool legacy = true;
-    if (!masked && g.mma_ok) {
+    if (!masked && g.mma_fiber_ok) {
         CUtensorMap map;
-        const int rc = c2c_make_fiber_map(&map, a.X, g.P, g.E, g.fm_na);
+        const int boxes2d = (g.E % 32) != 0;
+        const int rc = boxes2d ? c2c_make_fiber_map2d(&map, a.X, g.P, g.E) : c2c_make_fiber_map(&map, a.X, g.P, g.E, g.fm_na);
         if (rc != 0) return fail(-41, "cuTensorMapEncodeTiled (fiber map) failed: %d", rc);
         FiberMmaArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.P = g.P; fa.E = (int)g.E; fa.R = a.R; fa.ldr = a.ldr; fa.lead = a.lead; fa.part = w.part; fa.done = a.done;
         fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : (g.fm_stack ? 16 : 8);
+        fa.boxes2d = boxes2d;
         fa.zero_ptr = reinterpret_cast<float4*>(po.zero_T); fa.zero_n4 = po.zero_n / 4;
         const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_mma launch");
@@ -1147,7 +1158,7 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     // waits for its predecessor before it touches that predecessor's results, so a streaming pass fills its ring while the
     // update kernel before it is still running).  On the tensor-pipe path T is cleared once here and then by every fiber pass.
     c.pdl = (use_pdl() && fused && mask == nullptr) ? 1 : 0;
-    c.mma_zero = g.mma_ok && mask == nullptr;
+    c.mma_zero = g.mma_ok && g.mma_fiber_ok && mask == nullptr;
     if (c.mma_zero) CK(cudaMemsetAsync(c.w.T, 0, (size_t)g.P * ldr * sizeof(float), st), "memset T");
 
     // `unroll` iterations are captured once and replayed: ~6 launches per iteration become a fraction of a graph launch, and

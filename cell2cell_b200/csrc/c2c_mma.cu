@@ -94,3 +94,17 @@ int c2c_make_fiber_map(CUtensorMap* map, const float* X, long long P, long long 
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+
+int c2c_make_fiber_map2d(CUtensorMap* map, const float* X, long long P, long long E)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)E, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)E * sizeof(float)};
+    cuuint32_t box[2] = {32, 8};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}

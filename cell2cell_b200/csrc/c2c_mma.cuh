@@ -361,6 +361,8 @@ struct FiberMmaArgs {
     int dbg;                   // timing experiments only (see PlaneMmaArgs)
     int epoch;                 // stages per accumulator chain
     long long nst_total;       // 8-plane stages: ceil(P / 8)
+    int boxes2d;               // 1: the tensor map is 2-D {E, P} and a stage is `na` boxes of {32, 8} (in-plane size not a multiple of 32
+                               // floats: the ragged last atom is zero-filled by the TMA unit); 0: one 3-D box per stage
     float4* zero_ptr;          // optional: buffer this pass clears for the next plane_mma (T, no longer read once the leading
     long long zero_n4;         // modes are updated), in float4 units; the epilogue warps do it while the stream runs
 };
@@ -406,7 +408,17 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
     const long long sb = (long long)j * a.nst_total / nj, se = (long long)(j + 1) * a.nst_total / nj;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (a.boxes2d) {
+            int sx = 0; unsigned phx = 0;
+            for (long long g = sb; g < se; ++g) {
+                mbar_wait(emptyx + sx, phx ^ 1u);
+                if (lane == 0) mbar_expect_tx(fullx + sx, (unsigned)x_bytes);
+                __syncwarp();
+                for (int at = lane; at < na; at += 32)               // one {32 positions x 8 planes} box per atom and lane
+                    tma_load_2d(xring + (size_t)sx * x_bytes + (size_t)at * 1024, &mapX, (at0 + at) * 32, (int)(g * 8), fullx + sx);
+                if (++sx == DX) { sx = 0; phx ^= 1u; }
+            }
+        } else if (lane == 0) {
             int sx = 0; unsigned phx = 0;
             for (long long g = sb; g < se; ++g) {
                 mbar_wait(emptyx + sx, phx ^ 1u);
@@ -609,3 +621,4 @@ size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);
 // tensor maps over X: [P][E] rows of 32 floats (128-byte swizzle) / {32, P, E/32} (32-byte-atom 128-byte swizzle)
 int c2c_make_plane_map(CUtensorMap* map, const float* X, long long P, long long E);
 int c2c_make_fiber_map(CUtensorMap* map, const float* X, long long P, long long E, int na);
+int c2c_make_fiber_map2d(CUtensorMap* map, const float* X, long long P, long long E);

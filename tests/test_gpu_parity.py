@@ -483,7 +483,7 @@ def test_full_size_build_roundtrip():
 # tensor-pipe streaming passes (TMA + tcgen05.mma kind::tf32 with the three-term split, c2c_mma.cuh): taken when the rank
 # reaches c2c_set_mma_min_rank, the in-plane size is a multiple of 32 and there are >= 128 planes per SM
 # ----------------------------------------------------------------------------------------------------------------------
-MMA_SHAPES = [(40, 500, 16, 8), (25, 801, 8, 32), (19000, 16, 16), (10, 1900, 40, 40)]
+MMA_SHAPES = [(40, 500, 16, 8), (25, 801, 8, 32), (19000, 16, 16), (10, 1900, 40, 40), (20000, 12, 12), (22, 870, 30, 30)]
 
 
 @pytest.fixture
@@ -521,7 +521,7 @@ def test_mma_passes_match_einsum(shape, rank, mma_from_rank_1):
 
 
 @pytest.mark.parametrize("shape,rank,n_iter", [((40, 500, 16, 8), 16, 30), ((40, 500, 16, 8), 20, 30), ((25, 801, 8, 32), 5, 30),
-                                               ((19000, 16, 16), 32, 15)])
+                                               ((19000, 16, 16), 32, 15), ((20000, 12, 12), 10, 20)])
 def test_mma_ncp_matches_oracle(shape, rank, n_iter, mma_from_rank_1):
     """Whole factorization through the tensor-pipe passes against the float64 oracle: factors and error within 1e-4."""
     _compare_run(lowrank(shape, 6, seed=11), rank, n_iter)
