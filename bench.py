@@ -273,11 +273,19 @@ def run_ours(args, rank_id, local_rank, world):
     t_fiber = time_kernel(lambda: engine.fiber_contract(X, None, f, rank, ws=ws, out=U), reps)
 
     times = torch.tensor([sec, e2e_sec], dtype=torch.float64, device=dev)
+    my_clk = clk.summary()
+    per_rank = torch.zeros((world, 3), dtype=torch.float64, device=dev)      # [seconds, median SM MHz, any throttle reason]
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    per_rank[rank_id, 0] = sec
+    per_rank[rank_id, 1] = float(my_clk["sm_mhz"] or 0.0)
+    per_rank[rank_id, 2] = 1.0 if bad & set(my_clk["reasons"]) else 0.0
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     sec, e2e_sec = float(times[0]), float(times[1])
     if rank_id != 0:
         return
+    per_rank = per_rank.cpu().numpy()
     peak, peak_kind = peaks()
     total_iters = world * args.steps * iters
     value = total_iters / sec
@@ -297,7 +305,8 @@ def run_ours(args, rank_id, local_rank, world):
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_sec / e2e_steps,
                 "api": "PreBuiltTensor(pinned host fp32).compute_tensor_factorization(rank, init='random', n_iter_max=%d, tol=-1)" % iters},
         "gpu_launches": int(launches),
-        "clocks": clk.summary(),
+        "clocks": dict(my_clk, per_gpu_sm_mhz=[float(v) for v in per_rank[:, 1]], any_gpu_thermal_or_hw_slowdown=bool(per_rank[:, 2].any())),
+        "per_gpu_ms_per_step": [round(1e3 * float(v) / args.steps, 3) for v in per_rank[:, 0]],
         "roofline": {"bound": "hbm", "kernel": name, "achieved": n_x * 4 / worst / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": n_x * 4 / worst / 1e9 / peak, "traffic": ncu_traffic(name), "peak_kind": "of " + peak_kind,
                      "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
