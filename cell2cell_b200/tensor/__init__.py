@@ -3,7 +3,10 @@ from .metrics import correlation_index, pairwise_correlation_index
 from .tensor import (BaseTensor, InteractionTensor, PreBuiltTensor, build_context_ccc_tensor, generate_tensor_metadata)
 from .factorization import (non_negative_parafac, non_negative_parafac_hals, normalized_error)
 from .cp import CPTensor
+from .external_scores import dataframes_to_tensor
+from .subset import concatenate_interaction_tensors, find_element_indexes, subset_metadata, subset_tensor
 
 __all__ = ["BaseTensor", "InteractionTensor", "PreBuiltTensor", "build_context_ccc_tensor", "generate_tensor_metadata",
            "correlation_index", "pairwise_correlation_index", "non_negative_parafac", "non_negative_parafac_hals",
-           "normalized_error", "CPTensor"]
+           "normalized_error", "CPTensor", "dataframes_to_tensor", "subset_tensor", "subset_metadata", "find_element_indexes",
+           "concatenate_interaction_tensors"]

@@ -69,3 +69,37 @@ OPTION_GRID = [
     for agg in ("min", "mean", "gmean")
     for grp, gm in ((None, "gmean"), ("pathway", "gmean"), ("pathway", "sum"), ("pathway", "mean"))
 ]
+
+
+def long_tables(seed, n_contexts=3, n_cells=5, n_lrs=8, dup=True):
+    """Seeded long-format communication-score tables (one per context) for ``dataframes_to_tensor``: every context misses a
+    cell type and a few LR pairs, LR pairs do not cover every cell pair, a few rows are duplicated."""
+    import pandas as pd
+    rs = np.random.RandomState(seed)
+    cells = ["CT%d" % i for i in range(n_cells)]
+    lrs = [("L%d" % i, "R%d" % (i % 3)) for i in range(n_lrs)]
+    out = {}
+    for c in range(n_contexts):
+        ctx_cells = [x for i, x in enumerate(cells) if i != (c % n_cells)]
+        ctx_lrs = [x for i, x in enumerate(lrs) if (i + c) % 4 != 0]
+        rows = []
+        for lig, rec in ctx_lrs:
+            senders = [x for x in ctx_cells if rs.rand() > 0.15]
+            receivers = [x for x in ctx_cells if rs.rand() > 0.15]
+            for s in senders:
+                for r in receivers:
+                    if rs.rand() > 0.2:
+                        rows.append((s, r, lig, rec, float(np.round(rs.rand() * (rs.rand() > 0.1), 4))))
+        df = pd.DataFrame(rows, columns=["source", "target", "ligand", "receptor", "score"])
+        if dup and len(df) > 4:
+            extra = df.iloc[rs.choice(len(df), 4, replace=False)].copy()
+            extra["score"] = np.round(extra["score"] + rs.rand(4), 4)
+            df = pd.concat([df, extra], ignore_index=True)
+        out["ctx%d" % (n_contexts - c)] = df.sample(frac=1.0, random_state=seed + c).reset_index(drop=True)
+    return out
+
+
+LONG_TABLE_OPTIONS = [dict(how=h, outer_fraction=f, lr_fill=lf, cell_fill=cf, dup_aggregation=d)
+                      for h, f in (("inner", 0.0), ("outer", 0.0), ("outer", 0.6), ("outer_lrs", 0.0), ("outer_cells", 0.5))
+                      for lf, cf in ((np.nan, np.nan), (0.0, np.nan), (np.nan, 0.0))
+                      for d in ("max", "min")]
