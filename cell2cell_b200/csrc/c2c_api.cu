@@ -119,6 +119,8 @@ static void stream_geometry(Geo& g, int rank)
         const int ppw = 32 / G;
         g.ps_ns = ns;
         g.ps_rp = (2 * g.np2 + 3) / 4 * 4;
+        // A2 / A3 copies + barriers, and the per-warp scratch rows of the plane reduction (32 x (NP2 | 1) float2 per warp)
+        const size_t red_bytes = (size_t)C2C_ST_MAXWARPS * 32 * (g.np2 | 1) * 8;
         const size_t fixed = align_up((size_t)(g.I2 + g.I3) * g.ps_rp * sizeof(float) + (size_t)C2C_ST_MAXWARPS * C2C_ST_MAXRING * 8, 128);
         const long long target = 10 * 1024;                          // bytes per stage
         long long spw = 0, rs = 1, pitch = g.E;
@@ -145,14 +147,14 @@ static void stream_geometry(Geo& g, int rank)
         const size_t stage_bytes = (size_t)(spw * pitch * 4);
         if (fixed < C2C_SMEM_BUDGET / 2 && stage_bytes <= 24 * 1024) {
             long long nw = C2C_ST_MAXWARPS;
-            long long ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed) / (nw * (long long)stage_bytes);
-            if (ring < 2) { nw = 4; ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed) / (nw * (long long)stage_bytes); }
+            long long ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed - (long long)red_bytes) / (nw * (long long)stage_bytes);
+            if (ring < 2) { nw = 4; ring = ((long long)C2C_SMEM_BUDGET - (long long)fixed - (long long)red_bytes) / (nw * (long long)stage_bytes); }
             if (ring > C2C_ST_MAXRING) ring = C2C_ST_MAXRING;
             const long long ngroups = g.P / spw;
             if (ring >= 2 && ngroups >= 2LL * nsm * nw) {
                 g.ps_ok = 1; g.ps_spw = (int)spw; g.ps_rs = (int)rs; g.ps_ring = (int)ring; g.ps_nwarps = (int)nw;
                 g.ps_pitch = (int)pitch; g.ps_nstage = ngroups; g.ps_grid = nsm;
-                g.ps_smem = fixed + (size_t)nw * ring * stage_bytes;
+                g.ps_smem = fixed + (size_t)nw * ring * stage_bytes + red_bytes;
             }
         }
     }

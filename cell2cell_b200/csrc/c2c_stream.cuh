@@ -114,8 +114,9 @@ plane_stream_kernel(const StreamArgs sa)
     const size_t stage_floats = (size_t)sa.spw * chunk_pitch;
     const size_t off = ((size_t)(I2 + I3) * rp * sizeof(float) + (size_t)sa.nwarps * S * 8 + 127) / 128 * 128;
     float* stage0 = reinterpret_cast<float*>(smem_raw + off);
-
+    constexpr int PITCH2 = NP2 | 1;                                  // odd pitch (in float2): conflict-free scratch rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* red = reinterpret_cast<float2*>(stage0 + (size_t)sa.nwarps * S * stage_floats) + warp * 32 * PITCH2;
     unsigned long long* mybar = bars + warp * S;
     float* mystage = stage0 + (size_t)warp * S * stage_floats;
     const unsigned stage_bytes = (unsigned)((size_t)sa.spw * chunk_floats * sizeof(float));
@@ -234,27 +235,21 @@ plane_stream_kernel(const StreamArgs sa)
                     }
                 }
                 if (h == RS - 1) {
-                    // segmented reduction over the G lanes of a plane (all 32 lanes take part in the shuffles)
+                    // sum over the G lanes of a plane through the warp's scratch rows: lane writes its NP2 pairs, then lane
+                    // (plane, pair) adds the G partial pairs of its plane and stores them (G need not be a power of two)
+                    __syncwarp();
 #pragma unroll
-                    for (int q = 0; q < NP2; ++q) {
-                        float vx = out[q].x, vy = out[q].y;
-                        int width = G;
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float tx = __shfl_down_sync(0xffffffffu, vx, o);
-                            const float ty = __shfl_down_sync(0xffffffffu, vy, o);
-                            if (o < width) {
-                                if (lig + o < width) { vx += tx; vy += ty; }
-                                width = o;
-                            }
-                        }
-                        out[q] = make_float2(vx, vy);
-                    }
-                    if (on && lig == 0) {
-                        float* t = a.out + ((size_t)g * sa.spw + pl) * ldr;
-#pragma unroll
-                        for (int q = 0; q < NP2; ++q) {
-                            if (2 * q + 1 < R) *reinterpret_cast<float2*>(t + 2 * q) = out[q];
-                            else if (2 * q < R) t[2 * q] = out[q].x;
+                    for (int q = 0; q < NP2; ++q) red[lane * PITCH2 + q] = out[q];
+                    __syncwarp();
+                    for (int j = lane; j < ppw * NP2; j += 32) {
+                        const int pj = j / NP2, q = j - pj * NP2;
+                        if (pl0 + pj < sa.spw) {
+                            const float2* src = red + (pj * G) * PITCH2 + q;
+                            float2 sum = src[0];
+                            for (int i = 1; i < G; ++i) { const float2 v = src[i * PITCH2]; sum.x += v.x; sum.y += v.y; }
+                            float* t = a.out + ((size_t)g * sa.spw + pl0 + pj) * ldr;
+                            if (2 * q + 1 < R) *reinterpret_cast<float2*>(t + 2 * q) = sum;
+                            else if (2 * q < R) t[2 * q] = sum.x;
                         }
                     }
                 }
