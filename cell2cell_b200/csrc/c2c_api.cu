@@ -88,7 +88,7 @@ struct Geo {
     int mma_ok, mma_n;         // mma_ok: plane_mma applies;  mma_fiber_ok: fiber_mma applies too
     int mma_fiber_ok;
     int pm_nstages, pm_grid, pm_nkb; long long pm_ntiles; size_t pm_smem;
-    int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack; long long fm_nst; size_t fm_smem;
+    int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack, fm_in_smem; long long fm_nst; size_t fm_smem;
 };
 
 #define C2C_SMEM_BUDGET (200 * 1024)
@@ -265,7 +265,7 @@ static void mma_geometry(Geo& g, int rank)
         // running sums and >= 5 X slots of 8 planes fit in shared memory and its accumulators + lo(X) ring in TMEM --
         // preferably with the stacked B tile (2N accumulator columns per tile)
         const int na_total = (int)((g.E + 31) / 32);
-        int best_es = 0, best_nx = 0, best_stack = 0;
+        int best_es = 0, best_nx = 0, best_stack = 0, best_in_smem = 1;
         // pass 0: stacked B tile with whole-machine splits of <= 2 parts (big stages amortise the per-stage hand-offs);
         // pass 1: unstacked, >= 5 X slots; pass 2: whatever fits (>= 3 X slots)
         for (int pass = 0; pass < 3 && best_es == 0; ++pass) {
@@ -277,10 +277,19 @@ static void mma_geometry(Geo& g, int rank)
                 const int stack = ntile * (2 * n + 8 * C2C_MMA_RING2) <= 512;
                 if (pass == 0 && (!stack || cand > 2)) continue;
                 if (ntile > C2C_FM_MAXTILE || ntile * (n + 8 * C2C_MMA_RING2) > 512) continue;
-                const size_t fixed = c2c_fiber_mma_smem(n, na, ldr, 0);
-                if (fixed > C2C_MMA_SMEM_BUDGET) continue;
-                const int fit = (int)((C2C_MMA_SMEM_BUDGET - fixed) / ((size_t)na * 1024 + 16));
-                if (fit >= 5 || (pass == 2 && fit >= 3)) { best_es = cand; best_nx = fit > 12 ? 12 : fit; best_stack = stack; break; }
+                // running sums in shared memory when that still leaves >= 5 X slots, else in the global partial
+                int in_smem = 1;
+                size_t fixed = c2c_fiber_mma_smem(n, na, ldr, 0);
+                int fit = fixed > C2C_MMA_SMEM_BUDGET ? 0 : (int)((C2C_MMA_SMEM_BUDGET - fixed) / ((size_t)na * 1024 + 16));
+                if (fit < 5) {
+                    in_smem = 0;
+                    fixed = c2c_fiber_mma_smem(n, na, 0, 0);
+                    if (fixed > C2C_MMA_SMEM_BUDGET) continue;
+                    fit = (int)((C2C_MMA_SMEM_BUDGET - fixed) / ((size_t)na * 1024 + 16));
+                }
+                if (fit >= 5 || (pass == 2 && fit >= 3)) {
+                    best_es = cand; best_nx = fit > 12 ? 12 : fit; best_stack = stack; best_in_smem = in_smem; break;
+                }
             }
         }
         // a ragged last atom (in-plane size not a multiple of 32 floats) needs one small TMA box per atom: slower than the
@@ -288,11 +297,11 @@ static void mma_geometry(Geo& g, int rank)
         const bool fiber_worth = (g.E % 32 == 0) || rank >= mma_min_rank();
         if (best_es != 0 && nsm / best_es >= 1 && fiber_worth) {
             g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
-            g.fm_nstages = best_nx; g.fm_stack = best_stack;
+            g.fm_nstages = best_nx; g.fm_stack = best_stack; g.fm_in_smem = best_in_smem;
             g.fm_nj = nsm / best_es;
             g.fm_grid = g.fm_nj * best_es;
             g.fm_nst = (g.P + 7) / 8;
-            g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, ldr, best_nx);
+            g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, best_in_smem ? ldr : 0, best_nx);
             if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
             g.mma_fiber_ok = 1;
         }
@@ -529,8 +538,8 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         FiberMmaArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.P = g.P; fa.E = (int)g.E; fa.R = a.R; fa.ldr = a.ldr; fa.lead = a.lead; fa.part = w.part; fa.done = a.done;
-        fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : (g.fm_stack ? 16 : 8);
-        fa.boxes2d = boxes2d;
+        fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : 16;
+        fa.boxes2d = boxes2d; fa.sums_in_smem = g.fm_in_smem;
         fa.zero_ptr = reinterpret_cast<float4*>(po.zero_T); fa.zero_n4 = po.zero_n / 4;
         const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_mma launch");
@@ -971,7 +980,8 @@ struct RunCtx {
     Geo g; Ws w; const float* X; const uint8_t* mask; float* const* A; int ldr, R, algo, n_iter_max; double tol; int cvg;
     const double* normX2; double* errors; int* state; cudaStream_t st; float eps;
     int pdl;                   // launch the fused unmasked iteration's kernels as programmatic dependents
-    int rr, nruns;             // batched runs: nruns independent factorizations of rank rr side by side (R = rr * nruns)
+    int nruns;                 // batched runs: nruns independent factorizations side by side, column c belongs to run run_of[c]
+    unsigned char run_of[32];
     int* run_flags; int* run_iters;
     bool mma_zero;             // plane_mma / fiber_mma: T is kept cleared by the fiber pass
 };
@@ -1008,7 +1018,7 @@ static int launch_lead_update(const RunCtx& c, int mode)
     memset(&u, 0, sizeof(u));
     u.T = c.w.T; fill_lead(u.lead, g, (const float* const*)c.A); u.k = mode; u.P = g.P; u.R = c.R; u.ldr = c.ldr; u.N = g.ndim;
     u.A = c.A[mode]; u.S = c.w.S; u.state = c.state; u.eps = c.eps; u.done = c.state + 1;
-    u.rr = c.rr; u.run_flags = c.nruns > 1 ? c.run_flags : nullptr;
+    memcpy(u.run_of, c.run_of, sizeof(u.run_of)); u.run_flags = c.nruns > 1 ? c.run_flags : nullptr;
     const long long I = g.shape[mode];
     const long long cnt = g.P / I;                                   // planes carrying one index of this mode
     const int block = cnt >= 1024 ? 1024 : 256;
@@ -1048,7 +1058,7 @@ static int launch_trail_update(const RunCtx& c, int which_begin, int which_end)
     u.S = c.w.S; u.eps = c.eps; u.which_begin = which_begin; u.which_end = which_end;
     u.normX2 = c.normX2; u.errors = c.errors; u.state = c.state; u.n_iter_max = c.n_iter_max; u.tol = c.tol; u.cvg = c.cvg;
     u.done = c.state + 1;
-    u.rr = c.rr; u.nruns = c.nruns; u.run_flags = c.nruns > 1 ? c.run_flags : nullptr; u.run_iters = c.run_iters;
+    memcpy(u.run_of, c.run_of, sizeof(u.run_of)); u.nruns = c.nruns; u.run_flags = c.nruns > 1 ? c.run_flags : nullptr; u.run_iters = c.run_iters;
     const size_t smem = trail_update_smem(g, c.R, c.ldr, &u.u_in_smem);
     if (smem > 48 * 1024) {
         static thread_local size_t set_for = 0;
@@ -1109,7 +1119,7 @@ static int enqueue_iteration(const RunCtx& c)
 static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
                         int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
                         double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream,
-                        int rank_per_run, int nruns)
+                        const int* run_ranks, int nruns)
 {
     RunCtx c; int rc;
     if (!shape) return fail(-1, "shape is NULL");
@@ -1128,9 +1138,15 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     cudaStream_t st = c.st;
     const Geo& g = c.g;
 
-    c.rr = rank_per_run; c.nruns = nruns; c.run_flags = state + 2; c.run_iters = state + 2 + nruns;
+    c.nruns = nruns; c.run_flags = state + 2; c.run_iters = state + 2 + nruns;
+    memset(c.run_of, 0, sizeof(c.run_of));
     if (nruns > 1) {
-        if (nruns > 32 || rank_per_run * nruns != rank) return fail(-26, "batched runs: need rank = rank_per_run * nruns and nruns <= 32");
+        int total = 0;
+        for (int b = 0; b < nruns && nruns <= 32; ++b) {
+            if (run_ranks[b] < 1) return fail(-26, "batched runs: every run needs rank >= 1");
+            for (int q = 0; q < run_ranks[b]; ++q) { if (total < 32) c.run_of[total] = (unsigned char)b; ++total; }
+        }
+        if (nruns > 32 || total != rank) return fail(-26, "batched runs: the run ranks must add up to the total rank (<= 32), at most 32 runs");
         if (algo != C2C_ALGO_MU || mask != nullptr) return fail(-27, "batched runs: multiplicative updates without a mask only");
     }
     CK(cudaMemsetAsync(state, 0, (size_t)(nruns > 1 ? 2 + 2 * nruns : 2) * sizeof(int), st), "memset state");
@@ -1228,14 +1244,17 @@ extern "C" int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const 
                            double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
 {
     return ncp_run_impl(X, mask, ndim, shape, A, ldr, rank, algo, n_iter_max, tol, cvg_criterion, normX2, errors, state,
-                        check_every, ws, ws_bytes, stream, rank, 1);
+                        check_every, ws, ws_bytes, stream, nullptr, 1);
 }
 
-extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, int rank_per_run,
+extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, const int* run_ranks,
                                    int nruns, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
                                    double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream)
 {
-    if (rank_per_run < 1 || nruns < 1) return fail(-26, "batched runs: rank_per_run and nruns must be >= 1");
-    return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, rank_per_run * nruns, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
-                        normX2, errors, state, check_every, ws, ws_bytes, stream, rank_per_run, nruns);
+    if (!run_ranks || nruns < 1) return fail(-26, "batched runs: run_ranks is NULL or nruns < 1");
+    long long total = 0;
+    for (int b = 0; b < nruns; ++b) total += run_ranks[b];
+    if (total < 1 || total > 32) return fail(-26, "batched runs: the run ranks must add up to 1..32, got %lld", total);
+    return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, (int)total, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
+                        normX2, errors, state, check_every, ws, ws_bytes, stream, run_ranks, nruns);
 }

@@ -361,6 +361,8 @@ struct FiberMmaArgs {
     int dbg;                   // timing experiments only (see PlaneMmaArgs)
     int epoch;                 // stages per accumulator chain
     long long nst_total;       // 8-plane stages: ceil(P / 8)
+    int sums_in_smem;          // 1: the CTA's running sums live in shared memory ([na * 32][ldr] floats after the B ring) and are
+                               // copied out at the end; 0: they are kept in the (L2-resident) global partial itself
     int boxes2d;               // 1: the tensor map is 2-D {E, P} and a stage is `na` boxes of {32, 8} (in-plane size not a multiple of 32
                                // floats: the ragged last atom is zero-filled by the TMA unit); 0: one 3-D box per stage
     float4* zero_ptr;          // optional: buffer this pass clears for the next plane_mma (T, no longer read once the leading
@@ -382,8 +384,8 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
     constexpr int B_BYTES = 2 * N * 32;                          // rows 0..N-1 hi(W^T), N..2N-1 lo(W^T); 8 planes each, K-major core matrices
     unsigned char* xring = base;
     unsigned char* bring = base + (size_t)DX * x_bytes;
-    float* spart = reinterpret_cast<float*>(bring + (size_t)D2 * B_BYTES);             // [na * 32][ldr] running sums of this CTA
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(spart + (size_t)na * 32 * ldr);
+    float* spart = reinterpret_cast<float*>(bring + (size_t)D2 * B_BYTES);             // [na * 32][ldr] when sums_in_smem
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(spart + (a.sums_in_smem ? (size_t)na * 32 * ldr : 0));
     unsigned long long *fullx = bars, *emptyx = bars + DX, *ready = bars + 2 * DX, *empty2 = ready + D2, *tfull = empty2 + D2, *tempty = tfull + C2C_FM_MAXTILE;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + C2C_FM_MAXTILE);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -485,7 +487,8 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
         }
     } else if (warp < C2C_MMA_PREP_WARP0) {
         // ---- epilogue: TMEM lane = in-plane position of the tile; every chain is added, round-to-nearest, into the CTA's
-        // running sums in shared memory (a row is only ever touched by its own thread) ----
+        // running sums -- in shared memory when they leave room for >= 5 X slots, else in the (L2-resident) global partial
+        // itself; a row is only ever touched by its own thread, in a fixed order ----
         const int lg = warp & 3;
         unsigned phe = 0;
         bool first = true;
@@ -495,13 +498,29 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
             const long long z0 = (long long)blockIdx.x * per, z1 = z0 + per < a.zero_n4 ? z0 + per : a.zero_n4;
             for (long long i = z0 + (warp - 2) * 32 + lane; i < z1; i += 128) a.zero_ptr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (se <= sb) {                                          // empty plane range: the partial still has to be defined
+            const int q4 = ldr >> 2, t128 = (warp - 2) * 32 + lane;
+            for (int it = t128; it < na_own * 32 * q4; it += 128) {
+                const long long e = (long long)at0 * 32 + it / q4;
+                if (e < a.E) *reinterpret_cast<float4*>(a.part + ((size_t)j * a.E + (size_t)e) * ldr + (it % q4) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         for (long long g = sb; g < se; ) {
             const long long ep_end = g + F < se ? g + F : se;
             for (int i = 0; i < ntile; ++i) {
                 const bool shifted = !(i + 1 < ntile || (na & 3) == 0);
                 const int el = (shifted ? na - 4 : 4 * i) * 32 + lg * 32 + lane;   // position inside the part
-                const bool on = !(shifted && el < 128 * (ntile - 1));              // rows the previous tile already covers
-                float* row = spart + (size_t)el * ldr;
+                const long long e = (long long)at0 * 32 + el;
+                // rows the previous tile already covers, rows of the next part (fetched, not owned) and rows past the end are skipped
+                const bool on = !(shifted && el < 128 * (ntile - 1)) && el < na_own * 32 && e < a.E;
+                float* row = a.sums_in_smem ? spart + (size_t)el * ldr : a.part + ((size_t)j * a.E + (size_t)(on ? e : 0)) * ldr;
+                // the running sums of this row are fetched before the chain is waited for (they do not depend on it)
+                float4 old[N / 4];
+                if (on && !first) {
+#pragma unroll
+                    for (int qq = 0; qq < N / 4; ++qq)
+                        if (4 * qq < ldr) old[qq] = *reinterpret_cast<const float4*>(row + 4 * qq);
+                }
                 mbar_wait(tfull + i, phe);
                 tc_fence_after();
                 // every MMA into the full-size columns truncated the running sum: ~2^-24 of it per MMA on average (measured)
@@ -522,16 +541,17 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
                         }
                         if (on) {
 #pragma unroll
-                            for (int qq = 0; qq < 16; qq += 4) {
-                                if (c0 + qq < ldr) {
-                                    float4* dst = reinterpret_cast<float4*>(row + c0 + qq);
-                                    float4 o = make_float4(v[qq], v[qq + 1], v[qq + 2], v[qq + 3]);
-                                    if (!first) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-                                    *dst = o;
+                            for (int qq = 0; qq < 4; ++qq) {
+                                if (c0 + 4 * qq < ldr) {
+                                    float4 o = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+                                    if (!first) { const float4 od = old[c0 / 4 + qq]; o.x += od.x; o.y += od.y; o.z += od.z; o.w += od.w; }
+                                    *reinterpret_cast<float4*>(row + c0 + 4 * qq) = o;
                                 }
                             }
                         }
                     }
+                } else if (on && first) {
+                    for (int c = 0; c < ldr; ++c) row[c] = 0.0f;
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -541,18 +561,17 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
             first = false;
             g = ep_end;
         }
-        // the CTA's partial: rows of this part, all `ldr` columns (zeros for an empty range)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int nrow = na_own * 32;
-        const int t128 = (warp - 2) * 32 + lane;
-        const int q4 = ldr >> 2;
-        for (int it = t128; it < nrow * q4; it += 128) {
-            const int el = it / q4, c = it - el * q4;
-            const long long e = (long long)at0 * 32 + el;
-            if (e < a.E) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (se > sb && !(a.dbg & 8)) v = *reinterpret_cast<const float4*>(spart + (size_t)el * ldr + c * 4);
-                *reinterpret_cast<float4*>(a.part + ((size_t)j * a.E + (size_t)e) * ldr + c * 4) = v;
+        if (a.sums_in_smem && se > sb) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int q4 = ldr >> 2, t128 = (warp - 2) * 32 + lane;
+            for (int it = t128; it < na_own * 32 * q4; it += 128) {
+                const int el = it / q4, c = it - el * q4;
+                const long long e = (long long)at0 * 32 + el;
+                if (e < a.E) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!(a.dbg & 8)) v = *reinterpret_cast<const float4*>(spart + (size_t)el * ldr + c * 4);
+                    *reinterpret_cast<float4*>(a.part + ((size_t)j * a.E + (size_t)e) * ldr + c * 4) = v;
+                }
             }
         }
     } else {
@@ -617,7 +636,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
 cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
 cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
 size_t c2c_plane_mma_smem(int n, int I2, int I3, int nx);
-size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);
+size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);       // ldr = 0: running sums not in shared memory
 // tensor maps over X: [P][E] rows of 32 floats (128-byte swizzle) / {32, P, E/32} (32-byte-atom 128-byte swizzle)
 int c2c_make_plane_map(CUtensorMap* map, const float* X, long long P, long long E);
 int c2c_make_fiber_map(CUtensorMap* map, const float* X, long long P, long long E, int na);

@@ -31,21 +31,22 @@ struct LeadUpdArgs {
     int rows_per_cta;
     float eps;
     const int* done;
-    // batched runs: the R columns are R / rr independent factorizations of rank rr each (rr = R: one run).  Columns of
-    // different runs do not interact (their Gram-Hadamard entries are taken as zero); a run whose flag is set is frozen.
-    int rr;
-    const int* run_flags;      // [R / rr] or null
+    // batched runs: the R (<= 32) columns belong to independent factorizations, column c to run run_of[c] (all zero: one
+    // run).  Columns of different runs do not interact (their Gram-Hadamard entries are taken as zero); a run whose flag is
+    // set is frozen.
+    unsigned char run_of[32];
+    const int* run_flags;      // [number of runs] or null
 };
 
 // G[q][r] = prod_{j < k} Snew_j[q][r] * prod_{j > k} Sold_j[q][r] into shared memory (float), R x R; zero across runs
-__device__ __forceinline__ void hadamard_to_smem(const double* Snew, const double* Sold, int N, int k, int R, int ldr, int rr, float* sG)
+__device__ __forceinline__ void hadamard_to_smem(const double* Snew, const double* Sold, int N, int k, int R, int ldr, const unsigned char* run_of, float* sG)
 {
     for (int t = threadIdx.x; t < R * R; t += blockDim.x) {
         const int q = t / R, r = t - q * R;
         double g = 1.0;
         for (int j = 0; j < N; ++j)
             if (j != k) g *= (j < k ? Snew : Sold)[(size_t)j * ldr * ldr + q * ldr + r];
-        sG[t] = (q / rr == r / rr) ? (float)g : 0.0f;
+        sG[t] = (run_of[q & 31] == run_of[r & 31]) ? (float)g : 0.0f;
     }
 }
 
@@ -69,7 +70,7 @@ lead_update_kernel(const LeadUpdArgs a, const int tpr)
     double* Snew = a.S + (size_t)par * a.N * LL;
     const double* Sold = a.S + (size_t)(par ^ 1) * a.N * LL;
 
-    hadamard_to_smem(Snew, Sold, a.N, a.k, R, ldr, a.rr, sG);
+    hadamard_to_smem(Snew, Sold, a.N, a.k, R, ldr, a.run_of, sG);
 
     const int dk = a.lead.dim[a.k];
     int inner = 1;
@@ -155,7 +156,7 @@ lead_update_kernel(const LeadUpdArgs a, const int tpr)
                 float den = 0.0f;
                 for (int q = 0; q < R; ++q) den = fmaf(arow[q], sG[q * R + r], den);
                 nv = arow[r] * fmaxf((float)m, a.eps) / fmaxf(den, a.eps);
-                if (a.run_flags != nullptr && a.run_flags[r / a.rr]) nv = arow[r];          // this run has stopped
+                if (a.run_flags != nullptr && a.run_flags[a.run_of[r & 31]]) nv = arow[r];  // this run has stopped
             }
             sNew[rslot * ldr + r] = nv;
         }
@@ -192,7 +193,8 @@ struct TrailUpdArgs {
     const double* normX2; double* errors; int* state; int n_iter_max; double tol; int cvg;
     const int* done;
     // batched runs (see LeadUpdArgs): errors is [nruns][n_iter_max], run_flags / run_iters are [nruns]
-    int rr, nruns;
+    unsigned char run_of[32];
+    int nruns;
     int* run_flags; int* run_iters;
 };
 
@@ -244,7 +246,6 @@ trail_update_kernel(const TrailUpdArgs a)
     double iprod = 0.0;
     __shared__ double s_ip[32], s_rn[32];                      // per-run <M, A> and ||rec||^2 (batched runs)
     if (threadIdx.x < 32) { s_ip[threadIdx.x] = 0.0; s_rn[threadIdx.x] = 0.0; }
-    const int rr = a.rr;
     __syncthreads();
 
     for (int which = a.which_begin; which < a.which_end; ++which) {
@@ -256,7 +257,7 @@ trail_update_kernel(const TrailUpdArgs a)
         for (int t = threadIdx.x; t < RR; t += blockDim.x) {
             double g = 1.0;
             for (int j = 0; j < N; ++j) if (j != mode) g *= sS[(size_t)j * RR + t];
-            sG[t] = ((t / R) / rr == (t % R) / rr) ? (float)g : 0.0f;
+            sG[t] = (a.run_of[(t / R) & 31] == a.run_of[(t % R) & 31]) ? (float)g : 0.0f;
         }
         // M[i, r] = sum_j U[e(i, j), r] * O[j, r]
         for (int t = threadIdx.x; t < I * R; t += blockDim.x) {
@@ -286,9 +287,9 @@ trail_update_kernel(const TrailUpdArgs a)
             for (int q = 0; q < R; ++q) den = fmaf(sA[i * R + q], sG[q * R + r], den);
             const float m = sM[t];
             float nv = sA[t] * fmaxf(m, a.eps) / fmaxf(den, a.eps);
-            if (a.run_flags != nullptr && a.run_flags[r / rr]) nv = sA[t];                    // this run has stopped
+            if (a.run_flags != nullptr && a.run_flags[a.run_of[r & 31]]) nv = sA[t];          // this run has stopped
             ip += (double)m * (double)nv;
-            if (a.nruns > 1 && which == 1) atomicAdd(&s_ip[r / rr], (double)m * (double)nv);
+            if (a.nruns > 1 && which == 1) atomicAdd(&s_ip[a.run_of[r & 31]], (double)m * (double)nv);
             gA[(size_t)i * ldr + r] = nv;
             nv_keep[nk & 1] = nv;
         }
@@ -320,10 +321,10 @@ trail_update_kernel(const TrailUpdArgs a)
         // batched runs: one error / stop decision per run
         for (int pr = threadIdx.x; pr < RR; pr += blockDim.x) {
             const int q = pr / R, r = pr - q * R;
-            if (q / rr == r / rr) {
+            if (a.run_of[q & 31] == a.run_of[r & 31]) {
                 double g = 1.0;
                 for (int j = 0; j < N; ++j) g *= sS[(size_t)j * RR + pr];
-                atomicAdd(&s_rn[q / rr], g);
+                atomicAdd(&s_rn[a.run_of[q & 31]], g);
             }
         }
         __syncthreads();

@@ -251,15 +251,16 @@ def ncp_run(X, mask, factors, rank, tf_type="non_negative_cp", n_iter_max=100, t
         return errors[:n_iter].cpu().numpy(), n_iter, bool(st[1])
 
 
-def ncp_run_batched(X, factors, rank_per_run, nruns, n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error", check_every=10,
+def ncp_run_batched(X, factors, run_ranks, n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error", check_every=10,
                     norm_x2=None, ws=None):
-    """``nruns`` independent MU factorizations of rank ``rank_per_run`` side by side (``c2c_ncp_run_batched``): ``factors`` are
-    packed ``[I_n, ldr(rank_per_run * nruns)]`` tensors, run ``b`` owning columns ``[b * rank_per_run, (b + 1) * rank_per_run)``.
-    Returns ``(errors [nruns, n_iter_max] float64, iterations [nruns] int)``."""
+    """Independent MU factorizations side by side (``c2c_ncp_run_batched``): run ``b`` has rank ``run_ranks[b]`` and owns the
+    next ``run_ranks[b]`` columns of the packed ``[I_n, ldr(sum(run_ranks))]`` factors.  Returns
+    ``(errors [nruns, n_iter_max] float64, iterations [nruns] int)``."""
     _check_tensor(X, None)
-    rank = int(rank_per_run) * int(nruns)
-    if rank < 1 or rank > 32 or nruns > 32:
-        raise C2CError("batched runs need rank_per_run * nruns <= 32, got %d x %d" % (rank_per_run, nruns))
+    run_ranks = [int(r) for r in run_ranks]
+    nruns, rank = len(run_ranks), int(sum(run_ranks))
+    if nruns < 1 or min(run_ranks) < 1 or rank > 32 or nruns > 32:
+        raise C2CError("batched runs need ranks >= 1 adding up to <= 32, got %r" % (run_ranks,))
     if cvg_criterion not in CVG:
         raise C2CError("cvg_criterion %r is not one of %s" % (cvg_criterion, sorted(CVG)))
     for f, s in zip(factors, X.shape):
@@ -268,19 +269,20 @@ def ncp_run_batched(X, factors, rank_per_run, nruns, n_iter_max=100, tol=1e-6, c
     with torch.cuda.device(X.device):
         ws = _ws_for(X, rank, None, ws)
         n_it = max(int(n_iter_max), 1)
-        errors = torch.zeros((int(nruns), n_it), dtype=torch.float64, device=X.device)
-        state = torch.zeros(2 + 2 * int(nruns), dtype=torch.int32, device=X.device)
+        errors = torch.zeros((nruns, n_it), dtype=torch.float64, device=X.device)
+        state = torch.zeros(2 + 2 * nruns, dtype=torch.int32, device=X.device)
         nx2 = None
         if norm_x2 is not None:
             nx2 = torch.tensor([float(norm_x2)], dtype=torch.float64, device=X.device)
-        check(lib().c2c_ncp_run_batched(_ptr(X), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), int(rank_per_run),
-                                        int(nruns), int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(nx2), _ptr(errors),
+        ranks_arr = (ctypes.c_int * nruns)(*run_ranks)
+        check(lib().c2c_ncp_run_batched(_ptr(X), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), ranks_arr,
+                                        nruns, int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(nx2), _ptr(errors),
                                         _ptr(state), int(check_every), ws.ptr, ws.nbytes, _stream()), "c2c_ncp_run_batched")
         st = state.cpu().numpy()
         if nruns == 1:
             iters = np.array([int(st[0])])
         else:
-            iters = st[2 + int(nruns):2 + 2 * int(nruns)].astype(np.int64)
+            iters = st[2 + nruns:2 + 2 * nruns].astype(np.int64)
         return errors.cpu().numpy(), iters
 
 

@@ -90,20 +90,24 @@ def _factorize(tensor, rank, algo, n_iter_max, init, svd, tol, random_state, ver
     return cp
 
 
-def _factorize_batch(X, rank, seeds, n_iter_max, tol, cvg_criterion="abs_rec_error", check_every=10):
-    """The runs ``seeds`` of one rank, as one batched device factorization (``c2c_ncp_run_batched``): one read of the tensor
-    per pass serves every run.  Same results as ``len(seeds)`` calls of ``non_negative_parafac(init='random')`` (the runs do
-    not interact; each has its own error history and stop iteration).  Returns ``[(CPTensor, errors), ...]``."""
-    rank, nruns = int(rank), len(seeds)
-    host = [initialize_factors(X, rank, init="random", random_state=sd) for sd in seeds]           # [run][mode]
-    packed = [engine.pack_factor(np.concatenate([host[b][m].astype(np.float32) for b in range(nruns)], axis=1), rank * nruns,
+def _factorize_batch(X, runs, n_iter_max, tol, cvg_criterion="abs_rec_error", check_every=10):
+    """The factorizations ``runs = [(rank, seed), ...]`` (ranks adding up to <= 32) as ONE batched device factorization
+    (``c2c_ncp_run_batched``): one read of the tensor per pass serves every run.  Same results as the corresponding calls of
+    ``non_negative_parafac(init='random')`` (the runs do not interact; each has its own error history and stop iteration).
+    Returns ``[(CPTensor, errors), ...]`` in the order of ``runs``."""
+    ranks = [int(r) for r, _ in runs]
+    total = sum(ranks)
+    host = [initialize_factors(X, r, init="random", random_state=sd) for r, sd in runs]            # [run][mode]
+    packed = [engine.pack_factor(np.concatenate([host[b][m].astype(np.float32) for b in range(len(runs))], axis=1), total,
                                  X.device) for m in range(X.dim())]
-    errors, iters = engine.ncp_run_batched(X, packed, rank, nruns, n_iter_max=int(n_iter_max), tol=float(tol) if tol else -1.0,
+    errors, iters = engine.ncp_run_batched(X, packed, ranks, n_iter_max=int(n_iter_max), tol=float(tol) if tol else -1.0,
                                            cvg_criterion=cvg_criterion, check_every=check_every,
                                            norm_x2=getattr(X, "_c2c_norm_x2", None))
     out = []
-    for b in range(nruns):
-        fs = [engine.pack_factor(p[:, b * rank:(b + 1) * rank], rank, X.device) for p in packed]
+    c0 = 0
+    for b, rank in enumerate(ranks):
+        fs = [engine.pack_factor(p[:, c0:c0 + rank], rank, X.device) for p in packed]
+        c0 += rank
         errs = np.array(errors[b, :int(iters[b])], dtype=np.float64)
         sums = None
         if len(errs):
@@ -114,6 +118,22 @@ def _factorize_batch(X, rank, seeds, n_iter_max, tol, cvg_criterion="abs_rec_err
             cp.recon_sums_ = sums
         out.append((cp, [np.float64(e) for e in errs]))
     return out
+
+
+def _pack_runs(runs, capacity=28):
+    """First-fit-decreasing packing of ``(rank, run)`` units into bins of at most ``capacity`` factor columns (a pass over
+    the tensor costs about the same for 17 columns as for 28, so fuller bins mean fewer passes; past 28 columns the fiber pass
+    loses its shared-memory running sums and a bin costs more per column)."""
+    bins = []
+    for unit in sorted(runs, key=lambda u: (-u[0], u[1])):
+        for b in bins:
+            if b[0] + unit[0] <= capacity and len(b[1]) < 32:
+                b[0] += unit[0]
+                b[1].append(unit)
+                break
+        else:
+            bins.append([unit[0], [unit]])
+    return [b[1] for b in bins]
 
 
 def non_negative_parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", tol=10e-7, random_state=None,
@@ -212,41 +232,40 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
     # tensor per pass serves all of them (MU, unmasked, host-seeded random init: what the elbow analysis uses by default).
     batchable = (tf_type == "non_negative_cp" and M is None and init == "random" and random_state is not None and
                  set(kwargs) <= {"return_errors", "cvg_criterion"} and X.dim() >= 3 and batch_runs)
-    units = []
-    for r in range(1, upper_rank + 1):
-        per = max(1, min(runs, 32 // r)) if batchable else 1
-        for b0 in range(0, runs, per):
-            units.append((r, list(range(b0, min(runs, b0 + per)))))
+    all_units = [(r, run) for r in range(1, upper_rank + 1) for run in range(runs)]
+    if batchable:
+        units = _pack_runs([u for u in all_units if u[0] <= 32]) + [[u] for u in all_units if u[0] > 32]
+    else:
+        units = [[u] for u in all_units]
+
+    def single(r, run):
+        seed = None if random_state is None else random_state + run
+        return _compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=seed, mask=M,
+                                             n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs)
 
     def one(unit):
-        r, idx = unit
         res = None
-        if len(idx) > 1:
+        if len(unit) > 1:
             try:
-                res = _factorize_batch(X, r, [random_state + run for run in idx], n_iter_max, tol,
+                res = _factorize_batch(X, [(r, random_state + run) for r, run in unit], n_iter_max, tol,
                                        cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
             except C2CError:
                 res = None                       # shape outside the fused update kernels: run by run on the device instead
-        if res is None and len(idx) > 1:
-            res = [_compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=random_state + run,
-                                                 mask=M, n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs) for run in idx]
-        elif res is None:
-            seed = None if random_state is None else random_state + idx[0]
-            res = [_compute_tensor_factorization(X, rank=r, tf_type=tf_type, init=init, svd=svd, random_state=seed, mask=M,
-                                                 n_iter_max=n_iter_max, tol=tol, verbose=verbose, **kwargs)]
+        if res is None:
+            res = [single(r, run) for r, run in unit]
         if metric == "error":
             return [float(_loss_of(X, tl, errs, M)) for tl, errs in res]
         return [tl for tl, errs in res]
 
     def cost(unit):
-        cols = unit[0] * len(unit[1])
-        return 1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)
+        cols = sum(r for r, _ in unit)
+        return (1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)) if len(unit) > 1 or cols <= 32 else cols / 16.0
 
     parts = run_units(units, one, cost=cost, gather="object")
     flat = {}
-    for (r, idx), vals in zip(units, parts):
-        for run, v in zip(idx, vals):
-            flat[(r, run)] = v
+    for unit, vals in zip(units, parts):
+        for key, v in zip(unit, vals):
+            flat[key] = v
     if metric == "error":
         all_loss = np.asarray([[flat[(r, run)] for run in range(runs)] for r in range(1, upper_rank + 1)], dtype=np.float64)
     else:

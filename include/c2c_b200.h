@@ -159,14 +159,14 @@ int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* sh
                 int cvg_criterion, const double* normX2, double* errors, int* state, int check_every,
                 void* ws, size_t ws_bytes, void* stream);
 
-/* `nruns` independent multiplicative-update factorizations of the same tensor, all of rank `rank_per_run`, side by side in
- * one set of factor matrices ([I_n x ldr], run b owns columns [b * rank_per_run, (b + 1) * rank_per_run)): the streaming
- * passes serve every run with ONE read of the tensor, the updates treat the runs as independent (no cross-run Gram terms),
- * every run has its own error history errors[b * n_iter_max + it] and stops on its own (its columns are frozen from then
- * on).  This is the inner double loop of _multiple_runs_elbow_analysis (cell2cell/tensor/factorization.py:335-352) for
- * the runs of one rank.  state: int32[2 + 2 * nruns] = {iterations enqueued, all runs stopped, stopped[nruns],
- * iterations[nruns]}.  rank_per_run * nruns <= 32, unmasked tensors only. */
-int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, int rank_per_run, int nruns,
+/* `nruns` independent multiplicative-update factorizations of the same tensor side by side in one set of factor matrices
+ * ([I_n x ldr]): run b has rank run_ranks[b] and owns the next run_ranks[b] columns.  The streaming passes serve every run
+ * with ONE read of the tensor, the updates treat the runs as independent (no cross-run Gram terms), every run has its own
+ * error history errors[b * n_iter_max + it] and stops on its own (its columns are frozen from then on).  This is the double
+ * loop of _multiple_runs_elbow_analysis (cell2cell/tensor/factorization.py:335-352): runs of any ranks can share a pass as
+ * long as their ranks add up to <= 32.  state: int32[2 + 2 * nruns] = {iterations enqueued, all runs stopped,
+ * stopped[nruns], iterations[nruns]}.  Unmasked tensors only. */
+int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, const int* run_ranks, int nruns,
                         int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
                         int check_every, void* workspace, size_t workspace_bytes, void* stream);
 

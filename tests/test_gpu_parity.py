@@ -545,7 +545,7 @@ def test_batched_runs_match_single_runs(shape, rank, nruns, tol):
     X = as_device_tensor(x)
     seeds = [300 + 7 * b for b in range(nruns)]
     n_iter = 40
-    batch = _factorize_batch(X, rank, seeds, n_iter, tol, check_every=5)
+    batch = _factorize_batch(X, [(rank, sd) for sd in seeds], n_iter, tol, check_every=5)
     assert len(batch) == nruns
     n_its = set()
     for (cp_b, err_b), seed in zip(batch, seeds):
@@ -559,6 +559,23 @@ def test_batched_runs_match_single_runs(shape, rank, nruns, tol):
             assert a.shape == b.shape and rel_err(a, b) < FACTOR_RTOL, rel_err(a, b)
     if tol < 0:
         assert n_its == {n_iter}
+
+
+def test_mixed_rank_batch_matches_single_runs():
+    """Runs of different ranks sharing a pass (17 + 9 + 6 = 32 columns, tensor-pipe path): each equals the run alone."""
+    from cell2cell_b200.tensor.factorization import _factorize_batch, _pack_runs, as_device_tensor, non_negative_parafac
+    X = as_device_tensor(lowrank((40, 500, 16, 8), 5, seed=23))
+    runs = [(17, 5), (9, 6), (6, 7)]
+    batch = _factorize_batch(X, runs, 25, -1.0)
+    for (cp_b, err_b), (rank, seed) in zip(batch, runs):
+        cp_s, err_s = non_negative_parafac(X, rank, n_iter_max=25, init="random", tol=-1.0, random_state=seed, return_errors=True)
+        assert cp_b.rank == rank and len(err_b) == len(err_s) == 25
+        np.testing.assert_allclose(err_b, err_s, rtol=2e-5, atol=5e-6)
+        for a, b in zip(cp_b.factors, cp_s.factors):
+            assert rel_err(a, b) < FACTOR_RTOL, rel_err(a, b)
+    bins = _pack_runs([(r, run) for r in range(1, 26) for run in range(10)])
+    assert sorted(u for b in bins for u in b) == sorted((r, run) for r in range(1, 26) for run in range(10))
+    assert all(sum(r for r, _ in b) <= 28 for b in bins) and len(bins) <= 125
 
 
 def test_batched_elbow_equals_unbatched_elbow():
