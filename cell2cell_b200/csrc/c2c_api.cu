@@ -244,7 +244,7 @@ static void mma_geometry(Geo& g, int rank)
     const int nsm = sm_count();
     // shapes the FFMA kernels only take with narrow (< 128-bit) loads go to the tensor pipe at every rank
     const int min_rank = g.vec_plane < 4 ? 1 : mma_min_rank();
-    if (rank < min_rank || rank > 32 || g.nchunk != 1 || mma_min_rank() > 32) return;
+    if (rank < min_rank || rank > 32 || g.nchunk != 1 || mma_min_rank() > 32 || !c2c_mma_available()) return;
     if (g.E % 4 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
     const int n = rank <= 16 ? 16 : 32;
     g.mma_n = n;

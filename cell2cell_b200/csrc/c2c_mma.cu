@@ -108,3 +108,6 @@ int c2c_make_fiber_map2d(CUtensorMap* map, const float* X, long long P, long lon
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+
+// 1 when the driver exposes cuTensorMapEncodeTiled (the tensor-pipe passes need TMA tensor maps)
+int c2c_mma_available() { return encode_fn() != nullptr ? 1 : 0; }

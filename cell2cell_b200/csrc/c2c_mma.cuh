@@ -641,3 +641,4 @@ size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);       // ldr = 0: run
 int c2c_make_plane_map(CUtensorMap* map, const float* X, long long P, long long E);
 int c2c_make_fiber_map(CUtensorMap* map, const float* X, long long P, long long E, int na);
 int c2c_make_fiber_map2d(CUtensorMap* map, const float* X, long long P, long long E);
+int c2c_mma_available();

@@ -37,20 +37,59 @@ def lpt_schedule(costs, n_workers):
     return owner
 
 
-def run_units(units, fn, cost=None, gather="float"):
-    """Evaluate ``fn(unit)`` for every unit, spread over the ranks of the default process group.
+def _run_local(units, fn, threads):
+    """This rank's units, in order.  With ``threads > 1`` they are issued from that many host threads, each on a CUDA stream
+    of its own: the device work of the units still runs one kernel after the other (every streaming kernel fills the
+    machine), but the host part of one unit (factor init, graph capture, result read-back) overlaps the device part of
+    another.  Results do not depend on the interleaving: units share no state."""
+    if threads <= 1 or len(units) <= 1 or not torch.cuda.is_available():
+        return [fn(u) for u in units]
+    from concurrent.futures import ThreadPoolExecutor
+    dev = torch.cuda.current_device()
+    main = torch.cuda.current_stream(dev)
+    start = torch.cuda.Event()
+    start.record(main)
+
+    def work(u):
+        torch.cuda.set_device(dev)
+        st = _thread_stream(dev)
+        st.wait_event(start)                        # everything enqueued before the sweep (the tensor upload) is visible
+        with torch.cuda.stream(st):
+            out = fn(u)
+        st.synchronize()
+        return out
+
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        return list(pool.map(work, units))
+
+
+_tls = __import__("threading").local()
+
+
+def _thread_stream(dev):
+    streams = getattr(_tls, "streams", None)
+    if streams is None:
+        streams = _tls.streams = {}
+    if dev not in streams:
+        streams[dev] = torch.cuda.Stream(device=dev)
+    return streams[dev]
+
+
+def run_units(units, fn, cost=None, gather="float", threads=1):
+    """Evaluate ``fn(unit)`` for every unit, spread over the ranks of the default process group (and, inside a rank, over
+    ``threads`` host threads -- see ``_run_local``).
 
     gather='float': every rank returns the full list of floats (one all-reduce of a ``len(units)`` vector -- results
     only, never tensor data).  gather='object': full list of picklable objects (``all_gather_object``)."""
     rank, size = world()
     n = len(units)
     if size == 1:
-        return [fn(u) for u in units]
+        return _run_local(list(units), fn, threads)
     import torch.distributed as dist
     costs = [1.0 if cost is None else float(cost(u)) for u in units]
     owner = lpt_schedule(costs, size)
     mine = [i for i in range(n) if owner[i] == rank]
-    local = {i: fn(units[i]) for i in mine}
+    local = dict(zip(mine, _run_local([units[i] for i in mine], fn, threads)))
     if gather == "float":
         backend = dist.get_backend()
         dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")

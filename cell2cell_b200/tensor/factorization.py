@@ -216,7 +216,7 @@ def _run_elbow_analysis(tensor, upper_rank=50, tf_type="non_negative_cp", init="
 
 def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_negative_cp", init="svd",
                                   svd="truncated_svd", metric="error", random_state=None, mask=None, n_iter_max=100,
-                                  tol=10e-7, verbose=False, batch_runs=True, **kwargs):
+                                  tol=10e-7, verbose=False, batch_runs=True, host_threads=1, **kwargs):
     """``runs`` factorizations per rank; ndarray (runs x upper_rank) of losses (factorization.py:272-373).
 
     The ``upper_rank * runs`` units are independent; when ``torch.distributed`` is initialised they are spread over the
@@ -261,7 +261,7 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
         cols = sum(r for r, _ in unit)
         return (1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)) if len(unit) > 1 or cols <= 32 else cols / 16.0
 
-    parts = run_units(units, one, cost=cost, gather="object")
+    parts = run_units(units, one, cost=cost, gather="object", threads=host_threads)
     flat = {}
     for unit, vals in zip(units, parts):
         for key, v in zip(unit, vals):
