@@ -220,6 +220,13 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                                     umma_tf32(d, dx + 2 * ks, db + 2 * ks, IDESC2, (gg > g || ks > 0) ? 1u : 0u);   // [hi(x) hi(b) | hi(x) lo(b)]
                                     umma_tf32_ts(d + N, alo + ks * 8, db + 2 * ks, IDESC1, 1u);                    // lo(x) hi(b) -> the lo columns
                                 }
+                                if (a.dbg & 16) {                   // timing experiment: the same MMAs once more (results are wrong)
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) {
+                                        umma_tf32(d, dx + 2 * ks, db + 2 * ks, IDESC2, 1u);
+                                        umma_tf32_ts(d + N, alo + ks * 8, db + 2 * ks, IDESC1, 1u);
+                                    }
+                                }
                             }
                             umma_commit(emptyx + sx);
                             umma_commit(empty2 + s2);
@@ -299,6 +306,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
             unsigned char* bt = bring + (size_t)s2 * L::B_BYTES;
             mbar_wait(empty2 + s2, ph2 ^ 1u);                    // the MMAs of the slot's previous round are done
             // KR slab (does not need the X tile): row n, 16-byte chunk c = k positions kb*32 + 4c .. +3
+            // (computing the values before the wait was measured and is not faster here)
             for (int it = tg; it < ((a.dbg & 2) ? 0 : N * 8); it += 128) {
                 const int n = it % N, c = it / N;
                 const int k0 = kb * 32 + c * 4;
@@ -585,23 +593,37 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
             const int sx = (int)(t % DX), s2 = (int)(t % D2);
             const unsigned phx = (unsigned)((t / DX) & 1), ph2 = (unsigned)((t / D2) & 1);
             unsigned char* bt = bring + (size_t)s2 * B_BYTES;
-            mbar_wait(empty2 + s2, ph2 ^ 1u);
-            for (int it = tg; it < ((a.dbg & 2) ? 0 : N * 8); it += 128) {
-                const int n = it % N, k = it / N;
-                long long rem = g * 8 + k;
-                float w = (rem < a.P && n < R) ? 1.0f : 0.0f;
-                if (w != 0.0f) {
-                    for (int m = a.lead.nl - 1; m >= 0; --m) {
-                        const int dm = a.lead.dim[m];
-                        const long long qq = rem / dm;
-                        const int idx = (int)(rem - qq * dm);
-                        rem = qq;
-                        w *= __ldg(a.lead.fac[m] + (size_t)idx * ldr + n);
+            // the stage's 8 Khatri-Rao rows: the factor loads are issued before the slot is waited for (N * 8 <= 2 * 128)
+            float wv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int it = tg + u * 128;
+                wv[u] = 0.0f;
+                if (it < ((a.dbg & 2) ? 0 : N * 8)) {
+                    const int n = it % N, k = it / N;
+                    long long rem = g * 8 + k;
+                    float w = (rem < a.P && n < R) ? 1.0f : 0.0f;
+                    if (w != 0.0f) {
+                        for (int m = a.lead.nl - 1; m >= 0; --m) {
+                            const int dm = a.lead.dim[m];
+                            const long long qq = rem / dm;
+                            const int idx = (int)(rem - qq * dm);
+                            rem = qq;
+                            w *= __ldg(a.lead.fac[m] + (size_t)idx * ldr + n);
+                        }
                     }
+                    wv[u] = w;
                 }
-                const int nl = n + N;
-                *reinterpret_cast<float*>(bt + (unsigned)(n >> 3) * 256u + (unsigned)(k >> 2) * 128u + (unsigned)(n & 7) * 16u + (unsigned)(k & 3) * 4u) = w;
-                *reinterpret_cast<float*>(bt + (unsigned)(nl >> 3) * 256u + (unsigned)(k >> 2) * 128u + (unsigned)(nl & 7) * 16u + (unsigned)(k & 3) * 4u) = tf32_lo(w);
+            }
+            mbar_wait(empty2 + s2, ph2 ^ 1u);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int it = tg + u * 128;
+                if (it < ((a.dbg & 2) ? 0 : N * 8)) {
+                    const int n = it % N, k = it / N, nl = n + N;
+                    *reinterpret_cast<float*>(bt + (unsigned)(n >> 3) * 256u + (unsigned)(k >> 2) * 128u + (unsigned)(n & 7) * 16u + (unsigned)(k & 3) * 4u) = wv[u];
+                    *reinterpret_cast<float*>(bt + (unsigned)(nl >> 3) * 256u + (unsigned)(k >> 2) * 128u + (unsigned)(nl & 7) * 16u + (unsigned)(k & 3) * 4u) = tf32_lo(wv[u]);
+                }
             }
             mbar_wait(fullx + sx, phx);
             if (!(a.dbg & 1)) {
