@@ -585,3 +585,13 @@ def test_batched_elbow_equals_unbatched_elbow():
     b = _multiple_runs_elbow_analysis(x, upper_rank=7, runs=4, init="random", random_state=11, n_iter_max=25, tol=-1.0, batch_runs=False)
     assert a.shape == b.shape == (4, 7)
     np.testing.assert_allclose(a, b, rtol=2e-5)
+
+
+def test_mma_hals_matches_oracle(mma_from_rank_1):
+    """HALS (unfused update kernels) over the tensor-pipe passes."""
+    _compare_run(lowrank((40, 500, 16, 8), 6, seed=13), 16, 12, hals=True)
+
+
+def test_mma_short_runs_without_graph(mma_from_rank_1):
+    """n_iter_max < 3: the iteration is enqueued directly (no CUDA graph), dependent launches on the caller's stream."""
+    _compare_run(lowrank((40, 500, 16, 8), 6, seed=14), 20, 2)
