@@ -58,17 +58,21 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons of the job's GPUs, sampled every 200 ms while the timed region runs.  ONE sampler
+    per job (rank 0 watches every GPU): eight per-rank samplers at 50 ms were measured to slow the ranks' own launches
+    (39 vs 31 ms per step on 8 GPUs with clocks unchanged)."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices, enabled=True):
+        self.indices, self.rows, self.proc, self.enabled = [int(i) for i in indices], [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(map(str, self.indices)), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -91,19 +95,20 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        per, mx, reasons = {}, 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
+                per.setdefault(int(r[0]), []).append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        med = {k: float(np.median(v)) for k, v in per.items()}
+        return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": sum(len(v) for v in per.values()), "per_gpu_sm_mhz": [med.get(i) for i in self.indices]}
 
 
 def synth_host(shape, seed, pinned=True):
@@ -147,7 +152,7 @@ def run_reference(args, rank_id, world):
                 args.workload, "x".join(map(str, wl["shape"])), wl["rank"]), "iterations_per_step": iters},
             "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def time_kernel(fn, reps):
@@ -197,7 +202,7 @@ def run_ours(args, rank_id, local_rank, world):
     barrier()
     n0 = engine.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(range(world) if world > 1 else [local_rank], enabled=(rank_id == 0)) as clk:
         ev0.record()
         last_err = None
         for s in range(args.warmup, args.warmup + args.steps):
@@ -274,11 +279,8 @@ def run_ours(args, rank_id, local_rank, world):
 
     times = torch.tensor([sec, e2e_sec], dtype=torch.float64, device=dev)
     my_clk = clk.summary()
-    per_rank = torch.zeros((world, 3), dtype=torch.float64, device=dev)      # [seconds, median SM MHz, any throttle reason]
-    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    per_rank[rank_id, 0] = sec
-    per_rank[rank_id, 1] = float(my_clk["sm_mhz"] or 0.0)
-    per_rank[rank_id, 2] = 1.0 if bad & set(my_clk["reasons"]) else 0.0
+    per_rank = torch.zeros(world, dtype=torch.float64, device=dev)             # seconds of the timed region on every GPU
+    per_rank[rank_id] = sec
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
@@ -305,8 +307,8 @@ def run_ours(args, rank_id, local_rank, world):
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_sec / e2e_steps,
                 "api": "PreBuiltTensor(pinned host fp32).compute_tensor_factorization(rank, init='random', n_iter_max=%d, tol=-1)" % iters},
         "gpu_launches": int(launches),
-        "clocks": dict(my_clk, per_gpu_sm_mhz=[float(v) for v in per_rank[:, 1]], any_gpu_thermal_or_hw_slowdown=bool(per_rank[:, 2].any())),
-        "per_gpu_ms_per_step": [round(1e3 * float(v) / args.steps, 3) for v in per_rank[:, 0]],
+        "clocks": my_clk,
+        "per_gpu_ms_per_step": [round(1e3 * float(v) / args.steps, 3) for v in per_rank],
         "roofline": {"bound": "hbm", "kernel": name, "achieved": n_x * 4 / worst / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": n_x * 4 / worst / 1e9 / peak, "traffic": ncu_traffic(name), "peak_kind": "of " + peak_kind,
                      "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
@@ -329,7 +331,7 @@ def run_ours(args, rank_id, local_rank, world):
         line["cpu_baseline"] = {"value": n_it / tcpu, "unit": "iterations/s", "cores": threads, "kind": "port",
                                 "sample": "%d MU iterations on the full %s fp64 tensor, rank %d, numpy restatement of the "
                                           "tensorly path (oracle/ncp_oracle.py)" % (n_it, "x".join(map(str, shape)), rank)}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_sharded(args, rank_id, local_rank, world):
@@ -367,14 +369,35 @@ def run_sharded(args, rank_id, local_rank, world):
     if rank_id != 0:
         return
     sec = float(t[0])
-    print(json.dumps({"metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": steps * iters / sec,
+    emit({"metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": steps * iters / sec,
                       "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": max(1, args.warmup // 3),
                       "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "%s %s rank %d, ONE factorization sharded along the context mode" % (
                           args.workload, "x".join(map(str, shape)), rank), "iterations_per_step": iters,
                           "collectives_per_iteration": len(shape) - 1},
-                      "final_rec_error": errs[-1]}), flush=True)
+                      "final_rec_error": errs[-1]})
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything libraries print (NCCL's version banner, torchrun
+    notices) was redirected to stderr by ``quiet_stdout``."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -401,6 +424,7 @@ def main():
     rank_id = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank_id, world)
         return
