@@ -228,7 +228,6 @@ static int env_int(const char* name, int dflt)
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
-static int mma_lring() { static int v = -1; if (v < 0) { v = env_int("C2C_B200_MMA_LRING", 3); if (v < 2) v = 2; } return v; }
 static int mma_dbg() { static int v = -1; if (v < 0) v = env_int("C2C_B200_MMA_DBG", 0); return v; }
 
 static int mma_epoch()
