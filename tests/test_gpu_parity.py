@@ -595,3 +595,34 @@ def test_mma_hals_matches_oracle(mma_from_rank_1):
 def test_mma_short_runs_without_graph(mma_from_rank_1):
     """n_iter_max < 3: the iteration is enqueued directly (no CUDA graph), dependent launches on the caller's stream."""
     _compare_run(lowrank((40, 500, 16, 8), 6, seed=14), 20, 2)
+
+
+def test_api_shortcuts_keep_the_reference_values():
+    """The API-path shortcuts (finite check through sum(x^2), cached ||X||^2, recon sums shared between the factorization's last
+    pass and explained_variance, lazy loc_nans / loc_zeros) return what the long way returns."""
+    from cell2cell_b200 import engine
+    from cell2cell_b200.tensor import PreBuiltTensor
+    x = lowrank((6, 40, 9, 9), 3, seed=31)
+    x[x < 0.35] = 0.0
+    names = [list(range(s)) for s in x.shape]
+    t = PreBuiltTensor(x, order_names=names)
+    assert t.mask is None and abs(t.tensor._c2c_norm_x2 - float((x.astype(np.float64) ** 2).sum())) < 1e-6 * float((x ** 2).sum())
+    assert int(t.loc_nans.sum()) == 0 and np.array_equal(t.loc_zeros.cpu().numpy(), (x == 0).astype(np.uint8))
+    assert t.missing_fraction() == 0.0 and abs(t.sparsity_fraction() - float((x == 0).mean())) < 1e-12
+    t.compute_tensor_factorization(rank=3, init="random", random_state=4, n_iter_max=30, tol=-1.0)
+    cached = t.explained_variance_
+    assert getattr(t.tl_object, "recon_sums_", None) is not None
+    t.tl_object.recon_sums_ = None
+    assert abs(t.explained_variance() - cached) < 1e-9
+    rec = t.tl_object.to_tensor().double()
+    X = t.tensor.double()
+    want = 1.0 - float(((X - rec) - (X - rec).mean()).norm() / (X - X.mean()).norm())
+    assert abs(cached - want) < 1e-5
+    # a tensor with NaN / inf takes the full clean-up path (tensor.py:933-946)
+    y = x.copy()
+    y[0, 1, 2, 3] = np.nan
+    y[1, 0, 0, 0] = np.inf
+    u = PreBuiltTensor(y, order_names=names)
+    assert int(u.loc_nans.sum()) == 1 and bool(torch.isfinite(u.tensor).all()) and not hasattr(u.tensor, "_c2c_norm_x2")
+    assert float(u.tensor[0, 1, 2, 3]) == 0.0 and float(u.tensor[1, 0, 0, 0]) == float(np.finfo(np.float32).max)
+    assert abs(engine.sumsq(t.tensor) - t.tensor._c2c_norm_x2) == 0.0
