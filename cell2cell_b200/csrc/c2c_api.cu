@@ -241,8 +241,10 @@ static void mma_geometry(Geo& g, int rank)
 {
     g.mma_ok = 0; g.mma_fiber_ok = 0;
     const int nsm = sm_count();
-    // shapes the FFMA kernels only take with narrow (< 128-bit) loads go to the tensor pipe at every rank
-    const int min_rank = g.vec_plane < 4 ? 1 : mma_min_rank();
+    // shapes the FFMA kernels only take with narrow (< 128-bit) loads go to the tensor pipe at every rank; the plane pass
+    // switches two ranks before the fiber pass (measured at 60x2000x40x40: plane_mma 0.135 ms vs plane_stream 0.145 / 0.155 ms
+    // at ranks 11 / 12, fiber_mma 0.167 vs fiber_stream 0.145 at rank 12)
+    const int min_rank = g.vec_plane < 4 ? 1 : (mma_min_rank() > 2 ? mma_min_rank() - 2 : 1);
     if (rank < min_rank || rank > 32 || g.nchunk != 1 || mma_min_rank() > 32 || !c2c_mma_available()) return;
     if (g.E % 4 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
     const int n = rank <= 16 ? 16 : 32;
@@ -293,7 +295,7 @@ static void mma_geometry(Geo& g, int rank)
         }
         // a ragged last atom (in-plane size not a multiple of 32 floats) needs one small TMA box per atom: slower than the
         // FFMA pass below the rank where that pass leaves the HBM roof
-        const bool fiber_worth = (g.E % 32 == 0) || rank >= mma_min_rank();
+        const bool fiber_worth = rank >= mma_min_rank() || (g.E % 32 == 0 && g.vec_plane < 4);
         if (best_es != 0 && nsm / best_es >= 1 && fiber_worth) {
             g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
             g.fm_nstages = best_nx; g.fm_stack = best_stack; g.fm_in_smem = best_in_smem;

@@ -120,6 +120,20 @@ __host__ __device__ constexpr unsigned c2c_tmem_cols(unsigned need) { return nee
 // plane_mma
 // --------------------------------------------------------------------------------------------------------------------
 #define C2C_PM_CHUNK 2          // k blocks per accumulator chain (8 MMAs into the hi columns)
+// C2C_PM_ALL_TS (default): hi(X) goes through TMEM too (both MMAs take their A operand from TMEM): the X tile in shared
+// memory is read once (by the prep warps) instead of twice, and its ring slot is released by them instead of by the MMA
+// commit.  Measured against the shared-memory A operand (-DC2C_PM_SMEM_A): 0.160 -> 0.135 ms per pass at N = 16,
+// 0.178 -> 0.164 at N = 32 -- shared-memory bandwidth (TMA write + prep read + MMA read) is what bounds these kernels.
+#ifndef C2C_PM_SMEM_A
+#define C2C_PM_ALL_TS 1
+#endif
+#ifdef C2C_PM_ALL_TS
+#define C2C_PM_EMPTYX_COUNT 4
+#define C2C_PM_A_COLS 64        // TMEM columns per prep slot: hi | lo
+#else
+#define C2C_PM_EMPTYX_COUNT 1
+#define C2C_PM_A_COLS 32
+#endif
 
 struct PlaneMmaArgs {
     long long P;               // planes
@@ -162,7 +176,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < DX; ++s) { mbar_init(fullx + s, 1); mbar_init(emptyx + s, 1); }
+        for (int s = 0; s < DX; ++s) { mbar_init(fullx + s, 1); mbar_init(emptyx + s, C2C_PM_EMPTYX_COUNT); }
         for (int s = 0; s < D2; ++s) { mbar_init(ready + s, 4); mbar_init(empty2 + s, 1); }
         for (int s = 0; s < NR; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
         mbar_init_fence();
@@ -207,17 +221,23 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                     tc_fence_after();
                     const unsigned d = tmem + (unsigned)(r * 2 * N);
                     for (long long gg = g; gg < chunk_end; ++gg) {
-                        mbar_wait(fullx + sx, phx);
+#ifndef C2C_PM_ALL_TS
+                        mbar_wait(fullx + sx, phx);              // (all-TS: the issuer never touches the X ring -- its slots may be
+#endif                                                           //  a phase ahead by now, a wait here would alias)
                         mbar_wait(ready + s2, ph2);
                         tc_fence_after();
                         if (elect_one()) {
                             const unsigned long long dx = DK + (xa0 + (unsigned)sx * (L::X_BYTES >> 4));
                             const unsigned long long db = DK + (ba0 + (unsigned)s2 * (L::B_BYTES >> 4));
-                            const unsigned alo = tmem + (unsigned)(L::ALO_COL + s2 * 32);
+                            const unsigned alo = tmem + (unsigned)(L::ALO_COL + s2 * C2C_PM_A_COLS + (C2C_PM_A_COLS - 32));
                             if (!(a.dbg & 4)) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks) {
+#ifdef C2C_PM_ALL_TS
+                                    umma_tf32_ts(d, alo - 32 + ks * 8, db + 2 * ks, IDESC2, (gg > g || ks > 0) ? 1u : 0u);
+#else
                                     umma_tf32(d, dx + 2 * ks, db + 2 * ks, IDESC2, (gg > g || ks > 0) ? 1u : 0u);   // [hi(x) hi(b) | hi(x) lo(b)]
+#endif
                                     umma_tf32_ts(d + N, alo + ks * 8, db + 2 * ks, IDESC1, 1u);                    // lo(x) hi(b) -> the lo columns
                                 }
                                 if (a.dbg & 16) {                   // timing experiment: the same MMAs once more (results are wrong)
@@ -228,7 +248,11 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                                     }
                                 }
                             }
+#ifndef C2C_PM_ALL_TS
                             umma_commit(emptyx + sx);
+#else
+                            (void)dx;
+#endif
                             umma_commit(empty2 + s2);
                             if (gg + 1 == chunk_end) umma_commit(tfull + r);
                         }
@@ -328,7 +352,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                 // lane = plane row of the tile: its 32 floats, lo part, to the TMEM columns of this slot
                 const int row = lq * 32 + lane;
                 const unsigned char* xr = xring + (size_t)sx * L::X_BYTES + (size_t)row * 128;
-                const unsigned taddr = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)(L::ALO_COL + s2 * 32);
+                const unsigned taddr = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)(L::ALO_COL + s2 * C2C_PM_A_COLS + (C2C_PM_A_COLS - 32));
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     const float4 v0 = *reinterpret_cast<const float4*>(xr + ((c ^ (row & 7)) << 4));
@@ -336,9 +360,17 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                     const float lo8[8] = {tf32_lo(v0.x), tf32_lo(v0.y), tf32_lo(v0.z), tf32_lo(v0.w),
                                           tf32_lo(v1.x), tf32_lo(v1.y), tf32_lo(v1.z), tf32_lo(v1.w)};
                     tmem_st8(taddr + c * 4, lo8);
+#ifdef C2C_PM_ALL_TS
+                    const float hi8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};      // the hardware truncates: hi(x)
+                    tmem_st8(taddr - 32 + c * 4, hi8);
+#endif
                 }
                 tmem_st_wait();
             }
+#ifdef C2C_PM_ALL_TS
+            __syncwarp();
+            if (lane == 0) mbar_arrive(emptyx + sx);             // this warp is done with the X tile
+#endif
             proxy_fence_async();
             tc_fence_before();
             __syncwarp();
