@@ -88,7 +88,7 @@ struct Geo {
     int mma_ok, mma_n;         // mma_ok: plane_mma applies;  mma_fiber_ok: fiber_mma applies too
     int mma_fiber_ok;
     int pm_nstages, pm_grid, pm_nkb; long long pm_ntiles; size_t pm_smem;
-    int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack, fm_in_smem; long long fm_nst; size_t fm_smem;
+    int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack, fm_in_smem, fm_ring2; long long fm_nst; size_t fm_smem;
 };
 
 #define C2C_SMEM_BUDGET (200 * 1024)
@@ -275,9 +275,12 @@ static void mma_geometry(Geo& g, int rank)
                 const int na = (na_total + cand - 1) / cand;
                 if (na < 4) break;
                 const int ntile = (na + 3) / 4;
-                const int stack = ntile * (2 * n + 8 * C2C_MMA_RING2) <= 512;
+                // TMEM: accumulators (N or 2N columns per tile) + the X ring in TMEM: hi | lo (16 columns per tile and prep slot, all
+                // MMAs from TMEM: N = 16) or lo only (8 columns, hi(X) read from shared memory: N = 32)
+                const int a_cols = n == 16 ? 16 : 8;
+                const int stack = ntile * (2 * n + a_cols * (n == 16 ? 3 : C2C_MMA_RING2)) <= 512;
                 if (pass == 0 && (!stack || cand > 2)) continue;
-                if (ntile > C2C_FM_MAXTILE || ntile * (n + 8 * C2C_MMA_RING2) > 512) continue;
+                if (ntile > C2C_FM_MAXTILE || ntile * (n + a_cols * (n == 16 ? 3 : C2C_MMA_RING2)) > 512) continue;
                 // running sums in shared memory when that still leaves >= 5 X slots, else in the global partial
                 int in_smem = 1;
                 size_t fixed = c2c_fiber_mma_smem(n, na, ldr, 0);
@@ -299,6 +302,11 @@ static void mma_geometry(Geo& g, int rank)
         if (best_es != 0 && nsm / best_es >= 1 && fiber_worth) {
             g.fm_es = best_es; g.fm_na_total = na_total; g.fm_na = (na_total + best_es - 1) / best_es; g.fm_ntile = (g.fm_na + 3) / 4;
             g.fm_nstages = best_nx; g.fm_stack = best_stack; g.fm_in_smem = best_in_smem;
+            {
+                const int acc = g.fm_ntile * (best_stack ? 2 * n : n);
+                int r2 = (512 - acc) / (g.fm_ntile * (n == 16 ? 16 : 8));
+                g.fm_ring2 = r2 > C2C_MMA_RING2 ? C2C_MMA_RING2 : r2;
+            }
             g.fm_nj = nsm / best_es;
             g.fm_grid = g.fm_nj * best_es;
             g.fm_nst = (g.P + 7) / 8;
@@ -540,9 +548,9 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         memset(&fa, 0, sizeof(fa));
         fa.P = g.P; fa.E = (int)g.E; fa.R = a.R; fa.ldr = a.ldr; fa.lead = a.lead; fa.part = w.part; fa.done = a.done;
         fa.es = g.fm_es; fa.na_total = g.fm_na_total; fa.na = g.fm_na; fa.ntile = g.fm_ntile; fa.nx = g.fm_nstages; fa.dbg = mma_dbg(); fa.nst_total = g.fm_nst; fa.epoch = mma_epoch() > 0 ? mma_epoch() : 16;
-        fa.boxes2d = boxes2d; fa.sums_in_smem = g.fm_in_smem;
+        fa.boxes2d = boxes2d; fa.sums_in_smem = g.fm_in_smem; fa.ring2 = g.fm_ring2;
         fa.zero_ptr = reinterpret_cast<float4*>(po.zero_T); fa.zero_n4 = po.zero_n / 4;
-        const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, map, fa, g.fm_grid, g.fm_smem, st, po.pdl);
+        const cudaError_t e = c2c_launch_fiber_mma(g.mma_n, g.fm_stack, g.mma_n == 16 ? 1 : 0, map, fa, g.fm_grid, g.fm_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_mma launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         nparts = g.fm_nj;

@@ -9,12 +9,12 @@ static cudaError_t launch_plane_n(const CUtensorMap& map, const PlaneMmaArgs& a,
     return c2c_launch_ex(plane_mma_kernel<N>, dim3(grid), dim3(C2C_MMA_THREADS), smem, st, pdl, map, a);
 }
 
-template <int N, bool STACK>
+template <int N, bool STACK, bool ALLTS>
 static cudaError_t launch_fiber_n(const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
-    cudaError_t e = cudaFuncSetAttribute(fiber_mma_kernel<N, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fiber_mma_kernel<N, STACK, ALLTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return c2c_launch_ex(fiber_mma_kernel<N, STACK>, dim3(grid), dim3(C2C_MMA_THREADS), smem, st, pdl, map, a);
+    return c2c_launch_ex(fiber_mma_kernel<N, STACK, ALLTS>, dim3(grid), dim3(C2C_MMA_THREADS), smem, st, pdl, map, a);
 }
 
 cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
@@ -26,11 +26,12 @@ cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaAr
     }
 }
 
-cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
+cudaError_t c2c_launch_fiber_mma(int n, int stack, int allts, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl)
 {
     switch (n) {
-        case 16: return stack ? launch_fiber_n<16, true>(map, a, grid, smem, st, pdl) : launch_fiber_n<16, false>(map, a, grid, smem, st, pdl);
-        case 32: return stack ? launch_fiber_n<32, true>(map, a, grid, smem, st, pdl) : launch_fiber_n<32, false>(map, a, grid, smem, st, pdl);
+        case 16: return allts ? (stack ? launch_fiber_n<16, true, true>(map, a, grid, smem, st, pdl) : launch_fiber_n<16, false, true>(map, a, grid, smem, st, pdl))
+                              : (stack ? launch_fiber_n<16, true, false>(map, a, grid, smem, st, pdl) : launch_fiber_n<16, false, false>(map, a, grid, smem, st, pdl));
+        case 32: return stack ? launch_fiber_n<32, true, false>(map, a, grid, smem, st, pdl) : launch_fiber_n<32, false, false>(map, a, grid, smem, st, pdl);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -386,6 +386,12 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
 // fiber_mma
 // --------------------------------------------------------------------------------------------------------------------
 #define C2C_FM_MAXTILE 8
+// C2C_FM_ALL_TS (default): as in plane_mma, hi(X) and lo(X) both go through TMEM (16 columns per tile and prep slot), every MMA
+// takes its A operand from TMEM, the X ring slot is released by the prep warps.  The TMEM budget then decides the depth of
+// the prep ring (`ring2`): (512 - accumulator columns) / (16 columns x tiles), 2..4.  -DC2C_FM_SMEM_A restores the
+// shared-memory A operand (MN-major descriptors over the TMA image).
+// It is a template parameter (ALLTS): validated for N = 16 (prep ring of 3); the N = 32 instance (prep ring of 2) gave wrong
+// results / did not finish in the one run it got, so N = 32 keeps the shared-memory A operand for now.
 
 struct FiberMmaArgs {
     long long P; int E, R, ldr;
@@ -401,6 +407,7 @@ struct FiberMmaArgs {
     int dbg;                   // timing experiments only (see PlaneMmaArgs)
     int epoch;                 // stages per accumulator chain
     long long nst_total;       // 8-plane stages: ceil(P / 8)
+    int ring2;                 // depth of the prep -> MMA ring (B tile in shared memory + hi/lo(X) columns in TMEM), <= C2C_MMA_RING2
     int sums_in_smem;          // 1: the CTA's running sums live in shared memory ([na * 32][ldr] floats after the B ring) and are
                                // copied out at the end; 0: they are kept in the (L2-resident) global partial itself
     int boxes2d;               // 1: the tensor map is 2-D {E, P} and a stage is `na` boxes of {32, 8} (in-plane size not a multiple of 32
@@ -410,13 +417,14 @@ struct FiberMmaArgs {
 };
 
 // STACK: hi(x) hi(w) and hi(x) lo(w) in one MMA over the stacked B tile (needs 2N accumulator columns per tile)
-template <int N, bool STACK>
+template <int N, bool STACK, bool ALLTS>
 __global__ void __launch_bounds__(C2C_MMA_THREADS, 1)
 fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
 {
     if (run_done(a.done)) return;
-    constexpr int D2 = C2C_MMA_RING2;
+    const int D2 = a.ring2;
     constexpr int ACC_COLS = STACK ? 2 * N : N;                  // accumulator columns per tile
+    constexpr int A_COLS = ALLTS ? 16 : 8;                       // TMEM columns per tile and prep slot: hi | lo, or lo only
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int DX = a.nx, na = a.na, ntile = a.ntile, R = a.R, ldr = a.ldr, F = a.epoch;
@@ -424,16 +432,16 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
     constexpr int B_BYTES = 2 * N * 32;                          // rows 0..N-1 hi(W^T), N..2N-1 lo(W^T); 8 planes each, K-major core matrices
     unsigned char* xring = base;
     unsigned char* bring = base + (size_t)DX * x_bytes;
-    float* spart = reinterpret_cast<float*>(bring + (size_t)D2 * B_BYTES);             // [na * 32][ldr] when sums_in_smem
+    float* spart = reinterpret_cast<float*>(bring + (size_t)C2C_MMA_RING2 * B_BYTES);  // [na * 32][ldr] when sums_in_smem
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(spart + (a.sums_in_smem ? (size_t)na * 32 * ldr : 0));
-    unsigned long long *fullx = bars, *emptyx = bars + DX, *ready = bars + 2 * DX, *empty2 = ready + D2, *tfull = empty2 + D2, *tempty = tfull + C2C_FM_MAXTILE;
+    unsigned long long *fullx = bars, *emptyx = bars + DX, *ready = bars + 2 * DX, *empty2 = ready + C2C_MMA_RING2, *tfull = empty2 + C2C_MMA_RING2, *tempty = tfull + C2C_FM_MAXTILE;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + C2C_FM_MAXTILE);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const unsigned alo_col = (unsigned)(ntile * ACC_COLS);       // lo(X) ring: D2 x ntile x 8 columns
-    const unsigned tm_cols = c2c_tmem_cols(alo_col + (unsigned)(D2 * ntile * 8));
+    const unsigned alo_col = (unsigned)(ntile * ACC_COLS);       // hi/lo(X) ring: D2 x ntile x A_COLS columns
+    const unsigned tm_cols = c2c_tmem_cols(alo_col + (unsigned)(D2 * ntile * A_COLS));
 
     if (tid == 0) {
-        for (int s = 0; s < DX; ++s) { mbar_init(fullx + s, 1); mbar_init(emptyx + s, 1); }
+        for (int s = 0; s < DX; ++s) { mbar_init(fullx + s, 1); mbar_init(emptyx + s, ALLTS ? 4 : 1); }
         for (int s = 0; s < D2; ++s) { mbar_init(ready + s, 4); mbar_init(empty2 + s, 1); }
         for (int s = 0; s < C2C_FM_MAXTILE; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
         mbar_init_fence();
@@ -483,7 +491,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
             while (g < se) {
                 const long long ep_end = g + F < se ? g + F : se;
                 for (long long gg = g; gg < ep_end; ++gg) {
-                    mbar_wait(fullx + sx, phx);
+                    if (!ALLTS) mbar_wait(fullx + sx, phx);      // (all-TS: the issuer never touches the X ring)
                     mbar_wait(ready + s2, ph2);
                     if (gg == g) {
                         for (int i = 0; i < ntile; ++i) mbar_wait(tempty + i, phe ^ 1u);      // the previous chains are drained
@@ -494,7 +502,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
                         const unsigned long long dbh = DKB + (ba0 + (unsigned)s2 * (B_BYTES >> 4));      // rows 0 ..
                         const unsigned long long dbl = dbh + (N / 8) * (256 >> 4);                     // rows N ..
                         const unsigned acc = gg > g ? 1u : 0u;
-                        const unsigned alo = tmem + alo_col + (unsigned)(s2 * ntile * 8);
+                        const unsigned alo = tmem + alo_col + (unsigned)(s2 * ntile * A_COLS);
                         const bool last = gg + 1 == ep_end;
 #pragma unroll
                         for (int i = 0; i < C2C_FM_MAXTILE; ++i) {
@@ -502,7 +510,18 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
                                 const int at = i + 1 < ntile ? 4 * i : last_at;
                                 const unsigned long long dxh = dxa + (unsigned)(at * 64);
                                 const unsigned d = tmem + (unsigned)(i * ACC_COLS);
-                                if (STACK) {
+                                if constexpr (ALLTS) {
+                                    constexpr unsigned IDESC2T = umma_idesc_tf32(2 * N, 0);
+                                    const unsigned ahi = alo + i * 16, alw = ahi + 8;
+                                    if (STACK) {
+                                        umma_tf32_ts(d, ahi, dbh, IDESC2T, acc);                       // [hi(x) hi(w) | hi(x) lo(w)]
+                                        umma_tf32_ts(d + N, alw, dbh, IDESC1T, 1u);                    // lo(x) hi(w) -> the lo columns
+                                    } else {
+                                        umma_tf32_ts(d, alw, dbh, IDESC1T, acc);                       // small terms first
+                                        umma_tf32_ts(d, ahi, dbl, IDESC1T, 1u);
+                                        umma_tf32_ts(d, ahi, dbh, IDESC1T, 1u);
+                                    }
+                                } else if (STACK) {
                                     umma_tf32(d, dxh, dbh, IDESC2, acc);                               // [hi(x) hi(w) | hi(x) lo(w)]
                                     umma_tf32_ts(d + N, alo + i * 8, dbh, IDESC1T, 1u);                // lo(x) hi(w) -> the lo columns
                                 } else {
@@ -514,7 +533,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
                             }
                         }
                         if ((a.dbg & 4) && last) { for (int i = 0; i < ntile; ++i) umma_commit(tfull + i); }
-                        umma_commit(emptyx + sx);
+                        if (!ALLTS) umma_commit(emptyx + sx);
                         umma_commit(empty2 + s2);
                     }
                     __syncwarp();
@@ -665,15 +684,22 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
                     const int at = (i + 1 < ntile || (na & 3) == 0) ? 4 * i : na - 4;
                     const int ei = lane;                                            // position inside the atom
                     const unsigned char* xa = xst + (size_t)(at + lq) * 1024;
-                    float lo8[8];
+                    float lo8[8], hi8[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const float v = *reinterpret_cast<const float*>(xa + k * 128 + ((((ei >> 3) ^ (k & 3))) << 5) + (ei & 7) * 4);
                         lo8[k] = tf32_lo(v);
+                        hi8[k] = v;                                                 // the hardware truncates: hi(x)
                     }
-                    tmem_st8(tmem + ((unsigned)(lq * 32) << 16) + alo_col + (unsigned)(s2 * ntile * 8 + i * 8), lo8);
+                    const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + alo_col + (unsigned)(s2 * ntile * A_COLS + i * A_COLS);
+                    if (ALLTS) { tmem_st8(ta, hi8); tmem_st8(ta + 8, lo8); }
+                    else tmem_st8(ta, lo8);
                 }
                 tmem_st_wait();
+            }
+            if (ALLTS) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(emptyx + sx);         // this warp is done with the stage's planes
             }
             proxy_fence_async();
             tc_fence_before();
@@ -688,7 +714,7 @@ fiber_mma_kernel(const __grid_constant__ CUtensorMap mapX, const FiberMmaArgs a)
 
 // launchers (c2c_mma.cu); n = MMA N in {16, 32}
 cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
-cudaError_t c2c_launch_fiber_mma(int n, int stack, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
+cudaError_t c2c_launch_fiber_mma(int n, int stack, int allts, const CUtensorMap& map, const FiberMmaArgs& a, int grid, size_t smem, cudaStream_t st, int pdl);
 size_t c2c_plane_mma_smem(int n, int I2, int I3, int nx);
 size_t c2c_fiber_mma_smem(int n, int na, int ldr, int nx);       // ldr = 0: running sums not in shared memory
 // tensor maps over X: [P][E] rows of 32 floats (128-byte swizzle) / {32, P, E/32} (32-byte-atom 128-byte swizzle)
