@@ -925,6 +925,21 @@ extern "C" int c2c_mu_update(float* A_mode, const float* M, const float* G, int6
     return launch_mu(A_mode, M, G, I, rank, ldr, eps, w, false, false, nullptr, (cudaStream_t)stream);
 }
 
+extern "C" int c2c_mu_update_coupled(float* A1_mode, float* A2_mode, const float* M1, const float* M2, const float* G1,
+                                     const float* G2, int64_t I, int rank, int ldr, float eps, double* iprod, void* stream)
+{
+    if (!A1_mode || !A2_mode || !M1 || !M2 || !G1 || !G2) return fail(-1, "NULL argument");
+    if (I < 1 || rank < 1 || rank > C2C_MAX_RANK || ldr != ldr_of(rank)) return fail(-2, "bad I / rank / ldr");
+    if (A1_mode == A2_mode) return fail(-2, "the two tensors keep separate copies of a shared factor");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (iprod) CK(cudaMemsetAsync(iprod, 0, 2 * sizeof(double), st), "iprod memset");
+    const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+    const size_t smem = (size_t)2 * C2C_UPD_ROWS * rank * sizeof(float);
+    mu_update_coupled_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(A1_mode, A2_mode, M1, M2, G1, G2, I, rank, ldr, eps, iprod);
+    CKL("mu_update_coupled launch");
+    return 0;
+}
+
 extern "C" int c2c_hals_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, int max_sweeps,
                                float tol, void* stream)
 {

@@ -13,7 +13,7 @@ from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, li
 
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
            "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
-           "mu_update", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "build_ccc", "group_aggregate"]
+           "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "build_ccc", "group_aggregate"]
 
 _vp = ctypes.c_void_p
 
@@ -185,6 +185,15 @@ def mu_update(A, M, G, rank, eps=float(np.finfo(np.float32).eps)):
         check(lib().c2c_mu_update(_ptr(A), _ptr(M), _ptr(G), A.shape[0], rank, ldr_of(rank), eps, _vp(0), 0, _stream()),
               "c2c_mu_update")
     return A
+
+
+def mu_update_coupled(A1, A2, M1, M2, G1, G2, rank, iprod=None, eps=float(np.finfo(np.float32).eps)):
+    """Shared-mode update of the coupled factorization: averaged numerators / denominators of the two tensors, the new factor
+    written to both copies ``A1`` / ``A2``; ``iprod`` (fp64 ``[2]`` CUDA tensor or None) receives ``sum(M_k * new)``."""
+    with torch.cuda.device(A1.device):
+        check(lib().c2c_mu_update_coupled(_ptr(A1), _ptr(A2), _ptr(M1), _ptr(M2), _ptr(G1), _ptr(G2), A1.shape[0], rank,
+                                          ldr_of(rank), eps, _ptr(iprod), _stream()), "c2c_mu_update_coupled")
+    return A1
 
 
 def hals_update(A, M, G, rank, max_sweeps=100, tol=1e-8):

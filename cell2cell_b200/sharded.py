@@ -47,11 +47,11 @@ class DeviceOps:
     def sumsq(self, X):
         return engine.sumsq(X)
 
-    def plane(self, X, factors, ws):
-        return engine.plane_contract(X, None, factors, self.R, ws=ws)
+    def plane(self, X, factors, ws, out=None):
+        return engine.plane_contract(X, None, factors, self.R, ws=ws, out=out)
 
-    def fiber(self, X, factors, ws):
-        return engine.fiber_contract(X, None, factors, self.R, ws=ws)
+    def fiber(self, X, factors, ws, out=None):
+        return engine.fiber_contract(X, None, factors, self.R, ws=ws, out=out)
 
     def m_from(self, TU, shape, factors, mode):
         return engine.mttkrp_from_contraction(TU, shape, factors, self.R, mode)
@@ -65,8 +65,18 @@ class DeviceOps:
     def mu_update(self, A, M, G):
         return engine.mu_update(A, M, G, self.R)
 
-    def workspace(self, shape, device):
-        return engine.Workspace(shape, self.R, False, device)
+    def workspace(self, shape, device, masked=False):
+        return engine.Workspace(shape, self.R, masked, device)
+
+    # ---- used by the coupled factorization (tensor/coupled_factorization.py) ----
+    def masked_mttkrp(self, X, mask, factors, mode, ws):
+        return engine.mttkrp(X, mask, factors, self.R, mode, ws=ws)
+
+    def mu_update_coupled(self, A1, A2, M1, M2, G1, G2, iprod):
+        return engine.mu_update_coupled(A1, A2, M1, M2, G1, G2, self.R, iprod=iprod)
+
+    def recon_sums(self, X, mask, factors, ws):
+        return engine.recon_sums(X, mask, factors, self.R, ws=ws)
 
 
 def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter_max=100, tol=1e-6, group=None, ops=None,

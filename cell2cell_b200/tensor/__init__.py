@@ -4,9 +4,11 @@ from .tensor import (BaseTensor, InteractionTensor, PreBuiltTensor, build_contex
 from .factorization import (non_negative_parafac, non_negative_parafac_hals, normalized_error)
 from .cp import CPTensor
 from .external_scores import dataframes_to_tensor
+from .coupled_factorization import coupled_non_negative_parafac
+from .coupled_tensor import CoupledInteractionTensor
 from .subset import concatenate_interaction_tensors, find_element_indexes, subset_metadata, subset_tensor
 
 __all__ = ["BaseTensor", "InteractionTensor", "PreBuiltTensor", "build_context_ccc_tensor", "generate_tensor_metadata",
            "correlation_index", "pairwise_correlation_index", "non_negative_parafac", "non_negative_parafac_hals",
            "normalized_error", "CPTensor", "dataframes_to_tensor", "subset_tensor", "subset_metadata", "find_element_indexes",
-           "concatenate_interaction_tensors"]
+           "concatenate_interaction_tensors", "coupled_non_negative_parafac", "CoupledInteractionTensor"]

@@ -129,6 +129,14 @@ int c2c_gram_hadamard(const float* const* A /*host array*/, int ndim, const int6
 int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, float eps,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* ---- K4c: shared-mode multiplicative update of the coupled factorization (coupled_factorization.py:432-458) ---------
+ * new = A1 * max((M1 + M2) / 2, eps) / max((A1 G1 + A2 G2) / 2, eps), written to A1_mode and A2_mode (the two tensors'
+ * copies of the shared factor, distinct buffers).  iprod (device double[2], may be NULL) receives sum(M1 * new) and
+ * sum(M2 * new) -- the inner products <X_k, cp_k> of tensorly's error_calc (coupled_factorization.py:473-485) when
+ * this is the last update of the iteration. */
+int c2c_mu_update_coupled(float* A1_mode, float* A2_mode, const float* M1, const float* M2, const float* G1, const float* G2,
+                          int64_t I, int rank, int ldr, float eps, double* iprod, void* stream);
+
 /* ---- K5: HALS column sweeps (tensorly hals_nnls reached from cell2cell/tensor/factorization.py:106-115) ------------
  * sweeps k = 0..R-1: A[:,k] <- max(A[:,k] + (M[:,k] - A G[:,k]) / G[k,k], 0); stops when the squared change of a sweep
  * falls below tol * (first sweep's) or after min(max_sweeps, 2 + 0.5 * (1 + 2 I R / (R R + R))) sweeps. */

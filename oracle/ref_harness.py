@@ -38,6 +38,59 @@ def _stub_package(name, path):
 _loaded = {}
 
 
+def _add_coupled_shim(tl):
+    """What ``cell2cell/tensor/coupled_factorization.py`` needs from tensorly (its imports at :4-12 and the ``tl.*`` calls
+    of :222-482), on numpy.  The array helpers are numpy's; ``initialize_cp`` / ``unfolding_dot_khatri_rao`` /
+    ``error_calc`` / ``cp_normalize`` / ``cp_to_tensor`` are the restatements of ``oracle/ncp_oracle.py`` (tensorly itself is
+    not installable here), so a run of the reference's function under this shim pins the reference's coupling logic, not
+    tensorly's primitives."""
+    from . import ncp_oracle as o
+    tl.eps = lambda dtype: np.finfo(dtype).eps
+    tl.ndim = np.ndim
+    tl.shape = np.shape
+    tl.ones = lambda shape, **k: np.ones(shape, dtype=k.get("dtype", np.float64))
+    tl.dot = np.dot
+    tl.transpose = np.transpose
+    tl.reshape = np.reshape
+    tl.clip = lambda x, a_min=None, a_max=None: np.clip(x, a_min, a_max)
+    tl.copy = np.copy
+    tl.abs = np.abs
+    tl.cp_to_tensor = lambda cp, mask=None: o.cp_to_tensor(cp[0], cp[1], mask=mask)
+
+    def initialize_cp(tensor, rank, init="svd", svd="truncated_svd", non_negative=False, random_state=None,
+                      normalize_factors=False, mask=None, svd_mask_repeats=5):
+        assert non_negative and not normalize_factors
+        return o.CPResult(np.ones(rank), o.initialize_cp(np.asarray(tensor, dtype=np.float64), rank, init=init,
+                                                         random_state=random_state))
+
+    def error_calc(tensor, norm_tensor, weights, factors, sparsity, mask, mttkrp=None):
+        assert not sparsity and mask is None
+        if mttkrp is None:
+            mttkrp = o.mttkrp(tensor, None, factors, np.ndim(tensor) - 1)
+        iprod = np.sum(np.sum(mttkrp * factors[-1], axis=0) * weights)
+        return np.sqrt(np.abs(norm_tensor ** 2 + o.cp_norm(weights, factors) ** 2 - 2 * iprod)), tensor, norm_tensor
+
+    cp_mod = types.ModuleType("tensorly.decomposition._cp")
+    cp_mod.initialize_cp = initialize_cp
+    cp_mod.error_calc = error_calc
+    ct = types.ModuleType("tensorly.cp_tensor")
+    ct.CPTensor = lambda cp: o.CPResult(cp[0], cp[1])
+    ct.unfolding_dot_khatri_rao = lambda tensor, cp, mode: o.mttkrp(tensor, cp[0], cp[1], mode)
+    ct.cp_normalize = lambda cp: o.cp_normalize(cp[0], cp[1])
+    ct.validate_cp_rank = lambda shape, rank="same", rounding="round": int(rank)
+    tl.cp_tensor = ct
+    sys.modules["tensorly.decomposition._cp"] = cp_mod
+    sys.modules["tensorly.cp_tensor"] = ct
+
+
+def load_reference_coupled():
+    """The reference's own ``cell2cell/tensor/coupled_factorization.py`` (file imported unmodified) on the tensorly shim."""
+    load_reference()
+    if "coupled_factorization" not in _loaded:
+        _loaded["coupled_factorization"] = importlib.import_module("cell2cell.tensor.coupled_factorization")
+    return _loaded["coupled_factorization"]
+
+
 def load_reference():
     """Returns a namespace with the reference's build-path modules (tensor, communication_scores, rnaseq, ppi)."""
     if _loaded:
@@ -59,6 +112,7 @@ def load_reference():
     tl.prod = np.prod
     tl.mean = np.mean
     tl.norm = lambda x, order=2: np.sqrt(np.sum(np.asarray(x, dtype=float) ** 2))
+    _add_coupled_shim(tl)
     dec = types.ModuleType("tensorly.decomposition")
     for n in ("non_negative_parafac", "non_negative_parafac_hals", "parafac", "constrained_parafac"):
         setattr(dec, n, None)

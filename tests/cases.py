@@ -103,3 +103,58 @@ LONG_TABLE_OPTIONS = [dict(how=h, outer_fraction=f, lr_fill=lf, cell_fill=cf, du
                       for h, f in (("inner", 0.0), ("outer", 0.0), ("outer", 0.6), ("outer_lrs", 0.0), ("outer_cells", 0.5))
                       for lf, cf in ((np.nan, np.nan), (0.0, np.nan), (np.nan, 0.0))
                       for d in ("max", "min")]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Coupled Tensor Component Analysis (cell2cell/tensor/coupled_factorization.py): seeded pairs of tensors sharing modes
+# ----------------------------------------------------------------------------------------------------------------------
+COUPLED_CASES = {
+    # name: shape1, shape2, mode_mapping, rank, n_iter_max, tol, extra keyword arguments, masked tensors
+    "same_order_int_mapping": dict(shape1=(4, 7, 5, 5), shape2=(4, 9, 5, 5), mode_mapping=1, rank=3, n_iter_max=25, tol=-1.0),
+    "different_orders": dict(shape1=(6, 8, 5, 4), shape2=(6, 8, 7), mode_mapping={"shared": [(0, 0), (1, 1)]}, rank=4,
+                             n_iter_max=20, tol=-1.0),
+    "tensor2_all_shared": dict(shape1=(5, 10, 6, 6), shape2=(10, 6, 6), mode_mapping={"shared": [(1, 0), (2, 1), (3, 2)]},
+                               rank=2, n_iter_max=20, tol=-1.0),
+    "crossed_pairs": dict(shape1=(5, 6, 7), shape2=(7, 4, 5), mode_mapping={"shared": [(0, 2), (2, 0)]}, rank=3,
+                          n_iter_max=15, tol=-1.0),
+    "masked_first": dict(shape1=(4, 7, 5, 5), shape2=(4, 9, 5, 5), mode_mapping=[1], rank=3, n_iter_max=15, tol=-1.0,
+                         masked=(True, False)),
+    "masked_both": dict(shape1=(4, 6, 5, 5), shape2=(4, 5, 5), mode_mapping={"shared": [(0, 0), (2, 1), (3, 2)]}, rank=2,
+                        n_iter_max=15, tol=-1.0, masked=(True, True)),
+    "stop_abs": dict(shape1=(5, 12, 6, 6), shape2=(5, 9, 6, 6), mode_mapping=1, rank=3, n_iter_max=200, tol=2e-4),
+    "stop_rec_unbalanced": dict(shape1=(5, 12, 6, 6), shape2=(5, 30, 6, 6), mode_mapping=1, rank=3, n_iter_max=200, tol=2e-4,
+                                kwargs=dict(cvg_criterion="rec_error", balance_errors=False)),
+    "stop_balanced_uneven": dict(shape1=(5, 12, 6, 6), shape2=(5, 30, 6, 6), mode_mapping=1, rank=3, n_iter_max=200, tol=2e-4),
+}
+
+
+def coupled_inputs(name, seed=11):
+    """(x1, x2, mask1, mask2) of ``COUPLED_CASES[name]``: two noisy non-negative low-rank tensors whose shared modes have the
+    same true factors; masked tensors carry zeros where the uint8 mask is 0 (what ``PreBuiltTensor`` hands over)."""
+    case = COUPLED_CASES[name]
+    s1, s2 = case["shape1"], case["shape2"]
+    mm = case["mode_mapping"]
+    if not isinstance(mm, dict):
+        non_shared = [mm] if isinstance(mm, int) else list(mm)
+        mm = {"shared": [(i, i) for i in range(len(s1)) if i not in non_shared]}
+    rs = np.random.RandomState(seed)
+    true_rank = 3
+    f1 = [rs.gamma(1.0, 1.0, size=(s, true_rank)) for s in s1]
+    f2 = [rs.gamma(1.0, 1.0, size=(s, true_rank)) for s in s2]
+    for a, b in mm["shared"]:
+        f2[b] = f1[a]
+    out = []
+    for fs in (f1, f2):
+        letters = "abcdefgh"[: len(fs)]
+        x = np.einsum(",".join(l + "r" for l in letters) + "->" + letters, *fs)
+        x = x / x.mean() + 0.05 * rs.random_sample(x.shape)
+        out.append(np.ascontiguousarray(x, dtype=np.float32))
+    masks = [None, None]
+    for k, flag in enumerate(case.get("masked", (False, False))):
+        if flag:
+            m = np.ones(out[k].shape, dtype=np.uint8)
+            m[rs.rand(*out[k].shape) < 0.08] = 0
+            m[1, :, 2] = 0
+            masks[k] = m
+            out[k] = out[k] * m
+    return out[0], out[1], masks[0], masks[1]

@@ -10,80 +10,7 @@ import torch.multiprocessing as mp
 
 from cell2cell_b200.sharded import shard_bounds, sharded_non_negative_parafac
 from oracle import ncp_oracle as o
-
-
-class NumpyOps:
-    """fp64 numpy versions of the ops interface (test infrastructure)."""
-
-    def __init__(self, rank):
-        self.R = rank
-
-    def pack(self, f, device):
-        return torch.as_tensor(np.array(f, dtype=np.float64))
-
-    def unpack(self, a):
-        return a
-
-    def workspace(self, shape, device):
-        return None
-
-    def sumsq(self, X):
-        return float((X.numpy().astype(np.float64) ** 2).sum())
-
-    @staticmethod
-    def _kr(factors):
-        w = factors[0].numpy()
-        for f in factors[1:]:
-            w = (w[:, None, :] * f.numpy()[None, :, :]).reshape(-1, w.shape[1])
-        return w
-
-    def plane(self, X, factors, ws):
-        x = X.numpy().astype(np.float64)
-        x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
-        return torch.as_tensor(np.einsum("psv,sr,vr->pr", x3, factors[-2].numpy(), factors[-1].numpy()))
-
-    def fiber(self, X, factors, ws):
-        x = X.numpy().astype(np.float64)
-        x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
-        w = self._kr(factors[:-2])
-        return torch.as_tensor(np.einsum("psv,pr->svr", x3, w).reshape(-1, w.shape[1]))
-
-    def m_from(self, TU, shape, factors, mode):
-        nd = len(shape)
-        tu = TU.numpy()
-        R = tu.shape[1]
-        if mode < nd - 2:
-            lead = shape[:nd - 2]
-            t = tu.reshape(tuple(lead) + (R,))
-            letters = "abcdef"[: len(lead)]
-            ops = [letters + "r"]
-            args = [t]
-            for j, l in enumerate(letters):
-                if j != mode:
-                    ops.append(l + "r")
-                    args.append(factors[j].numpy())
-            return torch.as_tensor(np.einsum(",".join(ops) + "->" + letters[mode] + "r", *args))
-        u = tu.reshape(shape[-2], shape[-1], R)
-        if mode == nd - 2:
-            return torch.as_tensor(np.einsum("svr,vr->sr", u, factors[-1].numpy()))
-        return torch.as_tensor(np.einsum("svr,sr->vr", u, factors[-2].numpy()))
-
-    def gram_hadamard(self, factors, shape, skip):
-        R = factors[0].shape[1]
-        g = np.ones((R, R))
-        allg = np.ones((R, R))
-        for k, f in enumerate(factors):
-            gk = f.numpy().T @ f.numpy()
-            allg = allg * gk
-            if k != skip:
-                g = g * gk
-        return torch.as_tensor(g), torch.as_tensor(np.array([allg.sum()]))
-
-    def mu_update(self, A, M, G):
-        eps = np.finfo(np.float64).eps
-        a = A.numpy()
-        a *= np.clip(M.numpy(), eps, None) / np.clip(a @ G.numpy(), eps, None)
-        return A
+from tests.numpy_ops import NumpyOps
 
 
 def test_shard_bounds_cover():
