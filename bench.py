@@ -269,6 +269,29 @@ def run_ours(args, rank_id, local_rank, world):
                "passes": "plane_mma / fiber_mma (TMA + tcgen05.mma kind::tf32, 3-term split)"}
         del ws20, f20
 
+    # ---- Coupled Tensor Component Analysis: the atlas tensor + a second one sharing contexts / senders / receivers ------------
+    coupled = None
+    if args.workload == "atlas" and args.coupled:
+        shape2 = (shape[0], 1500, shape[2], shape[3])
+        X2 = torch.rand(shape2, generator=torch.Generator(device=dev).manual_seed(3), device=dev)
+        pairs = [(0, 0), (2, 2), (3, 3)]
+        mk = lambda sh, sd: [engine.pack_factor(np.random.RandomState(sd).random_sample((s, rank)).astype(np.float32), rank, dev)  # noqa: E731
+                             for s in sh]
+        engine.coupled_ncp_run(X, None, mk(shape, 1), X2, None, mk(shape2, 1), rank, pairs, n_iter_max=10, tol=-1.0, check_every=0)
+        torch.cuda.synchronize()
+        A1, A2 = mk(shape, 2), mk(shape2, 2)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        engine.coupled_ncp_run(X, None, A1, X2, None, A2, rank, pairs, n_iter_max=iters, tol=-1.0, check_every=0)
+        a1.record()
+        torch.cuda.synchronize()
+        csec = a0.elapsed_time(a1) * 1e-3
+        coupled = {"iterations_per_s_per_gpu": iters / csec, "rank": rank, "shape2": list(shape2), "shared_modes": pairs,
+                   "tensor_bytes": 4 * (n_x + X2.numel()), "reads_per_iteration": 2,
+                   "stream_gbs": 2 * 4 * (n_x + X2.numel()) * iters / csec / 1e9,
+                   "note": "c2c_coupled_ncp_run, whole call (workspaces, initial Grams, graph capture included)"}
+        del X2, A1, A2
+
     # ---- per-kernel roofline (rank 0 only reports) ---------------------------------------------------------------------
     f = fresh_factors(1)
     T = torch.empty((int(np.prod(shape[:-2])), engine.ldr_of(rank)), dtype=torch.float32, device=dev)
@@ -322,6 +345,8 @@ def run_ours(args, rank_id, local_rank, world):
         line["elbow_sweep"] = elbow
     if r20 is not None:
         line["rank20"] = r20
+    if coupled is not None:
+        line["coupled"] = coupled
     if not args.no_cpu:
         from threadpoolctl import threadpool_info
         threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
@@ -412,6 +437,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=2, help="CPU iterations per step of the reference arm / cpu_baseline")
     ap.add_argument("--ref-warm", action="store_true", help="also run the warm-up steps on the CPU reference arm")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-coupled", dest="coupled", action="store_false", help="skip the coupled-factorization line")
     ap.add_argument("--no-elbow", dest="elbow", action="store_false", help="skip the elbow-sweep wall time (second BASELINE metric)")
     ap.add_argument("--elbow-ranks", type=int, default=25)
     ap.add_argument("--elbow-runs", type=int, default=10)

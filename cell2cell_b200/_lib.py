@@ -47,6 +47,8 @@ SIGNATURES = {
     "c2c_gram_hadamard": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _i, _p, _p, _p, _sz, _p]),
     "c2c_mu_update": (_i, [_p, _p, _p, _i64, _i, _i, _c.c_float, _p, _sz, _p]),
     "c2c_mu_update_coupled": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _c.c_float, _p, _p]),
+    "c2c_coupled_ncp_run": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _p, _i, _i, _c.c_double, _i, _c.c_double,
+                                 _c.c_double, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),
     "c2c_hals_update": (_i, [_p, _p, _p, _i64, _i, _i, _i, _c.c_float, _p]),
     "c2c_recon_sums": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
     "c2c_cp_normalize": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _p, _p]),

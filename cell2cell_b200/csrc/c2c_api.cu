@@ -934,8 +934,9 @@ extern "C" int c2c_mu_update_coupled(float* A1_mode, float* A2_mode, const float
     cudaStream_t st = (cudaStream_t)stream;
     if (iprod) CK(cudaMemsetAsync(iprod, 0, 2 * sizeof(double), st), "iprod memset");
     const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
-    const size_t smem = (size_t)2 * C2C_UPD_ROWS * rank * sizeof(float);
-    mu_update_coupled_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(A1_mode, A2_mode, M1, M2, G1, G2, I, rank, ldr, eps, iprod);
+    const size_t smem = (size_t)3 * C2C_UPD_ROWS * rank * sizeof(float);
+    mu_update_coupled_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(A1_mode, A2_mode, M1, M2, G1, G2, I, rank, ldr, eps, iprod,
+                                                                   nullptr, nullptr);
     CKL("mu_update_coupled launch");
     return 0;
 }
@@ -1281,4 +1282,232 @@ extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shap
     if (total < 1 || total > 32) return fail(-26, "batched runs: the run ranks must add up to 1..32, got %lld", total);
     return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, (int)total, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
                         normX2, errors, state, check_every, ws, ws_bytes, stream, run_ranks, nruns);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// coupled factorization of two tensors sharing modes (cell2cell/tensor/coupled_factorization.py:123-482)
+// ---------------------------------------------------------------------------------------------------------------------
+struct CoupledSide {
+    Geo g; Ws w; const float* X; const uint8_t* mask; float* const* A;
+    bool T_ok, U_ok;           // is the cached plane / fiber contraction still the one of the current factors?
+    int seq[C2C_MAX_NDIM]; int nseq;   // this tensor's modes in the order they are updated within an iteration
+};
+
+struct CoupledCtx {
+    CoupledSide s[2];
+    int ldr, R, n_iter_max, cvg; double tol, w1, w2; float eps;
+    int kind[2 * C2C_MAX_NDIM], ma[2 * C2C_MAX_NDIM], mb[2 * C2C_MAX_NDIM], nsteps;   // kind 0: tensor 1 only, 1: tensor 2 only, 2: shared
+    const double* nx2[2]; double* iprod; double* errors; int* state; cudaStream_t st;
+};
+
+static int coupled_next_mode(const CoupledSide& sd, int mode)
+{
+    for (int i = 0; i < sd.nseq; ++i) if (sd.seq[i] == mode) return sd.seq[(i + 1) % sd.nseq];
+    return -1;
+}
+
+// M (in the side's workspace) of `mode` with the factors as they stand: a streaming pass only if the contraction this mode
+// is served from depends on a factor that changed since it was formed (always, with a mask: the imputed entries follow
+// every factor)
+static int coupled_mttkrp(CoupledSide& sd, int mode, int R, int ldr, const int* done, cudaStream_t st)
+{
+    const Geo& g = sd.g; int rc;
+    const float* const* A = (const float* const*)sd.A;
+    const bool lead = mode < g.ndim - 2;
+    const bool has_mask = sd.mask != nullptr;
+    if (has_mask || (lead ? !sd.T_ok : !sd.U_ok)) {
+        ContractArgs a = base_args(g, sd.X, sd.mask, A, ldr, R, done);
+        bool masked = has_mask;
+        if ((rc = maybe_impute(g, a, masked, sd.w, st)) != 0) return rc;
+        if (lead) { if ((rc = launch_plane(g, a, masked, sd.w.T, st)) != 0) return rc; sd.T_ok = true; }
+        else      { if ((rc = launch_fiber(g, a, masked, sd.w, st)) != 0) return rc; sd.U_ok = true; }
+    }
+    return launch_mode_mttkrp(g, A, mode, R, ldr, sd.w, sd.w.M, done, st);
+}
+
+static void coupled_touched(CoupledSide& sd, int mode)
+{
+    if (mode >= sd.g.ndim - 2) sd.T_ok = false; else sd.U_ok = false;
+}
+
+// Gram of the just-updated factor `mode` from the update kernel's partials, and the Gram-Hadamard product for the mode this
+// tensor updates next
+static int coupled_finalize(const CoupledCtx& c, int side, int mode, const double* gram_part, long long I, const int* done)
+{
+    const CoupledSide& sd = c.s[side];
+    FinalizeArgs f = fin_args(sd.g, c.R, c.ldr, sd.w, done);
+    f.k = mode; f.gram_part = gram_part; f.nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+    f.next = coupled_next_mode(sd, mode); f.G = sd.w.G;
+    gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, c.st>>>(f);
+    CKL("gram_finalize launch");
+    return 0;
+}
+
+static int coupled_enqueue_iteration(CoupledCtx& c)
+{
+    int rc;
+    const int* done = c.state + 1;
+    cudaStream_t st = c.st;
+    for (int k = 0; k < c.nsteps; ++k) {
+        if (c.kind[k] < 2) {
+            const int side = c.kind[k];
+            CoupledSide& sd = c.s[side];
+            const int mode = side == 0 ? c.ma[k] : c.mb[k];
+            const long long I = sd.g.shape[mode];
+            if ((rc = coupled_mttkrp(sd, mode, c.R, c.ldr, done, st)) != 0) return rc;
+            if ((rc = launch_mu(sd.A[mode], sd.w.M, sd.w.G, I, c.R, c.ldr, c.eps, sd.w, true, false, done, st)) != 0) return rc;
+            if ((rc = coupled_finalize(c, side, mode, sd.w.gram_part, I, done)) != 0) return rc;
+            coupled_touched(sd, mode);
+        } else {
+            const int a = c.ma[k], b = c.mb[k];
+            const long long I = c.s[0].g.shape[a];
+            if ((rc = coupled_mttkrp(c.s[0], a, c.R, c.ldr, done, st)) != 0) return rc;
+            if ((rc = coupled_mttkrp(c.s[1], b, c.R, c.ldr, done, st)) != 0) return rc;
+            const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+            const size_t smem = (size_t)3 * C2C_UPD_ROWS * c.R * sizeof(float);
+            mu_update_coupled_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(
+                c.s[0].A[a], c.s[1].A[b], c.s[0].w.M, c.s[1].w.M, c.s[0].w.G, c.s[1].w.G, I, c.R, c.ldr, c.eps,
+                k == c.nsteps - 1 ? c.iprod : nullptr, c.s[0].w.gram_part, done);
+            CKL("mu_update_coupled launch");
+            if ((rc = coupled_finalize(c, 0, a, c.s[0].w.gram_part, I, done)) != 0) return rc;
+            if ((rc = coupled_finalize(c, 1, b, c.s[0].w.gram_part, I, done)) != 0) return rc;
+            coupled_touched(c.s[0], a);
+            coupled_touched(c.s[1], b);
+        }
+    }
+    CoupledErrArgs e;
+    e.S1 = c.s[0].w.S; e.S2 = c.s[1].w.S; e.N1 = c.s[0].g.ndim; e.N2 = c.s[1].g.ndim; e.R = c.R; e.ldr = c.ldr;
+    e.iprod = c.iprod; e.nx2_1 = c.nx2[0]; e.nx2_2 = c.nx2[1]; e.errors = c.errors; e.state = c.state;
+    e.n_iter_max = c.n_iter_max; e.tol = c.tol; e.cvg = c.cvg; e.w1 = c.w1; e.w2 = c.w2;
+    coupled_error_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(e);
+    CKL("coupled_error launch");
+    return 0;
+}
+
+extern "C" int c2c_coupled_ncp_run(const float* X1, const uint8_t* mask1, int ndim1, const int64_t* shape1, float* const* A1,
+                                   const float* X2, const uint8_t* mask2, int ndim2, const int64_t* shape2, float* const* A2,
+                                   int ldr, int rank, const int* shared_pairs, int npairs, int n_iter_max, double tol,
+                                   int cvg_criterion, double w1, double w2, const double* normX2, double* errors, int* state,
+                                   int check_every, void* ws1, size_t ws1_bytes, void* ws2, size_t ws2_bytes, void* stream)
+{
+    static thread_local CoupledCtx c;          // large (two geometries): kept off the stack
+    int rc;
+    if (!shape1 || !shape2) return fail(-1, "shape is NULL");
+    if (!shared_pairs || npairs < 1) return fail(-40, "at least one mode must be shared between the tensors");
+    if (!errors || !state) return fail(-24, "errors / state is NULL");
+    if (cvg_criterion != C2C_CVG_ABS_REC_ERROR && cvg_criterion != C2C_CVG_REC_ERROR) return fail(-22, "unknown cvg_criterion %d", cvg_criterion);
+    if (n_iter_max < 0) return fail(-23, "n_iter_max < 0");
+    if (!(w1 > 0.0) || !(w2 > 0.0)) return fail(-41, "error weights must be positive");
+    const float* Xs[2] = {X1, X2}; const uint8_t* masks[2] = {mask1, mask2}; const int nds[2] = {ndim1, ndim2};
+    const int64_t* shapes[2] = {shape1, shape2}; float* const* As[2] = {A1, A2}; void* wss[2] = {ws1, ws2};
+    const size_t wsb[2] = {ws1_bytes, ws2_bytes};
+    for (int k = 0; k < 2; ++k) {
+        CoupledSide& sd = c.s[k];
+        if ((rc = make_geo(sd.g, nds[k], shapes[k], rank)) != 0) return rc;
+        if ((rc = check_common(Xs[k], (const float* const*)As[k], nds[k], ldr, rank)) != 0) return rc;
+        if (((uintptr_t)Xs[k] & 15) != 0) return fail(-25, "X must be 16-byte aligned");
+        if (sd.g.nchunk != 1) return fail(-42, "coupled factorization: rank must fit one chunk (<= 32)");
+        if ((rc = get_ws(sd.w, sd.g, rank, masks[k] != nullptr, wss[k], wsb[k])) != 0) return rc;
+        sd.X = Xs[k]; sd.mask = masks[k]; sd.A = As[k]; sd.T_ok = sd.U_ok = false; sd.nseq = 0;
+    }
+    if (ws1 == ws2) return fail(-43, "the two tensors need separate workspaces");
+    bool sh1[C2C_MAX_NDIM] = {false}, sh2[C2C_MAX_NDIM] = {false};
+    for (int p = 0; p < npairs; ++p) {
+        const int a = shared_pairs[2 * p], b = shared_pairs[2 * p + 1];
+        if (a < 0 || a >= ndim1 || b < 0 || b >= ndim2) return fail(-44, "shared pair (%d, %d) out of range", a, b);
+        if (sh1[a] || sh2[b]) return fail(-44, "a mode can be shared only once");
+        if (shape1[a] != shape2[b]) return fail(-45, "shared modes must have the same size: %lld vs %lld", (long long)shape1[a], (long long)shape2[b]);
+        sh1[a] = sh2[b] = true;
+    }
+    // update order (coupled_factorization.py:309-320): tensor-1-only modes, tensor-2-only modes, shared pairs in reverse
+    c.nsteps = 0;
+    for (int m = 0; m < ndim1; ++m) if (!sh1[m]) { c.kind[c.nsteps] = 0; c.ma[c.nsteps] = m; c.mb[c.nsteps] = -1; ++c.nsteps; c.s[0].seq[c.s[0].nseq++] = m; }
+    for (int m = 0; m < ndim2; ++m) if (!sh2[m]) { c.kind[c.nsteps] = 1; c.ma[c.nsteps] = -1; c.mb[c.nsteps] = m; ++c.nsteps; c.s[1].seq[c.s[1].nseq++] = m; }
+    for (int p = npairs - 1; p >= 0; --p) {
+        c.kind[c.nsteps] = 2; c.ma[c.nsteps] = shared_pairs[2 * p]; c.mb[c.nsteps] = shared_pairs[2 * p + 1]; ++c.nsteps;
+        c.s[0].seq[c.s[0].nseq++] = shared_pairs[2 * p]; c.s[1].seq[c.s[1].nseq++] = shared_pairs[2 * p + 1];
+    }
+    c.ldr = ldr; c.R = rank; c.n_iter_max = n_iter_max; c.tol = tol; c.cvg = cvg_criterion; c.w1 = w1; c.w2 = w2;
+    c.eps = 1.1920928955078125e-07f;
+    c.errors = errors; c.state = state; c.st = (cudaStream_t)stream;
+    cudaStream_t st = c.st;
+    c.iprod = c.s[0].w.scratch_d;
+    CK(cudaMemsetAsync(state, 0, 2 * sizeof(int), st), "memset state");
+    CK(cudaMemsetAsync(c.iprod, 0, 2 * sizeof(double), st), "memset iprod");
+    for (int k = 0; k < 2; ++k) {
+        CoupledSide& sd = c.s[k];
+        if (normX2) c.nx2[k] = normX2 + k;
+        else {
+            if ((rc = sumsq_into(sd.X, sd.g.P * sd.g.E, sd.w.normX2, sd.w.sums_part, st)) != 0) return rc;
+            c.nx2[k] = sd.w.normX2;
+        }
+        // Grams of the initial factors; G for the first mode this tensor updates
+        for (int m = 0; m < sd.g.ndim; ++m) {
+            if ((rc = launch_gram_partial(sd.A[m], nullptr, sd.g.shape[m], rank, ldr, sd.w, false, nullptr, st)) != 0) return rc;
+            FinalizeArgs f = fin_args(sd.g, rank, ldr, sd.w, nullptr);
+            f.k = m; f.gram_part = sd.w.gram_part; f.nblk = (int)((sd.g.shape[m] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
+            if (m == sd.g.ndim - 1) { f.next = sd.seq[0]; f.G = sd.w.G; }
+            gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);
+            CKL("gram_finalize launch");
+        }
+    }
+    if (n_iter_max == 0) return 0;
+
+    // Iteration 0 runs eagerly (cold contraction caches).  The cache state at the end of an iteration depends only on the
+    // update order, so from iteration 1 on every iteration starts and ends in the same state: one is captured and replayed.
+    if ((rc = coupled_enqueue_iteration(c)) != 0) return rc;
+    int it = 1;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    bool use_graph = n_iter_max >= 4;
+    if (use_graph) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+            (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone))
+            use_graph = false;
+    }
+    long long per_graph = 0;
+    if (use_graph) {
+        const bool before_state[4] = {c.s[0].T_ok, c.s[0].U_ok, c.s[1].T_ok, c.s[1].U_ok};
+        cudaStream_t cap = nullptr;
+        CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "create capture stream");
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cap); return cuda_fail(e, "begin capture"); }
+        const long long before = g_launches.load(std::memory_order_relaxed);
+        c.st = cap;
+        rc = coupled_enqueue_iteration(c);
+        c.st = st;
+        per_graph = g_launches.load(std::memory_order_relaxed) - before;
+        g_launches.fetch_sub(per_graph, std::memory_order_relaxed);
+        e = cudaStreamEndCapture(cap, &graph);
+        cudaStreamDestroy(cap);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "end capture");
+        if (before_state[0] != c.s[0].T_ok || before_state[1] != c.s[0].U_ok || before_state[2] != c.s[1].T_ok || before_state[3] != c.s[1].U_ok) {
+            cudaGraphDestroy(graph);
+            return fail(-46, "coupled iteration is not in a steady cache state");
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "graph instantiate"); }
+    }
+    int host_state[2] = {0, 0};
+    rc = 0;
+    for (; it < n_iter_max; ++it) {
+        if (use_graph) {
+            cudaError_t e = cudaGraphLaunch(exec, st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "graph launch"); break; }
+            g_launches.fetch_add(per_graph, std::memory_order_relaxed);
+        } else if ((rc = coupled_enqueue_iteration(c)) != 0) break;
+        if (check_every > 0 && (it + 1) % check_every == 0 && it + 1 < n_iter_max) {
+            cudaError_t e = cudaMemcpyAsync(host_state, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "poll state"); break; }
+            if (host_state[1]) break;
+        }
+    }
+    if (use_graph) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+    }
+    return rc;
 }

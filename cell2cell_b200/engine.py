@@ -13,7 +13,7 @@ from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, li
 
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
            "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
-           "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "build_ccc", "group_aggregate"]
+           "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "coupled_ncp_run", "build_ccc", "group_aggregate"]
 
 _vp = ctypes.c_void_p
 
@@ -293,6 +293,47 @@ def ncp_run_batched(X, factors, run_ranks, n_iter_max=100, tol=1e-6, cvg_criteri
         else:
             iters = st[2 + nruns:2 + 2 * nruns].astype(np.int64)
         return errors.cpu().numpy(), iters
+
+
+def coupled_ncp_run(X1, mask1, factors1, X2, mask2, factors2, rank, shared_pairs, n_iter_max=100, tol=1e-6,
+                    cvg_criterion="abs_rec_error", weights=(1.0, 1.0), check_every=10, norm_x2=None):
+    """Coupled multiplicative-update factorization of two tensors sharing the mode pairs ``shared_pairs``
+    (``c2c_coupled_ncp_run``), updating both sets of packed factors in place.  Returns ``(errors [n_iter, 2] float64,
+    n_iter, converged)``."""
+    _check_tensor(X1, mask1)
+    _check_tensor(X2, mask2)
+    if X1.device != X2.device:
+        raise C2CError("both tensors must live on the same device")
+    if rank < 1 or rank > 32:
+        raise C2CError("coupled factorization takes ranks 1..32, got %r" % (rank,))
+    if cvg_criterion not in CVG:
+        raise C2CError("cvg_criterion %r is not one of %s" % (cvg_criterion, sorted(CVG)))
+    for X, fs in ((X1, factors1), (X2, factors2)):
+        if len(fs) != X.dim():
+            raise C2CError("need one factor per mode")
+        for f, s in zip(fs, X.shape):
+            if f.shape != (s, ldr_of(rank)) or f.dtype != torch.float32 or not f.is_contiguous() or f.device != X.device:
+                raise C2CError("factors must be packed fp32 [I_n, ldr] tensors on the tensor's device (pack_factor)")
+    pairs = [int(v) for p in shared_pairs for v in p]
+    with torch.cuda.device(X1.device):
+        ws1 = Workspace(X1.shape, rank, mask1 is not None, X1.device)
+        ws2 = Workspace(X2.shape, rank, mask2 is not None, X2.device)
+        n_it = max(int(n_iter_max), 1)
+        errors = torch.zeros((n_it, 2), dtype=torch.float64, device=X1.device)
+        state = torch.zeros(2, dtype=torch.int32, device=X1.device)
+        nx2 = None
+        if norm_x2 is not None:
+            nx2 = torch.tensor([float(norm_x2[0]), float(norm_x2[1])], dtype=torch.float64, device=X1.device)
+        arr = (ctypes.c_int * len(pairs))(*pairs)
+        check(lib().c2c_coupled_ncp_run(_ptr(X1), _ptr(mask1), X1.dim(), _shape_arr(X1.shape), _ptr_arr(factors1),
+                                        _ptr(X2), _ptr(mask2), X2.dim(), _shape_arr(X2.shape), _ptr_arr(factors2),
+                                        ldr_of(rank), rank, arr, len(pairs) // 2, int(n_iter_max), float(tol),
+                                        CVG[cvg_criterion], float(weights[0]), float(weights[1]), _ptr(nx2), _ptr(errors),
+                                        _ptr(state), int(check_every), ws1.ptr, ws1.nbytes, ws2.ptr, ws2.nbytes, _stream()),
+              "c2c_coupled_ncp_run")
+        st = state.cpu().numpy()
+        n_iter = int(st[0])
+        return errors[:n_iter].cpu().numpy(), n_iter, bool(st[1])
 
 
 def build_ccc(expr, expr_off, expr_ld, cell_col, a_first, a_count, b_first, b_count, sub_rows, C, L, K, score, agg,

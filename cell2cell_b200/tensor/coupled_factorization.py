@@ -19,12 +19,18 @@ How it maps on the B200 kernels (``libc2c_b200.so`` through ``engine``; there is
 * shared modes: ``c2c_mu_update_coupled`` -- one kernel forms both denominators, averages, updates and writes the new
   factor into both tensors' copies; on the last update of the iteration it also accumulates the two inner products
   ``<X_k, cp_k>`` of tensorly's ``error_calc`` (the reference spends one more MTTKRP per tensor on them, :473-485).
-* the whole iteration is captured once into a CUDA graph and replayed; the error history stays on the device and is read
-  back after every iteration only when a real stop rule is active (``tol > 0``).
+* the error scalars and the combined stop rule are evaluated on the device (``coupled_error_kernel``); iteration 0 runs
+  eagerly (cold caches), then ONE iteration is captured into a CUDA graph and replayed: ~26 launches per iteration for two
+  4-way tensors sharing three modes, no host work besides the replay.
 
-The orchestration is written against the small ``ops`` interface of ``cell2cell_b200.sharded.DeviceOps`` so that the update
-order / cache logic is testable on CPU with numpy stand-ins (tests/test_coupled.py).
+Two drivers produce that sequence: ``c2c_coupled_ncp_run`` inside the library (the product path, rank <= 32) and
+``_coupled_mu`` below -- the same order / cache logic written against the small ``ops`` interface of
+``cell2cell_b200.sharded.DeviceOps`` over the single-step entry points; it serves ranks 33..128 and lets the CPU suite
+check the orchestration with numpy stand-ins for the kernels (tests/test_coupled_oracle.py).
+``C2C_B200_COUPLED_HOST_DRIVER=1`` forces it on the device as well (the GPU tests run both).
 """
+import os
+
 import numpy as np
 import torch
 from tqdm.auto import tqdm
@@ -274,24 +280,47 @@ def coupled_non_negative_parafac(tensor1, tensor2, rank, mode_mapping, mask1=Non
         raise ValueError("coupled factorization takes init='svd' or init='random'")
     init1 = initialize_factors(X1, rank, init=init, svd=svd, random_state=random_state)        # :272-280: same random_state
     init2 = initialize_factors(X2, rank, init=init, svd=svd, random_state=random_state)
-    if ops is None:
-        from ..sharded import DeviceOps
-        ops = DeviceOps(rank)
-    s1, s2, errors1, errors2 = _coupled_mu(X1, X2, M1, M2, [f.astype(np.float32) for f in init1],
-                                           [f.astype(np.float32) for f in init2], rank, shared_pairs, int(n_iter_max),
-                                           float(tol) if tol else -1.0, cvg_criterion, w1, w2, ops)
+    init1 = [f.astype(np.float32) for f in init1]
+    init2 = [f.astype(np.float32) for f in init2]
+    tol_run = float(tol) if tol else -1.0
+    passes = (None, None)
+    if ops is None and rank <= 32 and os.environ.get("C2C_B200_COUPLED_HOST_DRIVER") != "1":
+        # the whole run inside the library (c2c_coupled_ncp_run): update chain, contraction caches, error scalars and the
+        # combined stop rule on the device, one captured iteration replayed
+        A1 = [engine.pack_factor(f, rank, X1.device) for f in init1]
+        A2 = [engine.pack_factor(f, rank, X1.device) for f in init2]
+        for a, b in shared_pairs:                                   # :294-295 shared factors start as tensor 1's
+            A2[b].copy_(A1[a])
+        cached = [getattr(X, "_c2c_norm_x2", None) for X in (X1, X2)]
+        errs, n_iter, _ = engine.coupled_ncp_run(X1, M1, A1, X2, M2, A2, rank, shared_pairs, n_iter_max=int(n_iter_max),
+                                                 tol=tol_run, cvg_criterion=cvg_criterion, weights=(w1, w2), check_every=10,
+                                                 norm_x2=cached if all(c is not None for c in cached) else None)
+        errors1 = [np.float64(e) for e in errs[:, 0]]
+        errors2 = [np.float64(e) for e in errs[:, 1]]
+        recon = lambda X, A: engine.recon_sums(X, None, A, rank)      # noqa: E731
+    else:
+        # host-driven iteration over the single-step entry points (any rank up to 128; also what the CPU tests drive with
+        # numpy stand-ins for the kernels)
+        if ops is None:
+            from ..sharded import DeviceOps
+            ops = DeviceOps(rank)
+        s1, s2, errors1, errors2 = _coupled_mu(X1, X2, M1, M2, init1, init2, rank, shared_pairs, int(n_iter_max), tol_run,
+                                               cvg_criterion, w1, w2, ops)
+        A1, A2 = s1.A, s2.A
+        passes = (s1.passes, s2.passes)
+        recon = lambda X, A: ops.recon_sums(X, None, A, None)         # noqa: E731
     cps = []
-    for side, errors in ((s1, errors1), (s2, errors2)):
+    for X, M, A, errors, npass in ((X1, M1, A1, errors1, passes[0]), (X2, M2, A2, errors2, passes[1])):
         sums = None
-        if side.mask is None and len(errors):
+        if M is None and len(errors):
             # as in the single-tensor path the kept (last) error is the directly accumulated ||X - rec|| / ||X|| (fp64 sums
             # of one fused pass): the Gram form cancels in fp32 once the error is small
-            sums = ops.recon_sums(side.X, None, side.A, side.ws)
+            sums = recon(X, A)
             errors[-1] = np.float64(np.sqrt(sums[1]) / np.sqrt(sums[3]))
-        cp = CPTensor(np.ones(rank, dtype=np.float32), [ops.unpack(a).cpu().numpy() for a in side.A], device=X1.device)
+        cp = CPTensor(np.ones(rank, dtype=np.float32), [engine.unpack_factor(a, rank).cpu().numpy() for a in A], device=X1.device)
         if sums is not None:
             cp.recon_sums_ = sums
-        cp.passes_ = side.passes
+        cp.passes_ = npass
         cps.append(cp)
     if verbose:
         for it, (e1, e2) in enumerate(zip(errors1, errors2)):

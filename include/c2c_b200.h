@@ -137,6 +137,22 @@ int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int 
 int c2c_mu_update_coupled(float* A1_mode, float* A2_mode, const float* M1, const float* M2, const float* G1, const float* G2,
                           int64_t I, int rank, int ldr, float eps, double* iprod, void* stream);
 
+/* ---- Coupled factorization of two tensors sharing modes (cell2cell/tensor/coupled_factorization.py:123-482) --------
+ * shared_pairs: host int[2 * npairs] = (tensor-1 mode, tensor-2 mode) per shared pair, in the order of
+ * mode_mapping['shared'].  Per iteration: tensor-1-only modes, tensor-2-only modes (each a plain multiplicative update),
+ * then the shared pairs in reverse order with averaged numerators / denominators (K4c); A1 / A2 hold separate copies of
+ * a shared factor and both receive the update.  An unmasked tensor is read twice per iteration whatever the order (its
+ * plane / fiber contractions are reused until a factor they depend on changes); a masked one once per mode.
+ * errors: device double[2 * n_iter_max], errors[2 it + k] = Gram-form error of tensor k after iteration it
+ * (tensorly error_calc, :473-485); the stop rule (:487-509) runs on (w1 e1 + w2 e2) / (w1 + w2).
+ * state: device int[2] = {iterations done, converged}.  normX2: device double[2] (||X1||^2, ||X2||^2) or NULL.
+ * ws1 / ws2: one workspace per tensor (c2c_ncp_workspace_bytes(shape_k, rank, mask_k != NULL)).  rank <= 32. */
+int c2c_coupled_ncp_run(const float* X1, const uint8_t* mask1, int ndim1, const int64_t* shape1 /*host*/, float* const* A1 /*host array*/,
+                        const float* X2, const uint8_t* mask2, int ndim2, const int64_t* shape2 /*host*/, float* const* A2 /*host array*/,
+                        int ldr, int rank, const int* shared_pairs /*host*/, int npairs, int n_iter_max, double tol,
+                        int cvg_criterion, double w1, double w2, const double* normX2, double* errors, int* state,
+                        int check_every, void* ws1, size_t ws1_bytes, void* ws2, size_t ws2_bytes, void* stream);
+
 /* ---- K5: HALS column sweeps (tensorly hals_nnls reached from cell2cell/tensor/factorization.py:106-115) ------------
  * sweeps k = 0..R-1: A[:,k] <- max(A[:,k] + (M[:,k] - A G[:,k]) / G[k,k], 0); stops when the squared change of a sweep
  * falls below tol * (first sweep's) or after min(max_sweeps, 2 + 0.5 * (1 + 2 I R / (R R + R))) sweeps. */

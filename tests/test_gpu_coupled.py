@@ -55,8 +55,19 @@ def test_mu_update_coupled_kernel_matches_numpy():
         np.testing.assert_allclose(ip.cpu().numpy(), [(m1 * want).sum(), (m2 * want).sum()], rtol=1e-5)
 
 
+@pytest.fixture(params=["library", "host"])
+def driver(request, monkeypatch):
+    """``library``: the run inside libc2c_b200.so (c2c_coupled_ncp_run, the product path); ``host``: the same sequence driven
+    from Python over the single-step entry points (ranks > 32 take it)."""
+    if request.param == "host":
+        monkeypatch.setenv("C2C_B200_COUPLED_HOST_DRIVER", "1")
+    else:
+        monkeypatch.delenv("C2C_B200_COUPLED_HOST_DRIVER", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("name", sorted(COUPLED_CASES))
-def test_coupled_matches_reference_golden(name):
+def test_coupled_matches_reference_golden(name, driver):
     from cell2cell_b200.tensor.coupled_factorization import coupled_non_negative_parafac
     case = COUPLED_CASES[name]
     x1, x2, m1, m2 = coupled_inputs(name)
@@ -103,7 +114,7 @@ def _lowrank_pair(shape1, shape2, shared, seed, true_rank=5):
     ((150, 128, 16, 8), (150, 128, 20), [(0, 0), (1, 1)], 16, 15),              # tensor-pipe passes on tensor 1 (P >= 128 * 148)
     ((12, 300, 6, 6), (300, 6, 6), [(1, 0), (2, 1), (3, 2)], 12, 25),           # BALF family + a context-free tensor
 ])
-def test_coupled_matches_oracle_on_streaming_shapes(shape1, shape2, shared, rank, n_iter):
+def test_coupled_matches_oracle_on_streaming_shapes(shape1, shape2, shared, rank, n_iter, driver):
     from cell2cell_b200.tensor.coupled_factorization import coupled_non_negative_parafac
     x1, x2 = _lowrank_pair(shape1, shape2, shared, seed=21)
     mm = {"shared": shared}
@@ -119,7 +130,42 @@ def test_coupled_matches_oracle_on_streaming_shapes(shape1, shape2, shared, rank
             assert rel_err(f, g) < FACTOR_RTOL, rel_err(f, g)
     for a, b in shared:
         assert np.array_equal(c1.factors[a], c2.factors[b])
-    assert c1.passes_ <= 2 * 2 + 1                               # eager first iteration + the captured one: two reads each
+    if driver == "host":
+        assert c1.passes_ <= 2 * 2 + 1                           # eager first iteration + the captured one: two reads each
+
+
+def test_coupled_rank_above_32_takes_the_host_driver():
+    from cell2cell_b200.tensor.coupled_factorization import coupled_non_negative_parafac
+    shared = [(0, 0), (2, 2), (3, 3)]
+    x1, x2 = _lowrank_pair((4, 12, 6, 6), (4, 9, 6, 6), shared, seed=2)
+    r1, r2, (re1, re2) = co.coupled_non_negative_parafac(x1, x2, 40, 1, n_iter_max=10, init="random", tol=-1.0, random_state=1)
+    c1, c2, (e1, e2) = coupled_non_negative_parafac(x1, x2, 40, 1, n_iter_max=10, init="random", tol=-1.0, random_state=1,
+                                                    return_errors=True)
+    assert c1.passes_ is not None
+    for got, ref in ((c1, r1), (c2, r2)):
+        for f, g in zip(got.factors, ref[1]):
+            assert rel_err(f, g) < FACTOR_RTOL, rel_err(f, g)
+    assert abs(e1[-1] - re1[-1]) <= ERROR_RTOL * re1[-1] and abs(e2[-1] - re2[-1]) <= ERROR_RTOL * re2[-1]
+
+
+def test_coupled_library_launch_count():
+    """Two 4-way tensors sharing three modes: 22 small kernels per replayed iteration (8 MTTKRP tails, 5 updates, 8 Gram
+    finalizes, 1 error kernel) + the 4 streaming passes (1-3 launches each, depending on the shape's tail / reduce kernels)."""
+    from cell2cell_b200 import engine
+    shared = [(0, 0), (2, 2), (3, 3)]
+    x1, x2 = _lowrank_pair((6, 40, 8, 8), (6, 30, 8, 8), shared, seed=2)
+    dev = torch.device("cuda")
+    X1, X2 = torch.as_tensor(x1).to(dev), torch.as_tensor(x2).to(dev)
+    counts = []
+    for n in (10, 20):
+        A1 = [engine.pack_factor(np.random.RandomState(0).rand(s, 4), 4, dev) for s in x1.shape]
+        A2 = [engine.pack_factor(np.random.RandomState(0).rand(s, 4), 4, dev) for s in x2.shape]
+        l0 = engine.launch_count()
+        errs, n_iter, conv = engine.coupled_ncp_run(X1, None, A1, X2, None, A2, 4, shared, n_iter_max=n, tol=-1.0)
+        counts.append(engine.launch_count() - l0)
+        assert n_iter == n and not conv and errs.shape == (n, 2) and (np.diff(errs.sum(axis=1)) < 1e-6).all()
+    per_it = (counts[1] - counts[0]) / 10.0
+    assert per_it == int(per_it) and 26 <= per_it <= 34, per_it
 
 
 def _named(x, prefix, shared_names=None, mask=None):
