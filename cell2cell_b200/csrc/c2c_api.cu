@@ -1298,7 +1298,19 @@ struct CoupledCtx {
     int ldr, R, n_iter_max, cvg; double tol, w1, w2; float eps;
     int kind[2 * C2C_MAX_NDIM], ma[2 * C2C_MAX_NDIM], mb[2 * C2C_MAX_NDIM], nsteps;   // kind 0: tensor 1 only, 1: tensor 2 only, 2: shared
     const double* nx2[2]; double* iprod; double* errors; int* state; cudaStream_t st;
+    // tensor 2's chain (passes, MTTKRP tails, Gram finalizes) runs on a stream of its own between the shared updates, so the
+    // small kernels of one tensor hide behind the streaming pass of the other; ev12 / ev21 order the two streams
+    cudaStream_t st2; cudaEvent_t ev12, ev21;
 };
+
+// `to` waits for everything enqueued on `from` so far
+static int coupled_order(cudaStream_t from, cudaStream_t to, cudaEvent_t ev)
+{
+    if (from == to) return 0;
+    CK(cudaEventRecord(ev, from), "event record");
+    CK(cudaStreamWaitEvent(to, ev, 0), "stream wait event");
+    return 0;
+}
 
 static int coupled_next_mode(const CoupledSide& sd, int mode)
 {
@@ -1332,13 +1344,14 @@ static void coupled_touched(CoupledSide& sd, int mode)
 
 // Gram of the just-updated factor `mode` from the update kernel's partials, and the Gram-Hadamard product for the mode this
 // tensor updates next
-static int coupled_finalize(const CoupledCtx& c, int side, int mode, const double* gram_part, long long I, const int* done)
+static int coupled_finalize(const CoupledCtx& c, int side, int mode, const double* gram_part, long long I, const int* done,
+                            cudaStream_t st)
 {
     const CoupledSide& sd = c.s[side];
     FinalizeArgs f = fin_args(sd.g, c.R, c.ldr, sd.w, done);
     f.k = mode; f.gram_part = gram_part; f.nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
     f.next = coupled_next_mode(sd, mode); f.G = sd.w.G;
-    gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, c.st>>>(f);
+    gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);
     CKL("gram_finalize launch");
     return 0;
 }
@@ -1347,34 +1360,39 @@ static int coupled_enqueue_iteration(CoupledCtx& c)
 {
     int rc;
     const int* done = c.state + 1;
-    cudaStream_t st = c.st;
+    cudaStream_t st = c.st, st2 = c.st2;
+    if ((rc = coupled_order(st, st2, c.ev12)) != 0) return rc;          // fork: tensor 2's stream starts after the previous iteration
     for (int k = 0; k < c.nsteps; ++k) {
         if (c.kind[k] < 2) {
             const int side = c.kind[k];
             CoupledSide& sd = c.s[side];
+            cudaStream_t ss = side == 0 ? st : st2;
             const int mode = side == 0 ? c.ma[k] : c.mb[k];
             const long long I = sd.g.shape[mode];
-            if ((rc = coupled_mttkrp(sd, mode, c.R, c.ldr, done, st)) != 0) return rc;
-            if ((rc = launch_mu(sd.A[mode], sd.w.M, sd.w.G, I, c.R, c.ldr, c.eps, sd.w, true, false, done, st)) != 0) return rc;
-            if ((rc = coupled_finalize(c, side, mode, sd.w.gram_part, I, done)) != 0) return rc;
+            if ((rc = coupled_mttkrp(sd, mode, c.R, c.ldr, done, ss)) != 0) return rc;
+            if ((rc = launch_mu(sd.A[mode], sd.w.M, sd.w.G, I, c.R, c.ldr, c.eps, sd.w, true, false, done, ss)) != 0) return rc;
+            if ((rc = coupled_finalize(c, side, mode, sd.w.gram_part, I, done, ss)) != 0) return rc;
             coupled_touched(sd, mode);
         } else {
             const int a = c.ma[k], b = c.mb[k];
             const long long I = c.s[0].g.shape[a];
             if ((rc = coupled_mttkrp(c.s[0], a, c.R, c.ldr, done, st)) != 0) return rc;
-            if ((rc = coupled_mttkrp(c.s[1], b, c.R, c.ldr, done, st)) != 0) return rc;
+            if ((rc = coupled_mttkrp(c.s[1], b, c.R, c.ldr, done, st2)) != 0) return rc;
+            if ((rc = coupled_order(st2, st, c.ev21)) != 0) return rc;  // M2 and G2 are ready
             const int nblk = (int)((I + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
             const size_t smem = (size_t)3 * C2C_UPD_ROWS * c.R * sizeof(float);
             mu_update_coupled_kernel<<<nblk, C2C_SMALL_THREADS, smem, st>>>(
                 c.s[0].A[a], c.s[1].A[b], c.s[0].w.M, c.s[1].w.M, c.s[0].w.G, c.s[1].w.G, I, c.R, c.ldr, c.eps,
                 k == c.nsteps - 1 ? c.iprod : nullptr, c.s[0].w.gram_part, done);
             CKL("mu_update_coupled launch");
-            if ((rc = coupled_finalize(c, 0, a, c.s[0].w.gram_part, I, done)) != 0) return rc;
-            if ((rc = coupled_finalize(c, 1, b, c.s[0].w.gram_part, I, done)) != 0) return rc;
+            if ((rc = coupled_order(st, st2, c.ev12)) != 0) return rc;  // the new factor and its Gram partials are ready
+            if ((rc = coupled_finalize(c, 0, a, c.s[0].w.gram_part, I, done, st)) != 0) return rc;
+            if ((rc = coupled_finalize(c, 1, b, c.s[0].w.gram_part, I, done, st2)) != 0) return rc;
             coupled_touched(c.s[0], a);
             coupled_touched(c.s[1], b);
         }
     }
+    if ((rc = coupled_order(st2, st, c.ev21)) != 0) return rc;          // join
     CoupledErrArgs e;
     e.S1 = c.s[0].w.S; e.S2 = c.s[1].w.S; e.N1 = c.s[0].g.ndim; e.N2 = c.s[1].g.ndim; e.R = c.R; e.ldr = c.ldr;
     e.iprod = c.iprod; e.nx2_1 = c.nx2[0]; e.nx2_2 = c.nx2[1]; e.errors = c.errors; e.state = c.state;
@@ -1382,6 +1400,73 @@ static int coupled_enqueue_iteration(CoupledCtx& c)
     coupled_error_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(e);
     CKL("coupled_error launch");
     return 0;
+}
+
+// Iteration 0 runs eagerly (cold contraction caches).  The cache state at the end of an iteration depends only on the update
+// order, so from iteration 1 on every iteration starts and ends in the same state: one is captured and replayed.
+static int coupled_run_loop(CoupledCtx& c, int n_iter_max, int check_every)
+{
+    int rc;
+    cudaStream_t st = c.st, st2 = c.st2;
+    int* state = c.state;
+    if ((rc = coupled_enqueue_iteration(c)) != 0) return rc;
+    int it = 1;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    bool use_graph = n_iter_max >= 4;
+    if (use_graph) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
+            (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone))
+            use_graph = false;
+    }
+    long long per_graph = 0;
+    if (use_graph) {
+        const bool before_state[4] = {c.s[0].T_ok, c.s[0].U_ok, c.s[1].T_ok, c.s[1].U_ok};
+        cudaStream_t cap = nullptr;
+        CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "create capture stream");
+        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { cudaStreamDestroy(cap); return cuda_fail(e, "begin capture"); }
+        const long long before = g_launches.load(std::memory_order_relaxed);
+        cudaStream_t cap2 = cap;
+        if (st2 != st) CK(cudaStreamCreateWithFlags(&cap2, cudaStreamNonBlocking), "create capture stream");
+        c.st = cap; c.st2 = cap2;                 // cap2 joins the capture through the first event wait and rejoins before the end
+        rc = coupled_enqueue_iteration(c);
+        c.st = st; c.st2 = st2;
+        per_graph = g_launches.load(std::memory_order_relaxed) - before;
+        g_launches.fetch_sub(per_graph, std::memory_order_relaxed);
+        e = cudaStreamEndCapture(cap, &graph);
+        cudaStreamDestroy(cap);
+        if (cap2 != cap) cudaStreamDestroy(cap2);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return cuda_fail(e, "end capture");
+        if (before_state[0] != c.s[0].T_ok || before_state[1] != c.s[0].U_ok || before_state[2] != c.s[1].T_ok || before_state[3] != c.s[1].U_ok) {
+            cudaGraphDestroy(graph);
+            return fail(-46, "coupled iteration is not in a steady cache state");
+        }
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "graph instantiate"); }
+    }
+    int host_state[2] = {0, 0};
+    rc = 0;
+    for (; it < n_iter_max; ++it) {
+        if (use_graph) {
+            cudaError_t e = cudaGraphLaunch(exec, st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "graph launch"); break; }
+            g_launches.fetch_add(per_graph, std::memory_order_relaxed);
+        } else if ((rc = coupled_enqueue_iteration(c)) != 0) break;
+        if (check_every > 0 && (it + 1) % check_every == 0 && it + 1 < n_iter_max) {
+            cudaError_t e = cudaMemcpyAsync(host_state, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "poll state"); break; }
+            if (host_state[1]) break;
+        }
+    }
+    if (use_graph) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+    }
+    return rc;
 }
 
 extern "C" int c2c_coupled_ncp_run(const float* X1, const uint8_t* mask1, int ndim1, const int64_t* shape1, float* const* A1,
@@ -1453,61 +1538,22 @@ extern "C" int c2c_coupled_ncp_run(const float* X1, const uint8_t* mask1, int nd
     }
     if (n_iter_max == 0) return 0;
 
-    // Iteration 0 runs eagerly (cold contraction caches).  The cache state at the end of an iteration depends only on the
-    // update order, so from iteration 1 on every iteration starts and ends in the same state: one is captured and replayed.
-    if ((rc = coupled_enqueue_iteration(c)) != 0) return rc;
-    int it = 1;
-    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
-    bool use_graph = n_iter_max >= 4;
-    if (use_graph) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread &&
-            (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone))
-            use_graph = false;
+    // tensor 2's chain gets a stream of its own (C2C_B200_COUPLED_ONE_STREAM=1: everything on the caller's stream)
+    static int one_stream = -1;
+    if (one_stream < 0) one_stream = env_int("C2C_B200_COUPLED_ONE_STREAM", 0) ? 1 : 0;
+    c.st2 = st; c.ev12 = nullptr; c.ev21 = nullptr;
+    cudaStream_t own2 = nullptr;
+    if (!one_stream) {
+        CK(cudaStreamCreateWithFlags(&own2, cudaStreamNonBlocking), "create second stream");
+        cudaError_t e = cudaEventCreateWithFlags(&c.ev12, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c.ev21, cudaEventDisableTiming);
+        if (e != cudaSuccess) { cudaStreamDestroy(own2); if (c.ev12) cudaEventDestroy(c.ev12); return cuda_fail(e, "create events"); }
+        c.st2 = own2;
     }
-    long long per_graph = 0;
-    if (use_graph) {
-        const bool before_state[4] = {c.s[0].T_ok, c.s[0].U_ok, c.s[1].T_ok, c.s[1].U_ok};
-        cudaStream_t cap = nullptr;
-        CK(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking), "create capture stream");
-        cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-        if (e != cudaSuccess) { cudaStreamDestroy(cap); return cuda_fail(e, "begin capture"); }
-        const long long before = g_launches.load(std::memory_order_relaxed);
-        c.st = cap;
-        rc = coupled_enqueue_iteration(c);
-        c.st = st;
-        per_graph = g_launches.load(std::memory_order_relaxed) - before;
-        g_launches.fetch_sub(per_graph, std::memory_order_relaxed);
-        e = cudaStreamEndCapture(cap, &graph);
-        cudaStreamDestroy(cap);
-        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (e != cudaSuccess) return cuda_fail(e, "end capture");
-        if (before_state[0] != c.s[0].T_ok || before_state[1] != c.s[0].U_ok || before_state[2] != c.s[1].T_ok || before_state[3] != c.s[1].U_ok) {
-            cudaGraphDestroy(graph);
-            return fail(-46, "coupled iteration is not in a steady cache state");
-        }
-        e = cudaGraphInstantiate(&exec, graph, 0);
-        if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "graph instantiate"); }
-    }
-    int host_state[2] = {0, 0};
-    rc = 0;
-    for (; it < n_iter_max; ++it) {
-        if (use_graph) {
-            cudaError_t e = cudaGraphLaunch(exec, st);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "graph launch"); break; }
-            g_launches.fetch_add(per_graph, std::memory_order_relaxed);
-        } else if ((rc = coupled_enqueue_iteration(c)) != 0) break;
-        if (check_every > 0 && (it + 1) % check_every == 0 && it + 1 < n_iter_max) {
-            cudaError_t e = cudaMemcpyAsync(host_state, state, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { rc = cuda_fail(e, "poll state"); break; }
-            if (host_state[1]) break;
-        }
-    }
-    if (use_graph) {
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
-        if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+    rc = coupled_run_loop(c, n_iter_max, check_every);
+    if (own2) {
+        cudaStreamSynchronize(own2);
+        cudaStreamDestroy(own2); cudaEventDestroy(c.ev12); cudaEventDestroy(c.ev21);
     }
     return rc;
 }
