@@ -127,13 +127,20 @@ class BaseTensor:
     # ---- factorization ----------------------------------------------------------------------------------------------
     def compute_tensor_factorization(self, rank, tf_type="non_negative_cp", init="svd", svd="truncated_svd",
                                      random_state=None, runs=1, normalize_loadings=True, var_ordered_factors=True,
-                                     n_iter_max=100, tol=10e-7, verbose=False, **kwargs):
+                                     n_iter_max=100, tol=10e-7, verbose=False, batch_runs=True, **kwargs):
         """Best-of-``runs`` factorization; sets ``tl_object``, ``norm_tl_object``, ``factors``, ``rank``,
-        ``explained_variance_`` and ``explained_variance_ratio_`` (tensor.py:216-362)."""
+        ``explained_variance_`` and ``explained_variance_ratio_`` (tensor.py:216-362).
+
+        The runs are independent: with ``batch_runs`` as many as fit 28 factor columns are factorized side by side in one
+        device run (one read of the tensor per pass serves all of them; MU, unmasked, host-seeded random init -- what
+        ``run_tensor_cell2cell_pipeline(tf_optimization='robust')`` asks for with its 100 runs), and the units are spread
+        over the GPUs of the job when ``torch.distributed`` is initialised.  Same result as run by run."""
         tensor_dim = len(self.tensor.shape)
         kwargs = dict(kwargs or {})
         kwargs["return_errors"] = True
         from ..parallel import run_units
+        from .factorization import _factorize_batch, _pack_runs
+        from .._lib import C2CError
 
         def one(run):
             seed = None if random_state is None else random_state + run
@@ -146,7 +153,23 @@ class BaseTensor:
                 err = float(_compute_norm_error(self.tensor, local_tf, self.mask))
             return (err, local_tf)
 
-        results = run_units(list(range(runs)), one, gather="object") if runs > 1 else [one(0)]
+        batchable = (batch_runs and runs > 1 and tf_type == "non_negative_cp" and self.mask is None and init == "random" and
+                     random_state is not None and set(kwargs) <= {"return_errors", "cvg_criterion"} and 2 * int(rank) <= 28 and
+                     tensor_dim >= 3)
+
+        def one_bin(unit):
+            try:
+                res = _factorize_batch(self.tensor, [(rank, random_state + run) for _, run in unit], n_iter_max, tol,
+                                       cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
+                return [(run, float(errs[-1]), tf_) for (_, run), (tf_, errs) in zip(unit, res)]
+            except C2CError:                      # shape outside the fused update kernels: run by run on the device instead
+                return [(run,) + one(run) for _, run in unit]
+
+        if batchable:
+            parts = run_units(_pack_runs([(int(rank), run) for run in range(runs)]), one_bin, gather="object")
+            results = [(err, tf_) for _, err, tf_ in sorted((r for part in parts for r in part), key=lambda r: r[0])]
+        else:
+            results = run_units(list(range(runs)), one, gather="object") if runs > 1 else [one(0)]
         best_err, tf = np.inf, None
         for err, local_tf in results:
             if best_err > err:

@@ -587,6 +587,28 @@ def test_batched_elbow_equals_unbatched_elbow():
     np.testing.assert_allclose(a, b, rtol=2e-5)
 
 
+def test_best_of_runs_batched_equals_run_by_run(capsys):
+    """``compute_tensor_factorization(runs=N)`` (the 'robust' pipeline mode, tensor.py:294-323): the runs packed side by side
+    pick the same best model as the runs one after the other."""
+    from cell2cell_b200.tensor import PreBuiltTensor
+    x = lowrank((8, 120, 6, 6), 4, seed=6).astype(np.float64)
+    names = [["n%d_%d" % (k, i) for i in range(s)] for k, s in enumerate(x.shape)]
+    a, b = PreBuiltTensor(x, order_names=names), PreBuiltTensor(x, order_names=names)
+    a.compute_tensor_factorization(rank=5, init="random", random_state=3, runs=7, n_iter_max=30, tol=-1.0)
+    out_a = capsys.readouterr().out
+    b.compute_tensor_factorization(rank=5, init="random", random_state=3, runs=7, n_iter_max=30, tol=-1.0, batch_runs=False)
+    out_b = capsys.readouterr().out
+    assert "Best model has a normalized error of" in out_a and out_a == out_b
+    for k in a.factors:
+        np.testing.assert_allclose(a.factors[k].values, b.factors[k].values, rtol=2e-4, atol=1e-6)
+    assert a.explained_variance_ == pytest.approx(b.explained_variance_, rel=1e-5)
+    # the best run is the oracle's best run
+    errs = [o.non_negative_parafac(x, 5, n_iter_max=30, init="random", tol=-1.0, random_state=3 + r)[1][-1] for r in range(7)]
+    ref = o.non_negative_parafac(x, 5, n_iter_max=30, init="random", tol=-1.0, random_state=3 + int(np.argmin(errs)))[0]
+    for f, g in zip(a.tl_object.factors, ref.factors):
+        assert rel_err(f, g) < FACTOR_RTOL
+
+
 def test_mma_hals_matches_oracle(mma_from_rank_1):
     """HALS (unfused update kernels) over the tensor-pipe passes."""
     _compare_run(lowrank((40, 500, 16, 8), 6, seed=13), 16, 12, hals=True)
