@@ -8,4 +8,4 @@ built in-tree by ``python -m cell2cell_b200._build`` / ``__graft_entry__.build()
 __version__ = "0.1.0"
 
 from . import tensor  # noqa: E402,F401
-from . import analysis, io  # noqa: E402,F401
+from . import analysis, io, spatial  # noqa: E402,F401

@@ -83,12 +83,13 @@ def _nndsvd_columns(U, S, Vt, eps):
     return torch.sign(W) * (W.abs() - eps).clamp(min=0)
 
 
-def svd_factors(X, rank, random_state=None):
+def svd_factors(X, rank, random_state=None, non_negative=True):
     """tensorly ``initialize_cp(init='svd', svd='truncated_svd', non_negative=True)`` on a CUDA tensor.
 
     Per mode: left singular vectors of the unfolding from the eigen-decomposition of its fp64 Gram matrix
     ``X_(n) X_(n)^T`` (I_n x I_n, cuBLAS + cuSOLVER ``syevd``), right vectors as ``X_(n)^T U / S``, ``svd_flip``, NNDSVD,
-    mode-0 columns scaled by the singular values, random padding columns when ``I_n < rank``."""
+    mode-0 columns scaled by the singular values, random padding columns when ``I_n < rank``.  ``non_negative=False``
+    (plain ``parafac``) keeps the flipped left singular vectors instead of their NNDSVD."""
     rng = check_random_state(random_state)
     eps = float(np.finfo(np.float32).eps)
     out = []
@@ -106,7 +107,7 @@ def svd_factors(X, rank, random_state=None):
         signs = torch.sign(U[idx, torch.arange(k, device=U.device)])
         signs = torch.where(signs == 0, torch.ones_like(signs), signs)
         U, Vt = U * signs, Vt * signs[:, None]
-        W = _nndsvd_columns(U, S, Vt, eps)
+        W = _nndsvd_columns(U, S, Vt, eps) if non_negative else U
         if mode == 0:
             W = W * S[None, :]
         W = W.cpu().numpy()
@@ -117,15 +118,15 @@ def svd_factors(X, rank, random_state=None):
     return out
 
 
-def initialize_factors(X, rank, init="svd", svd="truncated_svd", random_state=None):
-    """List of non-negative ``[I_n, rank]`` float64 host factors (weights are ones)."""
+def initialize_factors(X, rank, init="svd", svd="truncated_svd", random_state=None, non_negative=True):
+    """List of ``[I_n, rank]`` float64 host factors (weights are ones); non-negative (``abs``) unless ``non_negative=False``."""
     if isinstance(init, str):
         if init == "random":
             factors = random_factors(X.shape, rank, random_state)
         elif init == "svd":
             if svd not in ("truncated_svd", "numpy_svd"):
                 raise ValueError("svd=%r is not supported (only 'truncated_svd')" % (svd,))
-            factors = svd_factors(X, rank, random_state)
+            factors = svd_factors(X, rank, random_state, non_negative=non_negative)
         else:
             raise ValueError('Initialization method "%s" not recognized' % init)
     else:
@@ -141,4 +142,5 @@ def initialize_factors(X, rank, init="svd", svd="truncated_svd", random_state=No
             w_avg = np.prod(w) ** (1.0 / w.shape[0])
             fs = [f * w_avg for f in fs]
         factors = fs
-    return [np.abs(np.asarray(f, dtype=np.float64)) for f in factors]
+    factors = [np.asarray(f, dtype=np.float64) for f in factors]
+    return [np.abs(f) for f in factors] if non_negative else factors

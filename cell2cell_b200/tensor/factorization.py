@@ -160,6 +160,92 @@ def non_negative_parafac_hals(tensor, rank, n_iter_max=100, init="svd", svd="tru
     return (cp, errors) if return_errors else cp
 
 
+def _khatri_rao_rows(factors, rank):
+    """[prod I_n, rank] Khatri-Rao rows of packed ``factors`` (first factor varies slowest, the tensor's C order)."""
+    kr = factors[0][:, :rank]
+    for f in factors[1:]:
+        kr = (kr[:, None, :] * f[None, :, :rank]).reshape(-1, rank)
+    return kr
+
+
+def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", normalize_factors=False, orthogonalise=False,
+            tol=1e-8, random_state=None, verbose=0, return_errors=False, sparsity=None, l2_reg=0, mask=None,
+            cvg_criterion="abs_rec_error", fixed_modes=None, svd_mask_repeats=5, linesearch=False, callback=None):
+    """tensorly ``parafac`` (alternating least squares, factors of any sign) on the device -- reached from cell2cell with
+    ``tf_type='parafac'`` (factorization.py:116-126).
+
+    The two streaming passes of the NCP path do the tensor work: ``T`` (every plane against the two trailing factors) gives
+    the MTTKRPs of the leading modes, ``U`` (every in-plane position against the leading Khatri-Rao rows) those of the two
+    trailing modes -- two reads of the tensor per iteration.  The ``R x R`` normal equations are solved in fp64 on the device
+    (``torch.linalg.solve``, cuSOLVER).  With a mask, tensorly re-imputes the missing entries once per iteration from the
+    factors of that iteration (``error_calc``); that imputed copy is materialised here (a cuBLAS product of the leading and
+    trailing Khatri-Rao rows and one extra write of the tensor per iteration).  Options tensorly offers beyond cell2cell's call are rejected loudly."""
+    for name, val in (("normalize_factors", normalize_factors), ("orthogonalise", orthogonalise), ("sparsity", sparsity),
+                      ("fixed_modes", fixed_modes), ("linesearch", linesearch), ("callback", callback)):
+        if val:
+            raise NotImplementedError("parafac(%s=%r) is not supported by the B200 path (cell2cell never sets it)" % (name, val))
+    if cvg_criterion not in ("abs_rec_error", "rec_error"):
+        raise TypeError("Unknown convergence criterion")
+    rank = int(rank)
+    X = as_device_tensor(tensor)
+    M = as_device_mask(mask, X)
+    if M is not None and isinstance(init, str) and init == "svd":
+        raise NotImplementedError("parafac(init='svd') with a mask (svd_mask_repeats) is not supported by the B200 path; "
+                                  "cell2cell forces init='random' for masked tensors (factorization.py:118)")
+    if X.dim() < 3:
+        raise C2CError("the B200 path factorizes tensors of order >= 3")
+    host = initialize_factors(X, rank, init=init, svd=svd, random_state=random_state, non_negative=False)
+    factors = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in host]
+    nd, shape = X.dim(), tuple(X.shape)
+    ws = engine.Workspace(shape, rank, False, X.device)
+    nx2 = torch.tensor(getattr(X, "_c2c_norm_x2", None) or engine.sumsq(X), dtype=torch.float64, device=X.device)
+    ridge = float(l2_reg) * torch.eye(rank, dtype=torch.float64, device=X.device)
+    Xc = X                                                   # masked: the re-imputed copy of the current iteration
+    keep = None if M is None else M.bool()
+    errors = []
+    converged = False
+    for it in range(int(n_iter_max)):
+        TU = None
+        for mode in range(nd):
+            G, _ = engine.gram_hadamard(factors, shape, rank, skip_mode=mode, ws=ws, as_tensor=True)
+            if mode == 0:
+                TU = engine.plane_contract(Xc, None, factors, rank, ws=ws)
+            elif mode == nd - 2:
+                TU = engine.fiber_contract(Xc, None, factors, rank, ws=ws)
+            Mk = engine.mttkrp_from_contraction(TU, shape, factors, rank, mode)
+            new = torch.linalg.solve(G[:rank, :rank].to(torch.float64).T + ridge, Mk[:, :rank].to(torch.float64).T).T
+            factors[mode][:, :rank] = new.to(torch.float32)
+        _, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=-1, ws=ws, as_tensor=True)
+        if keep is not None:
+            rec = (_khatri_rao_rows(factors[:-2], rank) @ _khatri_rao_rows(factors[-2:], rank).T).view(shape)
+            Xc = torch.where(keep, X, rec)
+            del rec
+            nx2 = torch.tensor(engine.sumsq(Xc), dtype=torch.float64, device=X.device)
+        iprod = (Mk[:, :rank].double() * factors[-1][:, :rank].double()).sum()
+        errors.append(float((torch.sqrt(torch.abs(nx2 + rn2[0] - 2.0 * iprod)) / torch.sqrt(nx2)).item()))
+        if verbose:
+            print("iteration {}, reconstruction error: {}".format(it, errors[-1]))
+        if tol and it >= 1:
+            dec = errors[-2] - errors[-1]
+            if (abs(dec) < tol) if cvg_criterion == "abs_rec_error" else (dec < tol):
+                converged = True
+                break
+    if verbose and converged:
+        print("PARAFAC converged after {} iterations".format(len(errors)))
+    sums = None
+    if M is None and errors:
+        # as for the NCP path: the kept (last) error is the directly accumulated ||X - rec|| / ||X|| (fp64 sums)
+        sums = engine.recon_sums(X, None, factors, rank)
+        errors[-1] = float(np.sqrt(sums[1]) / np.sqrt(sums[3]))
+    cp = CPTensor(np.ones(rank, dtype=np.float32), [engine.unpack_factor(f, rank).cpu().numpy() for f in factors],
+                  device=X.device)
+    if sums is not None:
+        cp.recon_sums_ = sums
+    if return_errors:
+        return cp, [np.float64(e) for e in errors]
+    return cp
+
+
 def _compute_tensor_factorization(tensor, rank, tf_type="non_negative_cp", init="svd", svd="truncated_svd",
                                   random_state=None, mask=None, n_iter_max=100, tol=10e-7, verbose=False, **kwargs):
     """Same contract as the reference's ``_compute_tensor_factorization`` (factorization.py:14-143)."""
@@ -176,8 +262,14 @@ def _compute_tensor_factorization(tensor, rank, tf_type="non_negative_cp", init=
         cp_tf, errors = non_negative_parafac_hals(tensor=tensor, rank=rank, init=init, svd=svd, random_state=random_state,
                                                   n_iter_max=n_iter_max, tol=tol, verbose=verbose, return_errors=True,
                                                   **kwargs)
-    elif tf_type in ("parafac", "constrained_parafac"):
-        raise NotImplementedError("tf_type=%r is outside the B200 hot path (non_negative_cp, non_negative_cp_hals)" % tf_type)
+    elif tf_type == "parafac":
+        kwargs.pop("return_errors", None)
+        cp_tf, errors = parafac(tensor=tensor, rank=rank, init="random" if mask is not None else init, svd=svd,
+                                random_state=random_state, mask=mask, n_iter_max=n_iter_max, tol=tol, verbose=verbose,
+                                return_errors=True, **kwargs)
+    elif tf_type == "constrained_parafac":
+        raise NotImplementedError("tf_type='constrained_parafac' (tensorly's AO-ADMM) is outside the B200 hot path "
+                                  "(non_negative_cp, non_negative_cp_hals, parafac)")
     else:
         raise ValueError("Not a valid tf_type.")
     if return_errors:

@@ -24,7 +24,8 @@ from .elbow import smooth_curve
 from .factorization import (_compute_elbow, _compute_norm_error, _compute_tensor_factorization,
                             _multiple_runs_elbow_analysis, _run_elbow_analysis, as_device_mask, as_device_tensor)
 
-__all__ = ["BaseTensor", "InteractionTensor", "PreBuiltTensor", "build_context_ccc_tensor", "generate_tensor_metadata"]
+__all__ = ["BaseTensor", "InteractionTensor", "PreBuiltTensor", "build_context_ccc_tensor", "generate_tensor_metadata",
+           "interactions_to_tensor"]
 
 _SCORES = ("expression_product", "expression_mean", "expression_gmean")
 
@@ -542,6 +543,34 @@ def generate_tensor_metadata(interaction_tensor, metadata_dicts, fill_with_order
             meta.index.name = "Element"
             meta.reset_index(inplace=True)
     return metadata
+
+
+def interactions_to_tensor(interactions, experiment="single_cell", context_names=None, how="inner", outer_fraction=0.0,
+                           communication_score="expression_product", upper_letter_comparison=True, verbose=True):
+    """4D tensor from a list of interaction pipelines, one per context (tensor.py:1318-1419).
+
+    The pipelines (``BulkInteractions`` / ``SingleCellInteractions``, cell2cell/analysis/cell2cell_pipelines.py) are outside
+    this package; any object with their attributes works: ``complex_sep``, ``complex_agg_method``, ``interaction_columns``,
+    ``analysis_setup['cci_type']``, ``ppi_data`` / ``ref_ppi`` and ``aggregated_expression`` (single cell) or
+    ``rnaseq_data`` (bulk).
+    """
+    ppis = []
+    rnaseq_matrices = []
+    first = interactions[0]
+    for inter in interactions:
+        ppis.append(inter.ref_ppi if inter.analysis_setup["cci_type"] == "undirected" else inter.ppi_data)
+        if experiment == "single_cell":
+            rnaseq_matrices.append(inter.aggregated_expression)
+        elif experiment == "bulk":
+            rnaseq_matrices.append(inter.rnaseq_data)
+        else:
+            raise ValueError("experiment must be 'single_cell' or 'bulk'")
+    ppi_data = pd.concat(ppis).drop_duplicates().reset_index(drop=True)
+    return InteractionTensor(rnaseq_matrices=rnaseq_matrices, ppi_data=ppi_data, context_names=context_names, how=how,
+                             outer_fraction=outer_fraction, complex_sep=first.complex_sep,
+                             complex_agg_method=first.complex_agg_method, interaction_columns=first.interaction_columns,
+                             communication_score=communication_score, upper_letter_comparison=upper_letter_comparison,
+                             verbose=verbose)
 
 
 _ = tqdm

@@ -29,7 +29,7 @@ import numpy as np
 
 __all__ = [
     "CPResult", "random_init", "svd_init", "initialize_cp", "mttkrp", "cp_to_tensor", "cp_norm", "cp_normalize",
-    "non_negative_parafac", "non_negative_parafac_hals", "hals_nnls", "masked_norm_error", "unfold",
+    "non_negative_parafac", "non_negative_parafac_hals", "hals_nnls", "masked_norm_error", "unfold", "parafac",
 ]
 
 
@@ -169,9 +169,10 @@ def _nndsvd(u, s, v, eps):
     return np.sign(w) * np.maximum(np.abs(w) - eps, 0.0)  # tensorly soft_thresholding(W, eps)
 
 
-def svd_init(x, rank, random_state=None):
+def svd_init(x, rank, random_state=None, non_negative=True):
     """initialize_cp(init='svd', svd='truncated_svd', non_negative=True): per mode, truncated SVD of the unfolding,
-    svd_flip, NNDSVD, scale mode 0 by the singular values, pad with random columns when I_n < R."""
+    svd_flip, NNDSVD, scale mode 0 by the singular values, pad with random columns when I_n < R.  ``non_negative=False``
+    (plain ``parafac``) keeps the flipped left singular vectors as they are."""
     rng = _rng(random_state)
     eps = np.finfo(x.dtype).eps
     factors = []
@@ -181,7 +182,7 @@ def svd_init(x, rank, random_state=None):
         u, s, vt = np.linalg.svd(m, full_matrices=False)
         u, s, vt = u[:, :k], s[:k], vt[:k, :]
         u, vt = _svd_flip(u, vt)
-        w = _nndsvd(u, s, vt, eps)
+        w = _nndsvd(u, s, vt, eps) if non_negative else u
         if mode == 0:
             w = w * s[None, :k]
         if x.shape[mode] < rank:
@@ -325,3 +326,59 @@ def non_negative_parafac_hals(tensor, rank, n_iter_max=100, init="svd", tol=10e-
                 if stop:
                     break
     return CPResult(weights, factors), errors
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# parafac (alternating least squares) -- tensorly/decomposition/_cp.py, reached from the reference at
+# cell2cell/tensor/factorization.py:116-126 (tf_type='parafac'; init='random' forced when a mask is given)
+# --------------------------------------------------------------------------------------------------------------------
+def parafac(tensor, rank, n_iter_max=100, init="svd", tol=1e-8, random_state=None, mask=None, l2_reg=0.0,
+            cvg_criterion="abs_rec_error", dtype=np.float64, return_iters=False):
+    """tensorly 0.8.x ``parafac`` with its defaults (no normalisation, orthogonalisation, sparsity, line search, fixed
+    modes): per mode ``A_n = solve(G^T, M^T)^T`` with ``G`` the Hadamard product of the other Grams (+ ``l2_reg`` I) and
+    ``M`` the MTTKRP; after the last mode ``error_calc``: with a mask the tensor is re-imputed ONCE per iteration
+    (``tensor*mask + rec*(1-mask)``, norm recomputed) and the Gram-form error uses the last mode's MTTKRP (taken before
+    the re-imputation) -- PARITY UNPINNED like the rest of this file.  Returns ``(CPResult, errors)``."""
+    x = np.array(tensor, dtype=dtype)
+    n_modes = x.ndim
+    if isinstance(init, str):
+        factors = random_init(x.shape, rank, random_state) if init == "random" else \
+            svd_init(x, rank, random_state, non_negative=False)
+    else:
+        w0, fs = init
+        factors = [np.array(f, dtype=float) for f in fs]
+        if w0 is not None and not np.all(np.asarray(w0) == 1):
+            w_avg = np.prod(np.asarray(w0, dtype=float)) ** (1.0 / len(w0))
+            factors = [f * w_avg for f in factors]
+    factors = [f.astype(dtype) for f in factors]
+    weights = np.ones(rank, dtype=dtype)
+    if mask is not None:
+        mask = np.asarray(mask).astype(dtype)
+    norm_x = np.sqrt(np.sum(x ** 2))
+    eye = np.eye(rank, dtype=dtype) * l2_reg
+    errors = []
+    it_done = 0
+    for it in range(n_iter_max):
+        for mode in range(n_modes):
+            g = np.ones((rank, rank), dtype=dtype)
+            for k in range(n_modes):
+                if k != mode:
+                    g = g * (factors[k].T @ factors[k])
+            g = g + eye
+            g = weights.reshape(-1, 1) * g * weights.reshape(1, -1)
+            m = mttkrp(x, weights, factors, mode)
+            factors[mode] = np.linalg.solve(g.T, m.T).T
+        it_done = it + 1
+        # error_calc(tensor, norm_tensor, weights, factors, sparsity=None, mask, mttkrp)
+        if mask is not None:
+            x = x * mask + cp_to_tensor(weights, factors) * (1 - mask)
+            norm_x = np.sqrt(np.sum(x ** 2))
+        iprod = np.sum(m * factors[n_modes - 1])
+        err = np.sqrt(np.abs(norm_x ** 2 + cp_norm(weights, factors) ** 2 - 2 * iprod)) / norm_x
+        errors.append(err)
+        if tol and it >= 1:
+            dec = errors[-2] - errors[-1]
+            if (abs(dec) < tol) if cvg_criterion == "abs_rec_error" else (dec < tol):
+                break
+    out = (CPResult(weights, factors), errors)
+    return out + (it_done,) if return_iters else out

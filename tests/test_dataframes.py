@@ -82,3 +82,73 @@ def test_subset_and_concatenate_follow_reference_semantics():
     assert np.array_equal(cat.mask.cpu().numpy(), np.concatenate([m, m[:2]], axis=0).take([0, 1, 2, 4], axis=0))
     plain = concatenate_interaction_tensors([t, PreBuiltTensor(x, order_names=names)], axis=1, order_labels=["a", "b", "c", "d"])
     assert plain.mask is None and plain.tensor.shape[1] == 12
+
+
+def _tiled_template(dist, shape, source_axis, target_axis):
+    """The reference's own template construction (spatial/filtering.py:52-70), kept in numpy as the checker."""
+    original_order = list(range(len(shape)))
+    new_order = []
+    template = dist
+    for i, size in enumerate(shape):
+        if i != source_axis and i != target_axis:
+            template = [template] * size
+            new_order.insert(0, i)
+    template = np.array(template)
+    new_order += [source_axis, target_axis]
+    return template.transpose([new_order.index(i) for i in original_order])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source_axis,target_axis", [(2, 3), (3, 2)])
+def test_dist_filter_tensor_follows_reference(source_axis, target_axis):
+    """spatial/filtering.py:6-82: scores of cell pairs outside [min_dist, max_dist] become real zeros."""
+    pd = pytest.importorskip("pandas")
+    from cell2cell_b200.spatial import dist_filter_tensor
+    from cell2cell_b200.tensor import PreBuiltTensor
+    rs = np.random.RandomState(3)
+    cells = list("ABCDE")
+    x = rs.rand(3, 7, 5, 5).astype(np.float32)
+    x[1, 2, 3, :] = np.nan
+    x[0, 0, 0, 0] = 0.0
+    names = [["c1", "c2", "c3"], ["lr%d" % i for i in range(7)], cells, cells]
+    t = PreBuiltTensor(x, order_names=names)
+    d = rs.rand(6, 6) * 10
+    distances = pd.DataFrame(d, index=list("FEDCBA"), columns=list("BFACED"))      # other order, one extra group
+    out = dist_filter_tensor(t, distances, max_dist=6.0, min_dist=1.0, source_axis=source_axis, target_axis=target_axis)
+    sub = distances.loc[cells, cells]
+    keep = ((1.0 <= sub) & (sub <= 6.0)).astype(int).values
+    want = np.nan_to_num(x) * _tiled_template(keep, x.shape, source_axis, target_axis)
+    assert np.array_equal(out.tensor.cpu().numpy(), want.astype(np.float32))
+    loc_nans = np.isnan(x).astype(int)
+    assert np.array_equal(out.loc_nans.cpu().numpy(), loc_nans)
+    assert np.array_equal(out.loc_zeros.cpu().numpy().astype(int), ((want == 0).astype(int) - loc_nans > 0).astype(int))
+    assert np.array_equal(t.tensor.cpu().numpy(), np.nan_to_num(x))               # the input object is untouched
+    with pytest.raises(AssertionError):
+        dist_filter_tensor(t, distances.drop(index="A"), max_dist=6.0)
+
+
+@pytest.mark.gpu
+def test_interactions_to_tensor_equals_direct_build():
+    """tensor.py:1318-1419: per-context pipeline objects -> one InteractionTensor over the union of their PPI lists."""
+    from types import SimpleNamespace
+    from cell2cell_b200.synthetic import synthetic_contexts, synthetic_ppi
+    from cell2cell_b200.tensor import InteractionTensor, interactions_to_tensor
+    ppi = synthetic_ppi(40, 80)
+    contexts = synthetic_contexts(3, 80, 5, outer=True)
+    pipes = []
+    for c, m in enumerate(contexts):
+        part = ppi.iloc[c * 10:(c + 2) * 10]                                        # overlapping slices: duplicates dropped
+        pipes.append(SimpleNamespace(complex_sep="&", complex_agg_method="min", interaction_columns=("A", "B"),
+                                     analysis_setup={"cci_type": "directed" if c else "undirected"},
+                                     ppi_data=part, ref_ppi=part, aggregated_expression=m, rnaseq_data=m))
+    got = interactions_to_tensor(pipes, experiment="single_cell", context_names=["a", "b", "c"], how="outer",
+                                 communication_score="expression_gmean", verbose=False)
+    import pandas as pd
+    merged = pd.concat([p.ppi_data for p in pipes]).drop_duplicates().reset_index(drop=True)
+    want = InteractionTensor(contexts, merged, context_names=["a", "b", "c"], how="outer", complex_sep="&",
+                             communication_score="expression_gmean", verbose=False)
+    assert got.order_names == want.order_names and len(got.order_names[1]) == len(merged)
+    assert np.array_equal(got.tensor.cpu().numpy(), want.tensor.cpu().numpy())
+    assert np.array_equal(got.mask.cpu().numpy(), want.mask.cpu().numpy())
+    with pytest.raises(ValueError):
+        interactions_to_tensor(pipes, experiment="spatial")

@@ -648,3 +648,45 @@ def test_api_shortcuts_keep_the_reference_values():
     assert int(u.loc_nans.sum()) == 1 and bool(torch.isfinite(u.tensor).all()) and not hasattr(u.tensor, "_c2c_norm_x2")
     assert float(u.tensor[0, 1, 2, 3]) == 0.0 and float(u.tensor[1, 0, 0, 0]) == float(np.finfo(np.float32).max)
     assert abs(engine.sumsq(t.tensor) - t.tensor._c2c_norm_x2) == 0.0
+
+
+@pytest.mark.parametrize("shape,rank", [((4, 30, 6, 6), 3), ((5, 11, 17, 17), 5), ((10, 6, 8), 2), ((40, 500, 16, 8), 16)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_parafac_als_matches_oracle(shape, rank, masked):
+    """tf_type='parafac' (factorization.py:116-126): ALS over the two streaming passes + fp64 R x R solves against the
+    numpy restatement of tensorly's parafac, identical random initial factors, fixed iteration count."""
+    from cell2cell_b200.tensor.factorization import _compute_tensor_factorization
+    n_iter = 12
+    x = lowrank(shape, min(rank, 4), seed=5, noise=0.05)
+    mask = (np.random.RandomState(9).rand(*shape) > 0.15).astype(np.uint8) if masked else None
+    xin = x * mask if masked else x
+    ref, ref_err = o.parafac(xin.astype(np.float64), rank, n_iter_max=n_iter, init="random", tol=-1.0, random_state=888,
+                             mask=None if mask is None else mask.astype(np.float64))
+    got, got_err = _compute_tensor_factorization(xin, rank, tf_type="parafac", init="svd" if masked else "random",
+                                                 random_state=888, mask=mask, n_iter_max=n_iter, tol=-1.0,
+                                                 return_errors=True)
+    assert len(got_err) == len(ref_err) == n_iter
+    # ALS factors are only defined up to the conditioning of the normal equations: compare the reconstructions
+    rec_ref, rec_got = ref.to_tensor(), o.cp_to_tensor(None, [f.astype(np.float64) for f in got.factors])
+    assert rel_err(rec_got, rec_ref) < 1e-3, rel_err(rec_got, rec_ref)
+    np.testing.assert_allclose(np.asarray(got_err), np.asarray(ref_err), rtol=1e-3, atol=1e-5)
+    if not masked:
+        direct = np.linalg.norm(x - rec_got) / np.linalg.norm(x)
+        assert abs(got_err[-1] - direct) <= 1e-4 * direct + 1e-7
+
+
+def test_parafac_through_the_api_and_rejected_options():
+    from cell2cell_b200.tensor import PreBuiltTensor
+    from cell2cell_b200.tensor.factorization import _compute_tensor_factorization, parafac
+    shape = (6, 40, 8, 8)
+    x = lowrank(shape, 3, seed=2, noise=0.02)
+    t = PreBuiltTensor(x, order_names=[["e%d_%d" % (m, i) for i in range(s)] for m, s in enumerate(shape)])
+    t.compute_tensor_factorization(rank=3, tf_type="parafac", init="svd", n_iter_max=50, tol=1e-7)
+    assert t.rank == 3 and list(t.factors.keys())[0].startswith("Dimension") or len(t.factors) == 4
+    assert t.explained_variance_ > 0.99
+    with pytest.raises(NotImplementedError):
+        parafac(x, 3, orthogonalise=True)
+    with pytest.raises(NotImplementedError):
+        _compute_tensor_factorization(x, 3, tf_type="constrained_parafac")
+    with pytest.raises(ValueError):
+        _compute_tensor_factorization(x, 3, tf_type="tucker")

@@ -81,3 +81,23 @@ def test_svd_init_shapes_nonneg():
     fs = o.initialize_cp(x, 5, init="svd", random_state=0)       # rank > I_0 -> random padding columns
     assert [f.shape for f in fs] == [(3, 5), (8, 5), (4, 5), (4, 5)]
     assert all((f >= 0).all() for f in fs)
+
+
+def test_parafac_als_recovers_low_rank_and_gram_error_matches_direct():
+    """ALS restatement (tensorly parafac): exact low-rank data is fitted to ~0, the error sequence is non-increasing
+    (unmasked: every mode update is an exact least-squares step) and the Gram-form error equals ||X - rec|| / ||X||."""
+    x, _ = lowrank((5, 8, 6, 7), 3, seed=1)
+    cp, errs = o.parafac(x, 3, init="random", random_state=2, n_iter_max=200, tol=1e-14)
+    assert errs[-1] < 1e-6
+    xn, _ = lowrank((5, 8, 6, 7), 3, seed=1, noise=0.05)
+    cp, errs = o.parafac(xn, 3, init="random", random_state=2, n_iter_max=30, tol=-1.0)
+    assert len(errs) == 30 and all(b <= a + 1e-12 for a, b in zip(errs, errs[1:]))
+    direct = np.linalg.norm(xn - cp.to_tensor()) / np.linalg.norm(xn)
+    assert abs(errs[-1] - direct) < 1e-10
+    cp_svd, errs_svd = o.parafac(xn, 3, init="svd", n_iter_max=30, tol=-1.0)
+    assert errs_svd[-1] < 1.05 * errs[-1] + 1e-3
+    # masked: missing entries are imputed once per iteration; the fit on the observed entries is close to the full fit
+    m = (np.random.RandomState(3).rand(*xn.shape) > 0.2).astype(float)
+    cpm, errm, n_it = o.parafac(xn * m, 3, init="random", random_state=2, n_iter_max=60, tol=1e-9, mask=m, return_iters=True)
+    assert n_it == len(errm) <= 60
+    assert o.masked_norm_error(xn * m, cpm, m) < 2.0 * direct + 1e-3
