@@ -26,6 +26,9 @@
 #include <cstring>
 
 #define C2C_VERSION 100
+#ifndef C2C_MMA_PLANE_LEAD
+#define C2C_MMA_PLANE_LEAD 2            // plane_mma takes over this many ranks before fiber_mma does
+#endif
 #ifndef C2C_MMA_DEFAULT_MIN_RANK
 #define C2C_MMA_DEFAULT_MIN_RANK 13
 #endif
@@ -244,7 +247,8 @@ static void mma_geometry(Geo& g, int rank)
     // shapes the FFMA kernels only take with narrow (< 128-bit) loads go to the tensor pipe at every rank; the plane pass
     // switches two ranks before the fiber pass (measured at 60x2000x40x40: plane_mma 0.135 ms vs plane_stream 0.145 / 0.155 ms
     // at ranks 11 / 12, fiber_mma 0.167 vs fiber_stream 0.145 at rank 12)
-    const int min_rank = g.vec_plane < 4 ? 1 : (mma_min_rank() > 2 ? mma_min_rank() - 2 : 1);
+    static const int plane_lead = env_int("C2C_B200_MMA_PLANE_LEAD", C2C_MMA_PLANE_LEAD);
+    const int min_rank = g.vec_plane < 4 ? 1 : (mma_min_rank() > plane_lead ? mma_min_rank() - plane_lead : 1);
     if (rank < min_rank || rank > 32 || g.nchunk != 1 || mma_min_rank() > 32 || !c2c_mma_available()) return;
     if (g.E % 4 != 0 || g.E < 128 || g.P < 128LL * nsm || g.P >= (1LL << 31) - 256) return;
     const int n = rank <= 16 ? 16 : 32;

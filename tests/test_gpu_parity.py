@@ -669,8 +669,14 @@ def test_parafac_als_matches_oracle(shape, rank, masked):
     # ALS factors are only defined up to the conditioning of the normal equations: compare the reconstructions
     rec_ref, rec_got = ref.to_tensor(), o.cp_to_tensor(None, [f.astype(np.float64) for f in got.factors])
     assert rel_err(rec_got, rec_ref) < 1e-3, rel_err(rec_got, rec_ref)
-    np.testing.assert_allclose(np.asarray(got_err), np.asarray(ref_err), rtol=1e-3, atol=1e-5)
-    if not masked:
+    # the per-iteration errors are tensorly's Gram form sqrt(|nx2 + rn2 - 2 ip|) / sqrt(nx2): in fp32 it cancels once the
+    # error is small (1e-7 relative on the squares is 5e-5 on an error of 1e-3)
+    np.testing.assert_allclose(np.asarray(got_err), np.asarray(ref_err), rtol=1e-3, atol=1e-4 if masked else 1e-5)
+    if masked:
+        from cell2cell_b200.tensor.factorization import _compute_norm_error
+        e_ref = o.masked_norm_error(xin.astype(np.float64), ref, mask.astype(np.float64))
+        assert abs(_compute_norm_error(xin, got, mask) - e_ref) <= 1e-3 * e_ref + 1e-6
+    else:
         direct = np.linalg.norm(x - rec_got) / np.linalg.norm(x)
         assert abs(got_err[-1] - direct) <= 1e-4 * direct + 1e-7
 
