@@ -45,6 +45,7 @@ SIGNATURES = {
     "c2c_mttkrp": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _p, _p, _sz, _p]),
     "c2c_mttkrp_from_contraction": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _p, _p]),
     "c2c_gram_hadamard": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "c2c_gram_hadamard_update": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "c2c_mu_update": (_i, [_p, _p, _p, _i64, _i, _i, _c.c_float, _p, _sz, _p]),
     "c2c_mu_update_coupled": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _c.c_float, _p, _p]),
     "c2c_coupled_ncp_run": (_i, [_p, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _p, _i, _i, _c.c_double, _i, _c.c_double,

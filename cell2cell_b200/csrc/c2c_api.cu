@@ -895,8 +895,8 @@ extern "C" int c2c_mttkrp_from_contraction(const float* TU, int ndim, const int6
     return launch_mode_mttkrp(g, A, mode, rank, ldr, w, M, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int c2c_gram_hadamard(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank, int skip_mode,
-                                 float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream)
+static int gram_hadamard_impl(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank, int changed_mode,
+                              int skip_mode, float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream)
 {
     Geo g; int rc;
     if (!shape) return fail(-1, "shape is NULL");
@@ -905,18 +905,35 @@ extern "C" int c2c_gram_hadamard(const float* const* A, int ndim, const int64_t*
     for (int i = 0; i < ndim; ++i) if (!A[i]) return fail(-11, "A[%d] is NULL", i);
     if (ldr != ldr_of(rank)) return fail(-12, "ldr must be %d", ldr_of(rank));
     if (skip_mode < -1 || skip_mode >= ndim) return fail(-13, "skip_mode %d out of range", skip_mode);
+    if (changed_mode < -1 || changed_mode >= ndim) return fail(-13, "changed_mode %d out of range", changed_mode);
     Ws w;
     if ((rc = get_ws(w, g, rank, 0, ws, ws_bytes)) != 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int k = 0; k < ndim; ++k) {
+    const int k0 = changed_mode < 0 ? 0 : changed_mode, k1 = changed_mode < 0 ? ndim : changed_mode + 1;
+    for (int k = k0; k < k1; ++k) {
         if ((rc = launch_gram_partial(A[k], nullptr, g.shape[k], rank, ldr, w, false, nullptr, st)) != 0) return rc;
         FinalizeArgs f = fin_args(g, rank, ldr, w, nullptr);
         f.k = k; f.gram_part = w.gram_part; f.nblk = (int)((g.shape[k] + C2C_UPD_ROWS - 1) / C2C_UPD_ROWS);
-        if (k == ndim - 1) { f.next = skip_mode < 0 ? ndim : skip_mode; f.G = G; f.rec_norm2 = rec_norm2; }
+        if (k == k1 - 1) { f.next = skip_mode < 0 ? ndim : skip_mode; f.G = G; f.rec_norm2 = rec_norm2; }
         gram_finalize_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(f);
         CKL("gram_finalize launch");
     }
     return 0;
+}
+
+extern "C" int c2c_gram_hadamard(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank, int skip_mode,
+                                 float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream)
+{
+    return gram_hadamard_impl(A, ndim, shape, ldr, rank, -1, skip_mode, G, rec_norm2, ws, ws_bytes, stream);
+}
+
+// only the Gram of factor `changed_mode` is recomputed; the others are the ones an earlier call left in this workspace
+extern "C" int c2c_gram_hadamard_update(const float* const* A, int ndim, const int64_t* shape, int ldr, int rank,
+                                        int changed_mode, int skip_mode, float* G, double* rec_norm2, void* ws,
+                                        size_t ws_bytes, void* stream)
+{
+    if (changed_mode < 0) return fail(-13, "changed_mode %d out of range", changed_mode);
+    return gram_hadamard_impl(A, ndim, shape, ldr, rank, changed_mode, skip_mode, G, rec_norm2, ws, ws_bytes, stream);
 }
 
 extern "C" int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, float eps,

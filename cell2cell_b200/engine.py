@@ -165,18 +165,27 @@ def launch_count():
     return int(lib().c2c_launch_count())
 
 
-def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None, as_tensor=False):
+def gram_hadamard(factors, shape, rank, skip_mode=-1, ws=None, as_tensor=False, changed_mode=None, out=None):
     """(G, cp_norm^2): Hadamard product of the factor Grams, skipping ``skip_mode`` (-1: none).  ``as_tensor`` returns the
-    norm as a 1-element fp64 CUDA tensor without synchronising."""
+    norm as a 1-element fp64 CUDA tensor without synchronising.  ``changed_mode``: only that factor changed since the last
+    call made with this ``ws`` -- its Gram alone is recomputed (``c2c_gram_hadamard_update``).  ``out``: the ``[ldr, ldr]``
+    buffer G is written to."""
     dev = factors[0].device
     with torch.cuda.device(dev):
         if ws is None:
+            if changed_mode is not None:
+                raise C2CError("gram_hadamard(changed_mode=...) needs the workspace of the call that computed the other Grams")
             ws = Workspace(shape, rank, False, dev)
         ldr = ldr_of(rank)
-        G = torch.empty((ldr, ldr), dtype=torch.float32, device=dev)
+        G = out if out is not None else torch.empty((ldr, ldr), dtype=torch.float32, device=dev)
         n2 = torch.zeros(1, dtype=torch.float64, device=dev)
-        check(lib().c2c_gram_hadamard(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr, rank, skip_mode, _ptr(G),
-                                      _ptr(n2), ws.ptr, ws.nbytes, _stream()), "c2c_gram_hadamard")
+        if changed_mode is None:
+            check(lib().c2c_gram_hadamard(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr, rank, skip_mode, _ptr(G),
+                                          _ptr(n2), ws.ptr, ws.nbytes, _stream()), "c2c_gram_hadamard")
+        else:
+            check(lib().c2c_gram_hadamard_update(_ptr_arr(factors), len(factors), _shape_arr(shape), ldr, rank,
+                                                 int(changed_mode), skip_mode, _ptr(G), _ptr(n2), ws.ptr, ws.nbytes,
+                                                 _stream()), "c2c_gram_hadamard_update")
         return (G, n2) if as_tensor else (G, float(n2.item()))
 
 

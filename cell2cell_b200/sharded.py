@@ -56,11 +56,14 @@ class DeviceOps:
     def m_from(self, TU, shape, factors, mode):
         return engine.mttkrp_from_contraction(TU, shape, factors, self.R, mode)
 
-    def gram_hadamard(self, factors, shape, skip):
+    def gram_hadamard(self, factors, shape, skip, changed=None, out=None):
+        """``changed``: only that factor changed since the previous call for this shape -- its Gram alone is recomputed."""
         key = (tuple(shape), factors[0].device)
         if key not in self._gws:
             self._gws[key] = engine.Workspace(shape, self.R, False, factors[0].device)
-        return engine.gram_hadamard(factors, shape, self.R, skip, ws=self._gws[key], as_tensor=True)
+            changed = None
+        return engine.gram_hadamard(factors, shape, self.R, skip, ws=self._gws[key], as_tensor=True, changed_mode=changed,
+                                    out=out)
 
     def mu_update(self, A, M, G):
         return engine.mu_update(A, M, G, self.R)
@@ -115,31 +118,39 @@ def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter
     err_dev = torch.zeros(1, dtype=torch.float64, device=dev)            # this iteration's error, written by `iteration`
     errors_dev = torch.zeros(max(int(n_iter_max), 1), dtype=torch.float64, device=dev)
 
+    # Gauss-Seidel changes one factor per update: after each update only that factor's Gram is recomputed and the Hadamard
+    # product for the NEXT mode comes out of the same call (2 launches per mode).  G0 (mode 0 of the next iteration) lives in
+    # a fixed buffer so that a replayed graph reads what the previous replay wrote.
+    G0, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, 0)
+
     def iteration():
         loc = [A_loc0] + A[1:]
+        full = [A_full0] + A[1:]
         T = ops.plane(X_local, loc, ws)
         # ---- mode 0: rows of the local contexts ----
         M0 = ops.m_from(T, local_shape, loc, 0)
-        G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, 0)
-        ops.mu_update(A_loc0, M0, G)
+        ops.mu_update(A_loc0, M0, G0)
         A_full0.zero_()
         A_full0[lo:hi] = A_loc0
         allreduce(A_full0)
+        G, _ = ops.gram_hadamard(full, full_shape, 1, changed=0)
         # ---- other leading modes: partial M all-reduced, update replicated ----
         for k in range(1, nd - 2):
-            Mk = ops.m_from(T, local_shape, [A_loc0] + A[1:], k)
+            Mk = ops.m_from(T, local_shape, loc, k)
             allreduce(Mk)
-            G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, k)
             ops.mu_update(A[k], Mk, G)
+            G, _ = ops.gram_hadamard(full, full_shape, k + 1, changed=k)
         # ---- trailing modes from the all-reduced fiber contraction ----
-        U = ops.fiber(X_local, [A_loc0] + A[1:], ws)
+        U = ops.fiber(X_local, loc, ws)
         allreduce(U)
-        M = None
+        M = rn2 = None
         for mode in (nd - 2, nd - 1):
-            M = ops.m_from(U, full_shape, [A_full0] + A[1:], mode)
-            G, _ = ops.gram_hadamard([A_full0] + A[1:], full_shape, mode)
+            M = ops.m_from(U, full_shape, full, mode)
             ops.mu_update(A[mode], M, G)
-        _, rn2 = ops.gram_hadamard([A_full0] + A[1:], full_shape, -1)
+            if mode == nd - 2:
+                G, _ = ops.gram_hadamard(full, full_shape, mode + 1, changed=mode)
+            else:                                                      # next iteration's mode-0 product + the cp norm
+                _, rn2 = ops.gram_hadamard(full, full_shape, 0, changed=mode, out=G0)
         iprod = (ops.unpack(M).double() * ops.unpack(A[nd - 1]).double()).sum()
         err_dev.copy_((torch.sqrt(torch.abs(norm_x2 + rn2 - 2.0 * iprod)) / np.sqrt(norm_x2)).reshape(1))
 

@@ -124,6 +124,12 @@ int c2c_mttkrp_from_contraction(const float* TU, int ndim, const int64_t* shape 
  */
 int c2c_gram_hadamard(const float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
                       int skip_mode, float* G, double* rec_norm2, void* ws, size_t ws_bytes, void* stream);
+/* Same result when only factor `changed_mode` was modified since the last c2c_gram_hadamard / _update call made with this
+ * workspace: its Gram is recomputed, the other Grams are the ones that call left in `ws` (2 launches instead of 2 * ndim;
+ * the Gauss-Seidel order of the update loop changes one factor at a time). */
+int c2c_gram_hadamard_update(const float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
+                             int changed_mode, int skip_mode, float* G, double* rec_norm2, void* ws, size_t ws_bytes,
+                             void* stream);
 
 /* ---- K4: multiplicative update  A <- A * max(M, eps) / max(A G, eps)  (coupled_factorization.py:346-348) ---------- */
 int c2c_mu_update(float* A_mode, const float* M, const float* G, int64_t I, int rank, int ldr, float eps,

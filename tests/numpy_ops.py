@@ -73,7 +73,7 @@ class NumpyOps:
             return torch.as_tensor(np.einsum("svr,vr->sr", u, factors[-1].numpy()))
         return torch.as_tensor(np.einsum("svr,sr->vr", u, factors[-2].numpy()))
 
-    def gram_hadamard(self, factors, shape, skip):
+    def gram_hadamard(self, factors, shape, skip, changed=None, out=None):
         R = factors[0].shape[1]
         g = np.ones((R, R))
         allg = np.ones((R, R))
@@ -82,6 +82,9 @@ class NumpyOps:
             allg = allg * gk
             if k != skip:
                 g = g * gk
+        if out is not None:
+            out.copy_(torch.as_tensor(g))
+            return out, torch.as_tensor(np.array([allg.sum()]))
         return torch.as_tensor(g), torch.as_tensor(np.array([allg.sum()]))
 
     def mu_update(self, A, M, G):
