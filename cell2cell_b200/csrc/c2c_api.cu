@@ -17,6 +17,7 @@
 #include "c2c_mma.cuh"
 #include "c2c_small.cuh"
 #include "c2c_update.cuh"
+#include "c2c_sums.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -992,6 +993,19 @@ extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, con
         sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, C2C_SUMS_BLOCKS, 5, 5, out);
         CKL("recon_sums reduce launch");
         return 0;
+    }
+    static const int stream_sums = env_int("C2C_B200_NO_STREAM_SUMS", 0) ? 0 : 1;
+    if (!mask && stream_sums) {                       // one read of X at streaming speed (c2c_sums.cu) when the shape allows
+        int sgrid = 0;
+        const cudaError_t e = c2c_launch_sums_stream(a, sm_count(), st, &sgrid);
+        if (e == cudaSuccess) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, sgrid, 5, 5, out);
+            CKL("recon_sums reduce launch");
+            return 0;
+        }
+        if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) return cuda_fail(e, "recon_sums (stream) launch");
+        (void)cudaGetLastError();
     }
     const int vec = g.vec_plane;
     const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);

@@ -1,0 +1,143 @@
+// recon_sums, streaming version (unmasked, in-plane row length a multiple of 4):
+//     sum (x - rec), sum (x - rec)^2, sum x, sum x^2        rec[p, s, v] = sum_q W[p, q] A2[s, q] A3[v, q]
+// -- the directly accumulated ||X - rec|| the factorization keeps as its final error (tensor.py:311-315) and the sums of
+// explained_variance (tensor.py:659-688).  One read of X at streaming speed:
+//   * a thread owns ONE float4 position (row s, columns v0..v0+3) of the plane for the whole kernel, so its A2 row and its four
+//     A3 rows live in registers (5 * NQ floats) and a reconstruction costs NQ multiplies + 4 * NQ FMAs per 4 elements with
+//     no shared-memory traffic besides the NQ / 4 broadcast reads of the plane's Khatri-Rao row W[p, :];
+//   * `nslots` thread groups take alternate planes; every thread keeps U = 8 float4 loads in flight (64 KB per SM with 512
+//     threads), the CTA's W rows of a batch of nslots * U planes are staged in shared memory first;
+//   * fp32 sums over the 4 * U elements of a batch, fp64 across batches, fixed-order block / grid reduction.
+#include "c2c_common.cuh"
+#include "c2c_sums.cuh"
+
+#define C2C_SF_U 8
+
+template <int NQ, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+recon_sums_stream_kernel(const float* __restrict__ X, const LeadInfo lead, const float* __restrict__ A2,
+                         const float* __restrict__ A3, long long P, int I2, int I3, int R, int ldr, int nquads, int nslots,
+                         double* __restrict__ sums_part)
+{
+    extern __shared__ __align__(16) float sW[];                      // [nslots * U][NQ]
+    __shared__ double red[4][THREADS / 32];
+    const int t = threadIdx.x;
+    const int slot = t / nquads, pos = t - slot * nquads;
+    const bool on = slot < nslots;
+    const int k4 = I3 >> 2;
+    const int s = pos / k4, v0 = (pos - s * k4) << 2;
+    const size_t E = (size_t)I2 * I3;
+    float a2[NQ], a3[4][NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const bool in = on && q < R;
+        a2[q] = in ? __ldg(A2 + (size_t)s * ldr + q) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a3[j][q] = in ? __ldg(A3 + (size_t)(v0 + j) * ldr + q) : 0.0f;
+    }
+    double acc_d = 0.0, acc_dd = 0.0, acc_x = 0.0, acc_xx = 0.0;
+    const int batch = nslots * C2C_SF_U;
+    for (long long p0 = (long long)blockIdx.x * batch; p0 < P; p0 += (long long)gridDim.x * batch) {
+        float4 x[C2C_SF_U];
+        if (on) {
+#pragma unroll
+            for (int u = 0; u < C2C_SF_U; ++u) {
+                const long long p = p0 + (long long)u * nslots + slot;
+                x[u] = p < P ? __ldcs(reinterpret_cast<const float4*>(X + (size_t)p * E) + pos) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();                                             // the previous batch's W rows are no longer read
+        for (int i = t; i < batch * NQ; i += THREADS) {
+            const int pl = i / NQ, q = i - pl * NQ;
+            const long long p = p0 + pl;
+            sW[i] = (p < P && q < R) ? lead_weight_col(p, lead, ldr, q, -1) : 0.0f;
+        }
+        __syncthreads();
+        if (on) {
+            float fd = 0.f, fdd = 0.f, fx = 0.f, fxx = 0.f;
+#pragma unroll
+            for (int u = 0; u < C2C_SF_U; ++u) {
+                const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)(u * nslots + slot) * NQ);
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+                for (int q4 = 0; q4 < NQ / 4; ++q4) {
+                    const float4 w = w4[q4];
+                    const float wq[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int q = q4 * 4 + i;
+                        const float wa = wq[i] * a2[q];
+                        r0 = fmaf(wa, a3[0][q], r0); r1 = fmaf(wa, a3[1][q], r1);
+                        r2 = fmaf(wa, a3[2][q], r2); r3 = fmaf(wa, a3[3][q], r3);
+                    }
+                }
+                const float4 xv = x[u];                              // planes past the end: x = 0 and W = 0 -> no contribution
+                const float d0 = xv.x - r0, d1 = xv.y - r1, d2 = xv.z - r2, d3 = xv.w - r3;
+                fd += (d0 + d1) + (d2 + d3);
+                fdd = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, fdd))));
+                fx += (xv.x + xv.y) + (xv.z + xv.w);
+                fxx = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, fxx))));
+            }
+            acc_d += (double)fd; acc_dd += (double)fdd; acc_x += (double)fx; acc_xx += (double)fxx;
+        }
+    }
+    // fixed-order block reduction: shuffle tree per warp, then warp 0 walks the per-warp values in order
+    double v[4] = {acc_d, acc_dd, acc_x, acc_xx};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double wsum = warp_sum(v[k]);
+        if ((t & 31) == 0) red[k][t >> 5] = wsum;
+    }
+    __syncthreads();
+    if (t < 4) {
+        double tot = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) tot += red[t][w];
+        sums_part[(size_t)blockIdx.x * 5 + t] = tot;
+    }
+    if (t == 4) sums_part[(size_t)blockIdx.x * 5 + 4] = blockIdx.x == 0 ? (double)P * (double)E : 0.0;
+}
+
+template <int NQ, int THREADS>
+static cudaError_t launch_one(const ContractArgs& a, int nquads, int grid_max, cudaStream_t st, int* grid_out)
+{
+    const int nslots_max = THREADS / nquads;
+    // no more slots than give every CTA of a full grid at least one batch
+    long long nslots = nslots_max;
+    const long long per_cta = (a.P + grid_max - 1) / grid_max;
+    if (nslots * C2C_SF_U > per_cta) nslots = (per_cta + C2C_SF_U - 1) / C2C_SF_U;
+    if (nslots < 1) nslots = 1;
+    const long long batch = nslots * C2C_SF_U;
+    long long grid = (a.P + batch - 1) / batch;
+    if (grid > grid_max) grid = grid_max;
+    const size_t smem = (size_t)batch * NQ * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    recon_sums_stream_kernel<NQ, THREADS><<<(unsigned)grid, THREADS, smem, st>>>(a.X, a.lead, a.A2, a.A3, a.P, a.I2, a.I3, a.R,
+                                                                               a.ldr, nquads, (int)nslots, a.sums);
+    *grid_out = (int)grid;
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorNotSupported when the shape / rank is outside this kernel (the caller then takes the general kernel).
+cudaError_t c2c_launch_sums_stream(const ContractArgs& a, int grid_max, cudaStream_t st, int* grid_out)
+{
+    if (a.mask != nullptr || a.r0 != 0 || a.p0 != 0 || (a.I3 & 3) != 0 || a.R > 32 || a.R < 1) return cudaErrorNotSupported;
+    if (((uintptr_t)a.X & 15) != 0) return cudaErrorNotSupported;
+    const long long nq = (long long)a.I2 * (a.I3 >> 2);
+    const int nq4 = (a.R + 3) / 4;
+    if (nq4 <= 3) {
+        if (nq > 512) return cudaErrorNotSupported;
+        switch (nq4) {
+            case 1: return launch_one<4, 512>(a, (int)nq, grid_max, st, grid_out);
+            case 2: return launch_one<8, 512>(a, (int)nq, grid_max, st, grid_out);
+            default: return launch_one<12, 512>(a, (int)nq, grid_max, st, grid_out);
+        }
+    }
+    if (nq > 256) return cudaErrorNotSupported;
+    switch (nq4) {
+        case 4: return launch_one<16, 256>(a, (int)nq, grid_max, st, grid_out);
+        case 5: return launch_one<20, 256>(a, (int)nq, grid_max, st, grid_out);
+        case 6: return launch_one<24, 256>(a, (int)nq, grid_max, st, grid_out);
+        case 7: return launch_one<28, 256>(a, (int)nq, grid_max, st, grid_out);
+        default: return launch_one<32, 256>(a, (int)nq, grid_max, st, grid_out);
+    }
+}

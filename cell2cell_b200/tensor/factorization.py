@@ -198,16 +198,18 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", norma
     factors = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in host]
     nd, shape = X.dim(), tuple(X.shape)
     ws = engine.Workspace(shape, rank, False, X.device)
+    gws = engine.Workspace(shape, rank, False, X.device)   # keeps the factor Grams between the calls below
     nx2 = torch.tensor(getattr(X, "_c2c_norm_x2", None) or engine.sumsq(X), dtype=torch.float64, device=X.device)
     ridge = float(l2_reg) * torch.eye(rank, dtype=torch.float64, device=X.device)
     Xc = X                                                   # masked: the re-imputed copy of the current iteration
     keep = None if M is None else M.bool()
     errors = []
     converged = False
+    # one factor changes per update: only its Gram is recomputed, and the same call yields the next mode's Hadamard product
+    G, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=0, ws=gws, as_tensor=True)
     for it in range(int(n_iter_max)):
         TU = None
         for mode in range(nd):
-            G, _ = engine.gram_hadamard(factors, shape, rank, skip_mode=mode, ws=ws, as_tensor=True)
             if mode == 0:
                 TU = engine.plane_contract(Xc, None, factors, rank, ws=ws)
             elif mode == nd - 2:
@@ -215,7 +217,8 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", norma
             Mk = engine.mttkrp_from_contraction(TU, shape, factors, rank, mode)
             new = torch.linalg.solve(G[:rank, :rank].to(torch.float64).T + ridge, Mk[:, :rank].to(torch.float64).T).T
             factors[mode][:, :rank] = new.to(torch.float32)
-        _, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=-1, ws=ws, as_tensor=True)
+            G, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=(mode + 1) % nd, ws=gws, as_tensor=True,
+                                          changed_mode=mode)
         if keep is not None:
             rec = (_khatri_rao_rows(factors[:-2], rank) @ _khatri_rao_rows(factors[-2:], rank).T).view(shape)
             Xc = torch.where(keep, X, rec)
