@@ -18,6 +18,7 @@
 #include "c2c_small.cuh"
 #include "c2c_update.cuh"
 #include "c2c_sums.cuh"
+#include "c2c_corr.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -384,6 +385,7 @@ static int make_geo(Geo& g, int ndim, const int64_t* shape, int rank)
 // ---------------------------------------------------------------------------------------------------------------------
 struct Ws {
     float* T; float* part; float* U; float* M; float* G; float* Bmat; float* Xh; float* W;
+    float* Tw; float* Uw; float* cpart;      // masked runs, dense pass + missing-entry correction (c2c_corr.cu)
     double* S; double* gram_part; double* iprod_part; double* normX2; double* sums_part; double* scratch_d;
     int* flags;
     size_t bytes;
@@ -407,6 +409,10 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     w.Bmat = (float*)take(masked ? (size_t)g.E * ldr * sizeof(float) : 0);
     // ranks beyond one chunk: the masked passes need the full-rank reconstruction, so the imputed tensor is materialised
     w.Xh = (float*)take((masked && g.nchunk > 1) ? (size_t)g.P * g.E * sizeof(float) : 0);
+    const bool corr_ws = masked && g.nchunk == 1;
+    w.Tw = (float*)take(corr_ws ? (size_t)g.P * ldr * sizeof(float) : 0);
+    w.Uw = (float*)take(corr_ws ? (size_t)g.E * ldr * sizeof(float) : 0);
+    w.cpart = (float*)take(corr_ws ? (size_t)C2C_CORR_MAX_PARTS * g.E * ldr * sizeof(float) : 0);
     w.S = (double*)take((size_t)2 * g.ndim * ldr * ldr * sizeof(double));        // two banks (c2c_update.cuh)
     const long long nblk_g = nblk > 512 ? nblk : 512;             // lead_update runs at most 2 CTAs per SM, capped at 512
     w.gram_part = (double*)take((size_t)nblk_g * ldr * ldr * sizeof(double));
@@ -1044,6 +1050,7 @@ struct RunCtx {
     unsigned char run_of[32];
     int* run_flags; int* run_iters;
     bool mma_zero;             // plane_mma / fiber_mma: T is kept cleared by the fiber pass
+    bool corr;                 // masked run as unmasked dense passes + missing-entry corrections (c2c_corr.cu)
 };
 
 static int update_mode(const RunCtx& c, int mode, bool last)
@@ -1148,8 +1155,57 @@ static bool fused_updates(const RunCtx& c)
            c.g.P < (1LL << 31);
 }
 
+// Masked iteration, dense + correction form (c2c_corr.cu): ONE unmasked plane pass serves every leading mode and ONE unmasked
+// fiber pass both trailing modes (the dense parts do not depend on the factors of their own side); before each mode's fused
+// update the contribution of the re-imputed missing entries -- which does -- is added by a kernel that streams the mask only.
+static int enqueue_iteration_corr(const RunCtx& c)
+{
+    const Geo& g = c.g; int rc;
+    const int* done = c.state + 1;
+    const float* const* A = (const float* const*)c.A;
+    const int nlead = g.ndim - 2;
+    const long long nB = g.E * c.ldr;
+    auto bmat = [&]() -> int {
+        bmat_kernel<<<(int)((nB + 255) / 256), 256, 0, c.st>>>(A[g.ndim - 2], A[g.ndim - 1], g.I2, g.I3, c.ldr, c.w.Bmat, done);
+        CKL("bmat launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    };
+    RunCtx c2 = c;
+    c2.w.T = c.w.Tw; c2.w.U = c.w.Uw;
+    if ((rc = bmat()) != 0) return rc;
+    {
+        ContractArgs a = base_args(g, c.X, nullptr, A, c.ldr, c.R, done);
+        if ((rc = launch_plane(g, a, false, c.w.T, c.st)) != 0) return rc;
+    }
+    for (int mode = 0; mode < nlead; ++mode) {
+        LeadInfo li; fill_lead(li, g, A);
+        const cudaError_t e = c2c_launch_plane_corr(c.mask, li, c.w.Bmat, c.w.T, c.w.Tw, g.P, g.E, c.R, c.ldr, done, sm_count(), c.st);
+        if (e != cudaSuccess) return cuda_fail(e, "plane_corr launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if ((rc = launch_lead_update(c2, mode)) != 0) return rc;
+    }
+    {
+        ContractArgs a = base_args(g, c.X, nullptr, A, c.ldr, c.R, done);
+        if ((rc = launch_fiber(g, a, false, c.w, c.st)) != 0) return rc;
+    }
+    for (int j = 0; j < 2; ++j) {
+        if (j == 1 && (rc = bmat()) != 0) return rc;                 // the first trailing factor has just changed
+        LeadInfo li; fill_lead(li, g, A);
+        int nparts = sm_count();
+        if (nparts > C2C_CORR_MAX_PARTS) nparts = C2C_CORR_MAX_PARTS;
+        const cudaError_t e = c2c_launch_fiber_corr(c.mask, li, c.w.Bmat, c.w.U, c.w.Uw, c.w.cpart, nparts, g.P, g.E, c.R, c.ldr,
+                                                    done, c.st);
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_corr launch");
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        if ((rc = launch_trail_update(c2, j, j + 1)) != 0) return rc;
+    }
+    return 0;
+}
+
 static int enqueue_iteration(const RunCtx& c)
 {
+    if (c.corr) return enqueue_iteration_corr(c);
     const Geo& g = c.g; int rc;
     const int* done = c.state + 1;
     const float* const* A = (const float* const*)c.A;
@@ -1211,6 +1267,19 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     }
     CK(cudaMemsetAsync(state, 0, (size_t)(nruns > 1 ? 2 + 2 * nruns : 2) * sizeof(int), st), "memset state");
     CK(cudaMemsetAsync(c.w.flags, 0, 4 * sizeof(int), st), "memset flags");
+    // masked run as dense passes + missing-entry corrections: needs the fused update kernels, one rank chunk, the U correction
+    // of a CTA in shared memory, and zeros at the missing entries of X (checked once here; cell2cell's tensors have them:
+    // nan_to_num of the NaN the mask was derived from, tensor.py:842-847, 933-946)
+    c.corr = false;
+    if (mask != nullptr && algo == C2C_ALGO_MU && g.nchunk == 1 && rank <= 32 && fused_updates(c) &&
+        c2c_fiber_corr_smem(g.E, ldr) <= C2C_CORR_SMEM_MAX && !env_int("C2C_B200_NO_MASK_CORR", 0)) {
+        int host_flag = 1;
+        const cudaError_t e = c2c_launch_masked_nonzero(X, mask, g.P * g.E, c.w.flags + 2, sm_count(), st);
+        if (e != cudaSuccess) return cuda_fail(e, "masked_nonzero launch");
+        CK(cudaMemcpyAsync(&host_flag, c.w.flags + 2, sizeof(int), cudaMemcpyDeviceToHost, st), "copy zero-fill flag");
+        CK(cudaStreamSynchronize(st), "zero-fill check");
+        c.corr = host_flag == 0;
+    }
     if (normX2) c.normX2 = normX2;
     else {
         if ((rc = sumsq_into(X, g.P * g.E, c.w.normX2, c.w.sums_part, st)) != 0) return rc;

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--shape", type=int, nargs="+", default=[60, 2000, 40, 40])
     ap.add_argument("--ranks", type=int, nargs="+", default=[10])
     ap.add_argument("--masked", action="store_true")
+    ap.add_argument("--structured", action="store_true", help="masked: missing rows / columns / planes instead of 20 %% random entries")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--tag", default=os.environ.get("C2C_B200_LIB", "product"))
@@ -42,6 +43,14 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     X = torch.rand(shape, generator=g, device="cuda")
     mask = (torch.rand(shape, generator=g, device="cuda") > 0.2).to(torch.uint8) if args.masked else None
+    if args.structured and mask is not None:          # what how='outer' produces: a cell type missing from every 3rd context
+        mask.fill_(1)                                 # (its sender rows and receiver columns) and 2 % of the planes missing
+        mask[2::3, ..., 5, :] = 0
+        mask[2::3, ..., :, 5] = 0
+        gone = torch.rand(shape[:-2], generator=g, device="cuda") < 0.02
+        mask[gone] = 0
+    if mask is not None:
+        X = X * mask                                  # cell2cell's tensors hold zeros at their missing entries (nan_to_num)
     n_x = X.numel()
     letters = "abcdefgh"[: len(shape)]
     for R in args.ranks:

@@ -696,3 +696,30 @@ def test_parafac_through_the_api_and_rejected_options():
         _compute_tensor_factorization(x, 3, tf_type="constrained_parafac")
     with pytest.raises(ValueError):
         _compute_tensor_factorization(x, 3, tf_type="tucker")
+
+
+@pytest.mark.parametrize("shape,rank", [((13, 60, 17, 17), 10), ((9, 50, 16, 12), 4), ((4, 5, 7, 8, 12), 6), ((40, 500, 16, 8), 20)])
+def test_masked_run_dense_plus_correction_equals_fused_imputation(shape, rank, monkeypatch):
+    """The masked factorization as unmasked passes + missing-entry corrections (c2c_corr.cu) against the kernels that
+    impute inside the pass (C2C_B200_NO_MASK_CORR=1) and against the oracle; values at the missing entries of the input do
+    not matter (a tensor that is not zero there takes the imputing kernels)."""
+    from cell2cell_b200.tensor.factorization import non_negative_parafac
+    rs = np.random.RandomState(11)
+    x = lowrank(shape, 4, seed=3, noise=0.05)
+    mask = (rs.rand(*shape) > 0.2).astype(np.uint8)
+    mask[1::3, ..., 2, :] = 0
+    mask[1::3, ..., :, 2] = 0
+    mask[0, 1] = 0
+    xz = x * mask
+    got, got_err = _compare_run(xz, rank, 25, mask=mask)
+    monkeypatch.setenv("C2C_B200_NO_MASK_CORR", "1")
+    old, old_err = non_negative_parafac(xz, rank, n_iter_max=25, init="random", tol=-1.0, random_state=888, mask=mask,
+                                        return_errors=True)
+    monkeypatch.delenv("C2C_B200_NO_MASK_CORR")
+    garbage = xz + (1 - mask) * rs.rand(*shape).astype(x.dtype)
+    dirty, dirty_err = non_negative_parafac(garbage, rank, n_iter_max=25, init="random", tol=-1.0, random_state=888, mask=mask,
+                                            return_errors=True)
+    for a, b, c in zip(got.factors, old.factors, dirty.factors):
+        assert rel_err(a, b) < 2e-5, rel_err(a, b)
+        assert rel_err(c, b) < 2e-5, rel_err(c, b)
+    np.testing.assert_allclose(np.asarray(got_err), np.asarray(old_err), rtol=1e-4, atol=3e-6)
