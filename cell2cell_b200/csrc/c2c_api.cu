@@ -1192,7 +1192,7 @@ static int enqueue_iteration_corr(const RunCtx& c)
     for (int j = 0; j < 2; ++j) {
         if (j == 1 && (rc = bmat()) != 0) return rc;                 // the first trailing factor has just changed
         LeadInfo li; fill_lead(li, g, A);
-        int nparts = sm_count();
+        int nparts = 2 * sm_count();
         if (nparts > C2C_CORR_MAX_PARTS) nparts = C2C_CORR_MAX_PARTS;
         const cudaError_t e = c2c_launch_fiber_corr(c.mask, li, c.w.Bmat, c.w.U, c.w.Uw, c.w.cpart, nparts, g.P, g.E, c.R, c.ldr,
                                                     done, c.st);

@@ -202,8 +202,10 @@ plane_corr16_kernel(const uint8_t* __restrict__ mask, const LeadInfo lead, const
 // in-plane size a multiple of 4: thread t owns the four positions 4t .. 4t+3 (and their rows of Us); it reads their mask bytes
 // of 32 planes as 32 independent 32-bit loads, then visits the (position, plane) pairs that are missing
 #define C2C_CORR_G4 32
-template <int NQ>
-__global__ void __launch_bounds__(C2C_CORR_THREADS, 1)
+// THREADS = 256: two CTAs per SM (one CTA's barriers / staging run under the other's loads) when two corrections fit shared
+// memory; THREADS = 512: one CTA per SM
+template <int NQ, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 fiber_corr4_kernel(const uint8_t* __restrict__ mask, const LeadInfo lead, const float* __restrict__ Bmat,
                    float* __restrict__ part, long long P, int E, int R, int pitch, long long ppc, const int* done)
 {
@@ -212,19 +214,19 @@ fiber_corr4_kernel(const uint8_t* __restrict__ mask, const LeadInfo lead, const 
     float* Us = smem_f;                                              // [E][pitch]
     float* sW = smem_f + (size_t)E * pitch;                          // [G4][NQ]
     const int t = threadIdx.x;
-    for (int i = t; i < E * pitch; i += C2C_CORR_THREADS) Us[i] = 0.0f;
+    for (int i = t; i < E * pitch; i += THREADS) Us[i] = 0.0f;
     const long long p_begin = (long long)blockIdx.x * ppc;
     const long long p_end = p_begin + ppc < P ? p_begin + ppc : P;
     const int n4 = E >> 2;
     for (long long pg = p_begin; pg < p_end; pg += C2C_CORR_G4) {
         __syncthreads();
-        for (int i = t; i < C2C_CORR_G4 * NQ; i += C2C_CORR_THREADS) {
+        for (int i = t; i < C2C_CORR_G4 * NQ; i += THREADS) {
             const int gq = i / NQ, q = i - gq * NQ;
             const long long p = pg + gq;
             sW[i] = (p < p_end && q < R) ? lead_weight32((unsigned)p, lead, NQ, q) : 0.0f;
         }
         __syncthreads();
-        for (int c = t; c < n4; c += C2C_CORR_THREADS) {
+        for (int c = t; c < n4; c += THREADS) {
             unsigned zm[4] = {0u, 0u, 0u, 0u};                       // per owned position: bit g set <=> missing in plane pg + g
             {
                 unsigned m[C2C_CORR_G4];
@@ -279,7 +281,7 @@ fiber_corr4_kernel(const uint8_t* __restrict__ mask, const LeadInfo lead, const 
     }
     __syncthreads();
     float* out = part + (size_t)blockIdx.x * E * NQ;
-    for (int i = t; i < E * NQ; i += C2C_CORR_THREADS) {
+    for (int i = t; i < E * NQ; i += THREADS) {
         const int e = i / NQ, q = i - e * NQ;
         out[i] = Us[(size_t)e * pitch + q];
     }
@@ -422,7 +424,9 @@ cudaError_t c2c_launch_fiber_corr(const uint8_t* mask, const LeadInfo& lead, con
     if (E >= (1LL << 31)) return cudaErrorNotSupported;
     const size_t smem = c2c_fiber_corr_smem(E, ldr);
     if (smem > C2C_CORR_SMEM_MAX) return cudaErrorNotSupported;
-    long long grid = max_parts;
+    const bool two_per_sm = (E & 3) == 0 && ((uintptr_t)mask & 3) == 0 && smem <= 100 * 1024;
+    long long grid = two_per_sm ? max_parts : max_parts / 2;
+    if (grid < 1) grid = 1;
     if (grid > P) grid = P;
     const long long ppc = (P + grid - 1) / grid;
     grid = (P + ppc - 1) / ppc;
@@ -436,21 +440,23 @@ cudaError_t c2c_launch_fiber_corr(const uint8_t* mask, const LeadInfo& lead, con
         }                                                                                                                \
         fiber_corr_kernel<N><<<(unsigned)grid, C2C_CORR_THREADS, smem, st>>>(mask, lead, Bmat, part, P, (int)E, R, pitch, ppc, done); \
     } while (0)
-#define FC4_CALL(N)                                                                                                      \
+#define FC4_CALL_T(N, T)                                                                                                 \
     do {                                                                                                                 \
         if (smem > 48 * 1024) {                                                                                          \
-            const cudaError_t ea = cudaFuncSetAttribute(fiber_corr4_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            const cudaError_t ea = cudaFuncSetAttribute(fiber_corr4_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                         (int)C2C_CORR_SMEM_MAX);                                         \
             if (ea != cudaSuccess) return ea;                                                                            \
         }                                                                                                                \
-        fiber_corr4_kernel<N><<<(unsigned)grid, C2C_CORR_THREADS, smem, st>>>(mask, lead, Bmat, part, P, (int)E, R, pitch, ppc, done); \
+        fiber_corr4_kernel<N, T><<<(unsigned)grid, T, smem, st>>>(mask, lead, Bmat, part, P, (int)E, R, pitch, ppc, done); \
     } while (0)
+#define FC4_CALL(N) do { if (two_per_sm) FC4_CALL_T(N, 256); else FC4_CALL_T(N, 512); } while (0)
     if ((E & 3) == 0 && ((uintptr_t)mask & 3) == 0) {
         C2C_CORR_DISPATCH(FC4_CALL)
     } else {
         C2C_CORR_DISPATCH(FC_CALL)
     }
 #undef FC4_CALL
+#undef FC4_CALL_T
 #undef FC_CALL
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

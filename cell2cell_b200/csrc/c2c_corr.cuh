@@ -3,7 +3,7 @@
 #include "c2c_common.cuh"
 
 #define C2C_CORR_SMEM_MAX (200 * 1024)
-#define C2C_CORR_MAX_PARTS 160           // CTAs (= partials) of fiber_corr
+#define C2C_CORR_MAX_PARTS 320           // CTAs (= partials) of fiber_corr
 
 // *flag |= 1 if some entry with mask == 0 holds a non-zero value (the dense + correction form needs zeros there)
 cudaError_t c2c_launch_masked_nonzero(const float* X, const uint8_t* mask, long long n, int* flag, int nsm, cudaStream_t st);
