@@ -49,8 +49,11 @@ def build(force=False, verbose=False, jobs=None, extra_flags=(), out_path=None):
     lib_path = out_path or LIB_PATH
     tag = _digest(extra_flags)
     obj_dir = os.path.join(ROOT, "build", tag)
-    stamp = os.path.join(obj_dir, "linked")
-    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == tag + lib_path:
+    # the tag of the sources the library at `lib_path` was linked from is kept beside it: a stamp inside the object directory
+    # alone would call a library current after the sources went back to an earlier state (the objects of that state are still
+    # cached, but the library on disk is the later build)
+    stamp = lib_path + ".tag"
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == tag:
         return lib_path
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
@@ -77,7 +80,7 @@ def build(force=False, verbose=False, jobs=None, extra_flags=(), out_path=None):
         raise RuntimeError("link failed:\n%s" % res.stderr[-4000:])
     os.replace(lib_path + ".tmp", lib_path)
     with open(stamp, "w") as fh:
-        fh.write(tag + lib_path)
+        fh.write(tag)
     return lib_path
 
 
