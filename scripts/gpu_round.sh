@@ -16,6 +16,7 @@ python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"; cat $
 python bench.py --impl reference --steps 2 --warmup 0 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; echo "ref exit $?"; cat $OUT/bench_ref.json
 python scripts/kbench.py --ranks 1 2 4 5 8 10 12 13 16 20 24 25 28 30 32 --iters 50 > $OUT/kbench_ranks.jsonl 2> $OUT/kbench_ranks.err; echo "kbench exit $?"
 cat $OUT/kbench_ranks.jsonl
+(python scripts/kbench.py --masked --ranks 10 --iters 50; python scripts/kbench.py --masked --structured --ranks 10 --iters 50; python scripts/kbench.py --masked --structured --shape 13 1900 17 17 --ranks 10 --iters 100) > $OUT/kbench_masked.jsonl 2> $OUT/kbench_masked.err; echo "kbench masked exit $?"
 kill $SMI
 if [ "${NCU:-1}" = "1" ]; then
 python bench.py --steps 2 --warmup 3 --iters 20 --no-cpu --no-elbow > $OUT/bench_short.json 2> $OUT/bench_short.err &&
