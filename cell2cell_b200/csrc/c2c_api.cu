@@ -409,7 +409,9 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     w.Bmat = (float*)take(masked ? (size_t)g.E * ldr * sizeof(float) : 0);
     // ranks beyond one chunk: the masked passes need the full-rank reconstruction, so the imputed tensor is materialised
     w.Xh = (float*)take((masked && g.nchunk > 1) ? (size_t)g.P * g.E * sizeof(float) : 0);
-    const bool corr_ws = masked && g.nchunk == 1;
+    // only for shapes the dense + correction form takes (ncp_run_impl makes the same test): otherwise 320 partials of E x ldr
+    // floats would be reserved for nothing (2.6 GB at a 255 x 255 plane)
+    const bool corr_ws = masked && g.nchunk == 1 && rank <= 32 && c2c_fiber_corr_smem(g.E, ldr) <= C2C_CORR_SMEM_MAX;
     w.Tw = (float*)take(corr_ws ? (size_t)g.P * ldr * sizeof(float) : 0);
     w.Uw = (float*)take(corr_ws ? (size_t)g.E * ldr * sizeof(float) : 0);
     w.cpart = (float*)take(corr_ws ? (size_t)C2C_CORR_MAX_PARTS * g.E * ldr * sizeof(float) : 0);
