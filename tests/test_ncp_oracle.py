@@ -101,3 +101,33 @@ def test_parafac_als_recovers_low_rank_and_gram_error_matches_direct():
     cpm, errm, n_it = o.parafac(xn * m, 3, init="random", random_state=2, n_iter_max=60, tol=1e-9, mask=m, return_iters=True)
     assert n_it == len(errm) <= 60
     assert o.masked_norm_error(xn * m, cpm, m) < 2.0 * direct + 1e-3
+
+
+def test_masked_mttkrp_is_dense_pass_plus_missing_entry_correction():
+    """The identity behind the masked device path (cell2cell_b200/csrc/c2c_corr.cu): with X zero at its missing entries,
+    MTTKRP(X*m + rec*(1-m)) = MTTKRP(X) + the contraction of the re-imputed entries alone, where the dense parts T / U do
+    not depend on the factors of their own side (one pass serves all leading modes, one both trailing modes)."""
+    rs = np.random.RandomState(4)
+    shape, rank = (4, 7, 5, 6), 3
+    x, _ = lowrank(shape, 3, seed=2, noise=0.05)
+    m = (rs.rand(*shape) > 0.25).astype(float)
+    m[1, :, 2, :] = 0
+    m[1, :, :, 2] = 0
+    m[0, 3] = 0
+    xz = x * m
+    fs = [rs.random_sample((s, rank)) for s in shape]
+    rec = o.cp_to_tensor(None, fs)
+    xhat = xz * m + rec * (1 - m)
+    P, E = shape[0] * shape[1], shape[2] * shape[3]
+    W = (fs[0][:, None, :] * fs[1][None, :, :]).reshape(P, rank)            # Khatri-Rao rows of the leading factors
+    B = (fs[2][:, None, :] * fs[3][None, :, :]).reshape(E, rank)            # ... of the trailing factors
+    miss = (1 - m).reshape(P, E)
+    recm = (W @ B.T) * miss                                                 # the re-imputed entries alone
+    T = xz.reshape(P, E) @ B + recm @ B                                     # plane contraction + correction
+    U = xz.reshape(P, E).T @ W + recm.T @ W                                 # fiber contraction + correction
+    T4, U4 = T.reshape(shape[0], shape[1], rank), U.reshape(shape[2], shape[3], rank)
+    want = [o.mttkrp(xhat, None, fs, mode) for mode in range(4)]
+    np.testing.assert_allclose(np.einsum("abr,br->ar", T4, fs[1]), want[0], rtol=1e-12)
+    np.testing.assert_allclose(np.einsum("abr,ar->br", T4, fs[0]), want[1], rtol=1e-12)
+    np.testing.assert_allclose(np.einsum("svr,vr->sr", U4, fs[3]), want[2], rtol=1e-12)
+    np.testing.assert_allclose(np.einsum("svr,sr->vr", U4, fs[2]), want[3], rtol=1e-12)
