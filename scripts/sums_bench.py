@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     args = ap.parse_args()
     shape = tuple(args.shape)
+    assert len(shape) == 4, "the fp64 check below is written for 4-way tensors"
     g = torch.Generator(device="cuda").manual_seed(0)
     X = torch.rand(shape, generator=g, device="cuda")
     for R in args.ranks:
