@@ -74,11 +74,19 @@ class NumpyOps:
         return torch.as_tensor(np.einsum("svr,sr->vr", u, factors[-2].numpy()))
 
     def gram_hadamard(self, factors, shape, skip, changed=None, out=None):
+        """Like the device op, the per-factor Grams are cached per shape and only the Gram of ``changed`` is recomputed -- so a
+        caller that names the wrong factor gets wrong numbers here too."""
         R = factors[0].shape[1]
+        key = tuple(int(s) for s in shape)
+        if not hasattr(self, "_grams"):
+            self._grams = {}
+        if changed is None or key not in self._grams:
+            self._grams[key] = [f.numpy().T @ f.numpy() for f in factors]
+        else:
+            self._grams[key][changed] = factors[changed].numpy().T @ factors[changed].numpy()
         g = np.ones((R, R))
         allg = np.ones((R, R))
-        for k, f in enumerate(factors):
-            gk = f.numpy().T @ f.numpy()
+        for k, gk in enumerate(self._grams[key]):
             allg = allg * gk
             if k != skip:
                 g = g * gk
