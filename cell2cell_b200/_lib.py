@@ -57,6 +57,13 @@ SIGNATURES = {
                          _p, _sz, _p]),
     "c2c_ncp_run_batched": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _c.POINTER(_i), _i, _i, _c.c_double, _i, _p, _p, _p, _i,
                                  _p, _sz, _p]),
+    "c2c_mask_plan_header_bytes": (_sz, [_i, _c.POINTER(_i64)]),
+    "c2c_mask_plan_scan": (_i, [_p, _p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p]),
+    "c2c_mask_plan_fill": (_i, [_p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p, _sz, _p]),
+    "c2c_ncp_run_planned": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _c.c_double, _i, _p, _p, _p, _i,
+                                 _p, _sz, _p, _sz, _p, _sz, _c.POINTER(_i64), _p]),
+    "c2c_masked_contract_planned": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _p, _p, _sz, _p, _sz, _p, _sz,
+                                         _c.POINTER(_i64), _p]),
 }
 
 _lock = threading.Lock()
@@ -84,4 +91,6 @@ def lib():
 def check(rc, what):
     if rc != 0:
         msg = lib().c2c_last_error().decode("utf-8", "replace")
-        raise C2CError("%s failed (%d): %s" % (what, rc, msg))
+        err = C2CError("%s failed (%d): %s" % (what, rc, msg))
+        err.code = int(rc)
+        raise err

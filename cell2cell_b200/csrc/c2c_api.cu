@@ -19,6 +19,7 @@
 #include "c2c_update.cuh"
 #include "c2c_sums.cuh"
 #include "c2c_corr.cuh"
+#include "c2c_plan.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -385,7 +386,9 @@ static int make_geo(Geo& g, int ndim, const int64_t* shape, int rank)
 // ---------------------------------------------------------------------------------------------------------------------
 struct Ws {
     float* T; float* part; float* U; float* M; float* G; float* Bmat; float* Xh; float* W;
-    float* Tw; float* Uw; float* cpart;      // masked runs, dense pass + missing-entry correction (c2c_corr.cu)
+    float* Tw; float* Uw; float* cpart;      // masked runs, dense pass + missing-entry correction (c2c_corr.cu, c2c_plan.cu)
+    int cparts;                              // partial U buffers reserved in cpart
+    float* Dmat; float* Ymat; float* Ypart;  // restricted Grams of the mask plan's separable model (c2c_plan.cu)
     double* S; double* gram_part; double* iprod_part; double* normX2; double* sums_part; double* scratch_d;
     int* flags;
     size_t bytes;
@@ -411,10 +414,23 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     w.Xh = (float*)take((masked && g.nchunk > 1) ? (size_t)g.P * g.E * sizeof(float) : 0);
     // only for shapes the dense + correction form takes (ncp_run_impl makes the same test): otherwise 320 partials of E x ldr
     // floats would be reserved for nothing (2.6 GB at a 255 x 255 plane)
-    const bool corr_ws = masked && g.nchunk == 1 && rank <= 32 && c2c_fiber_corr_smem(g.E, ldr) <= C2C_CORR_SMEM_MAX;
+    const bool scan_ok = c2c_fiber_corr_smem(g.E, ldr) <= C2C_CORR_SMEM_MAX;          // mask-scanning corrections (c2c_corr.cu)
+    const bool plan_ok = g.E <= C2C_PLAN_MAX_E;                                          // mask-plan corrections (c2c_plan.cu)
+    const bool corr_ws = masked && g.nchunk == 1 && rank <= 32 && (scan_ok || plan_ok);
     w.Tw = (float*)take(corr_ws ? (size_t)g.P * ldr * sizeof(float) : 0);
     w.Uw = (float*)take(corr_ws ? (size_t)g.E * ldr * sizeof(float) : 0);
-    w.cpart = (float*)take(corr_ws ? (size_t)C2C_CORR_MAX_PARTS * g.E * ldr * sizeof(float) : 0);
+    // partial U corrections: up to C2C_CORR_MAX_PARTS, fewer when a partial is large (at most ~256 MB in all)
+    long long cparts = (256LL << 20) / (g.E * ldr * (long long)sizeof(float));
+    if (cparts > C2C_CORR_MAX_PARTS) cparts = C2C_CORR_MAX_PARTS;
+    if (cparts < 4) cparts = 4;
+    if (scan_ok) cparts = C2C_CORR_MAX_PARTS;
+    w.cparts = corr_ws ? (int)cparts : 0;
+    w.cpart = (float*)take(corr_ws ? (size_t)cparts * g.E * ldr * sizeof(float) : 0);
+    const bool plan_ws = corr_ws && plan_ok;
+    const int C0 = (int)g.shape[0];
+    w.Dmat = (float*)take(plan_ws ? (size_t)(C0 + 1) * ldr * ldr * sizeof(float) : 0);
+    w.Ymat = (float*)take(plan_ws ? (size_t)(C0 + 1) * ldr * ldr * sizeof(float) : 0);
+    w.Ypart = (float*)take(plan_ws ? (size_t)C0 * c2c_lead_ctx_parts(C0, sm_count()) * 2 * ldr * ldr * sizeof(float) : 0);
     w.S = (double*)take((size_t)2 * g.ndim * ldr * ldr * sizeof(double));        // two banks (c2c_update.cuh)
     const long long nblk_g = nblk > 512 ? nblk : 512;             // lead_update runs at most 2 CTAs per SM, capped at 512
     w.gram_part = (double*)take((size_t)nblk_g * ldr * ldr * sizeof(double));
@@ -1053,6 +1069,8 @@ struct RunCtx {
     int* run_flags; int* run_iters;
     bool mma_zero;             // plane_mma / fiber_mma: T is kept cleared by the fiber pass
     bool corr;                 // masked run as unmasked dense passes + missing-entry corrections (c2c_corr.cu)
+    bool plan;                 // ... with the corrections taken from a mask plan (c2c_plan.cu): Gram form + residual lists
+    PlanView pv; long long n_resid; bool model_missing;
 };
 
 static int update_mode(const RunCtx& c, int mode, bool last)
@@ -1195,7 +1213,7 @@ static int enqueue_iteration_corr(const RunCtx& c)
         if (j == 1 && (rc = bmat()) != 0) return rc;                 // the first trailing factor has just changed
         LeadInfo li; fill_lead(li, g, A);
         int nparts = 2 * sm_count();
-        if (nparts > C2C_CORR_MAX_PARTS) nparts = C2C_CORR_MAX_PARTS;
+        if (nparts > c.w.cparts) nparts = c.w.cparts;
         const cudaError_t e = c2c_launch_fiber_corr(c.mask, li, c.w.Bmat, c.w.U, c.w.Uw, c.w.cpart, nparts, g.P, g.E, c.R, c.ldr,
                                                     done, c.st);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_corr launch");
@@ -1205,8 +1223,88 @@ static int enqueue_iteration_corr(const RunCtx& c)
     return 0;
 }
 
+// Masked iteration with a mask plan (c2c_plan.cu): the two unmasked streaming passes, plus -- before every mode's fused update
+// -- the contraction of the reconstruction over the missing entries: restricted-Gram products for the separable part of the
+// mask (no pass over the mask), list kernels for the residual entries.  Every kernel is a programmatic dependent of its
+// predecessor.
+static int enqueue_iteration_plan(const RunCtx& c)
+{
+    const Geo& g = c.g; int rc;
+    const int* done = c.state + 1;
+    const float* const* A = (const float* const*)c.A;
+    const int nlead = g.ndim - 2, nsm = sm_count();
+    const bool lists = c.n_resid > 0, gram = c.model_missing;
+    PassOpts po = kPlainPass;
+    po.pdl = c.pdl;
+    RunCtx c2 = c;
+    c2.w.T = (gram || lists) ? c.w.Tw : c.w.T;
+    c2.w.U = (gram || lists) ? c.w.Uw : c.w.U;
+    cudaError_t e;
+    {
+        ContractArgs a = base_args(g, c.X, nullptr, A, c.ldr, c.R, done);
+        if ((rc = launch_plane(g, a, false, c.w.T, c.st, po)) != 0) return rc;
+    }
+    if (gram) {
+        e = c2c_launch_trail_ctx_gram(c.pv, A[g.ndim - 2], A[g.ndim - 1], c.R, c.ldr, c.w.Dmat, done, c.st, c.pdl);
+        if (e != cudaSuccess) return cuda_fail(e, "trail_ctx_gram launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (lists) {
+        const long long nB = g.E * c.ldr;
+        e = c2c_launch_ex(bmat_kernel, dim3((unsigned)((nB + 255) / 256)), dim3(256), 0, c.st, 0, A[g.ndim - 2], A[g.ndim - 1], g.I2, g.I3,
+                          c.ldr, c.w.Bmat, done);
+        if (e != cudaSuccess) return cuda_fail(e, "bmat launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    for (int mode = 0; mode < nlead; ++mode) {
+        LeadInfo li; fill_lead(li, g, A);
+        const float* src = c.w.T;
+        if (gram) {
+            e = c2c_launch_plane_corr_gram(c.pv, li, c.w.Dmat, c.w.T, c.w.Tw, c.R, c.ldr, done, nsm, c.st, c.pdl);
+            if (e != cudaSuccess) return cuda_fail(e, "plane_corr_gram launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            src = c.w.Tw;
+        }
+        if (lists) {
+            e = c2c_launch_plane_corr_list(c.pv, li, c.w.Bmat, src, c.w.Tw, c.R, c.ldr, done, nsm, c.st, c.pdl);
+            if (e != cudaSuccess) return cuda_fail(e, "plane_corr_list launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if ((rc = launch_lead_update(c2, mode)) != 0) return rc;
+    }
+    {
+        ContractArgs a = base_args(g, c.X, nullptr, A, c.ldr, c.R, done);
+        if ((rc = launch_fiber(g, a, false, c.w, c.st, po)) != 0) return rc;
+    }
+    if (gram) {
+        LeadInfo li; fill_lead(li, g, A);
+        e = c2c_launch_lead_ctx_gram(c.pv, li, c.R, c.ldr, c.w.Ypart, c.w.Ymat, done, nsm, c.st, c.pdl);
+        if (e != cudaSuccess) return cuda_fail(e, "lead_ctx_gram launch");
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+    }
+    for (int j = 0; j < 2; ++j) {
+        const float* src = c.w.U;
+        if (gram) {
+            e = c2c_launch_fiber_corr_gram(c.pv, A[g.ndim - 2], A[g.ndim - 1], c.w.Ymat, c.w.U, c.w.Uw, c.R, c.ldr, done, c.st, c.pdl);
+            if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_gram launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            src = c.w.Uw;
+        }
+        if (lists) {
+            LeadInfo li; fill_lead(li, g, A);
+            e = c2c_launch_fiber_corr_list(c.pv, li, A[g.ndim - 2], A[g.ndim - 1], src, c.w.Uw, c.w.cpart, c.w.cparts, c.R, c.ldr, done,
+                                           nsm, c.st, c.pdl);
+            if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_list launch");
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+        }
+        if ((rc = launch_trail_update(c2, j, j + 1)) != 0) return rc;
+    }
+    return 0;
+}
+
 static int enqueue_iteration(const RunCtx& c)
 {
+    if (c.plan) return enqueue_iteration_plan(c);
     if (c.corr) return enqueue_iteration_corr(c);
     const Geo& g = c.g; int rc;
     const int* done = c.state + 1;
@@ -1234,12 +1332,24 @@ static int enqueue_iteration(const RunCtx& c)
     return 0;
 }
 
+// a caller-built mask plan (c2c_mask_plan_scan / _fill)
+struct PlanRef { const void* header; size_t header_bytes; const void* lists; size_t lists_bytes; const int64_t* info; };
+
+static int plan_dims(const Geo& g, long long* P, int* E, int* I2, int* I3, int* C0)
+{
+    if (g.E > C2C_PLAN_MAX_E) return fail(-50, "mask plan: in-plane size %lld exceeds %d", g.E, C2C_PLAN_MAX_E);
+    if (g.P >= (1LL << 31)) return fail(-50, "mask plan: too many planes");
+    *P = g.P; *E = (int)g.E; *I2 = g.I2; *I3 = g.I3; *C0 = (int)g.shape[0];
+    return 0;
+}
+
 static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
                         int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
                         double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream,
-                        const int* run_ranks, int nruns)
+                        const int* run_ranks, int nruns, const PlanRef* plan = nullptr)
 {
     RunCtx c; int rc;
+    const bool masked_ws = mask != nullptr;
     if (!shape) return fail(-1, "shape is NULL");
     if ((rc = make_geo(c.g, ndim, shape, rank)) != 0) return rc;
     if ((rc = check_common(X, (const float* const*)A, ndim, ldr, rank)) != 0) return rc;
@@ -1249,7 +1359,25 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     if (n_iter_max < 0) return fail(-23, "n_iter_max < 0");
     if (!errors || !state) return fail(-24, "errors / state is NULL");
     if (((uintptr_t)X & 15) != 0) return fail(-25, "X must be 16-byte aligned");
-    if ((rc = get_ws(c.w, c.g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    if ((rc = get_ws(c.w, c.g, rank, masked_ws, ws, ws_bytes)) != 0) return rc;
+    c.plan = false; c.n_resid = 0; c.model_missing = false;
+    if (plan != nullptr) {
+        if (!mask) return fail(-51, "mask plan given without a mask");
+        if (!plan->header || !plan->info) return fail(-51, "mask plan: header / info is NULL");
+        long long P; int E, I2, I3, C0;
+        if ((rc = plan_dims(c.g, &P, &E, &I2, &I3, &C0)) != 0) return rc;
+        if (plan->header_bytes < c2c_plan_header_bytes(P, E, I2, I3, C0)) return fail(-51, "mask plan: header buffer too small");
+        if (plan->info[2] != 0) return fail(-50, "mask plan: the tensor holds non-zero values under zero mask bytes");
+        if (plan->info[5] != 0) return fail(-50, "mask plan: too many residual entries");
+        if (algo != C2C_ALGO_MU || c.g.nchunk != 1 || rank > 32) return fail(-50, "mask plan: multiplicative updates at rank <= 32 only");
+        if (plan->info[1] > 0 && (!plan->lists || plan->lists_bytes < c2c_plan_lists_bytes(plan->info[1], plan->info[3])))
+            return fail(-51, "mask plan: lists buffer too small");
+        if (plan->info[0] == 0) mask = nullptr;                        // nothing is missing: the unmasked iteration
+        else {
+            c.plan = true; c.n_resid = plan->info[1]; c.model_missing = plan->info[4] != 0;
+            c2c_plan_view(c.pv, P, E, I2, I3, C0, const_cast<void*>(plan->header), const_cast<void*>(plan->lists), c.n_resid);
+        }
+    }
     c.X = X; c.mask = mask; c.A = A; c.ldr = ldr; c.R = rank; c.algo = algo; c.n_iter_max = n_iter_max; c.tol = tol;
     c.cvg = cvg_criterion; c.errors = errors; c.state = state; c.st = (cudaStream_t)stream;
     c.eps = 1.1920928955078125e-07f;      // finfo(float32).eps: tensorly clips numerator and denominator at the dtype's eps
@@ -1273,7 +1401,8 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     // of a CTA in shared memory, and zeros at the missing entries of X (checked once here; cell2cell's tensors have them:
     // nan_to_num of the NaN the mask was derived from, tensor.py:842-847, 933-946)
     c.corr = false;
-    if (mask != nullptr && algo == C2C_ALGO_MU && g.nchunk == 1 && rank <= 32 && fused_updates(c) &&
+    if (c.plan && !fused_updates(c)) return fail(-50, "mask plan: shape outside the fused update kernels");
+    if (!c.plan && mask != nullptr && algo == C2C_ALGO_MU && g.nchunk == 1 && rank <= 32 && fused_updates(c) &&
         c2c_fiber_corr_smem(g.E, ldr) <= C2C_CORR_SMEM_MAX && !env_int("C2C_B200_NO_MASK_CORR", 0)) {
         int host_flag = 1;
         const cudaError_t e = c2c_launch_masked_nonzero(X, mask, g.P * g.E, c.w.flags + 2, sm_count(), st);
@@ -1306,7 +1435,7 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     // The fused unmasked iteration is a chain of kernels only: they are launched as programmatic dependents (every kernel
     // waits for its predecessor before it touches that predecessor's results, so a streaming pass fills its ring while the
     // update kernel before it is still running).  On the tensor-pipe path T is cleared once here and then by every fiber pass.
-    c.pdl = (use_pdl() && fused && mask == nullptr) ? 1 : 0;
+    c.pdl = (use_pdl() && fused && (mask == nullptr || c.plan)) ? 1 : 0;
     c.mma_zero = g.mma_ok && g.mma_fiber_ok && mask == nullptr;
     if (c.mma_zero) CK(cudaMemsetAsync(c.w.T, 0, (size_t)g.P * ldr * sizeof(float), st), "memset T");
 
@@ -1388,6 +1517,145 @@ extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shap
     if (total < 1 || total > 32) return fail(-26, "batched runs: the run ranks must add up to 1..32, got %lld", total);
     return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, (int)total, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
                         normX2, errors, state, check_every, ws, ws_bytes, stream, run_ranks, nruns);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mask plan (c2c_plan.cu): built once per (tensor, mask), used by every masked factorization of that tensor
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" size_t c2c_mask_plan_header_bytes(int ndim, const int64_t* shape)
+{
+    Geo g;
+    if (!shape || make_geo(g, ndim, shape, 1) != 0) return 0;
+    long long P; int E, I2, I3, C0;
+    if (plan_dims(g, &P, &E, &I2, &I3, &C0) != 0) return 0;
+    return c2c_plan_header_bytes(P, E, I2, I3, C0);
+}
+
+extern "C" int c2c_mask_plan_scan(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, void* header,
+                                  size_t header_bytes, int64_t* info, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, 1)) != 0) return rc;
+    if (!mask || !header || !info) return fail(-51, "mask / header / info is NULL");
+    long long P; int E, I2, I3, C0;
+    if ((rc = plan_dims(g, &P, &E, &I2, &I3, &C0)) != 0) return rc;
+    if (header_bytes < c2c_plan_header_bytes(P, E, I2, I3, C0)) return fail(-51, "mask plan: header buffer too small");
+    if (((uintptr_t)header & 255) != 0) return fail(-6, "mask plan: header must be 256-byte aligned");
+    PlanView v;
+    c2c_plan_view(v, P, E, I2, I3, C0, header, nullptr, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cudaError_t e = c2c_plan_scan(X, mask, v, sm_count(), st);
+    if (e != cudaSuccess) return cuda_fail(e, "mask plan scan");
+    g_launches.fetch_add(4, std::memory_order_relaxed);
+    unsigned long long cnt[C2C_PLAN_NCOUNTERS];
+    CK(cudaMemcpyAsync(cnt, v.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st), "copy plan counters");
+    CK(cudaStreamSynchronize(st), "mask plan scan");
+    for (int i = 0; i < 6; ++i) info[i] = (int64_t)cnt[i];
+    info[6] = (int64_t)c2c_plan_lists_bytes((long long)cnt[1], (long long)cnt[3]);
+    info[7] = C2C_VERSION;
+    return 0;
+}
+
+extern "C" int c2c_mask_plan_fill(const uint8_t* mask, int ndim, const int64_t* shape, const void* header, size_t header_bytes,
+                                  const int64_t* info, void* lists, size_t lists_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, 1)) != 0) return rc;
+    if (!mask || !header || !info) return fail(-51, "mask / header / info is NULL");
+    long long P; int E, I2, I3, C0;
+    if ((rc = plan_dims(g, &P, &E, &I2, &I3, &C0)) != 0) return rc;
+    if (header_bytes < c2c_plan_header_bytes(P, E, I2, I3, C0)) return fail(-51, "mask plan: header buffer too small");
+    if (info[5] != 0) return fail(-50, "mask plan: too many residual entries");
+    if (info[1] == 0) return 0;                                        // no residual entries: nothing to list
+    if (!lists || lists_bytes < c2c_plan_lists_bytes(info[1], info[3])) return fail(-51, "mask plan: lists buffer too small");
+    if (((uintptr_t)lists & 255) != 0) return fail(-6, "mask plan: lists must be 256-byte aligned");
+    PlanView v;
+    c2c_plan_view(v, P, E, I2, I3, C0, const_cast<void*>(header), lists, info[1]);
+    const cudaError_t e = c2c_plan_fill(mask, v, sm_count(), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "mask plan fill");
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int c2c_ncp_run_planned(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
+                                   int rank, int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors,
+                                   int* state, int check_every, void* ws, size_t ws_bytes, const void* header, size_t header_bytes,
+                                   const void* lists, size_t lists_bytes, const int64_t* info, void* stream)
+{
+    PlanRef pr = {header, header_bytes, lists, lists_bytes, info};
+    return ncp_run_impl(X, mask, ndim, shape, A, ldr, rank, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion, normX2, errors, state,
+                        check_every, ws, ws_bytes, stream, nullptr, 1, &pr);
+}
+
+// T (which = 0) or U (which = 1) of the IMPUTED tensor -- X at the observed entries, the reconstruction of the given factors at
+// the missing ones -- as the unmasked pass over X plus the plan's corrections
+extern "C" int c2c_masked_contract_planned(const float* X, int ndim, const int64_t* shape, const float* const* A, int ldr, int rank,
+                                           int which, float* out, void* ws, size_t ws_bytes, const void* header, size_t header_bytes,
+                                           const void* lists, size_t lists_bytes, const int64_t* info, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!out || !header || !info) return fail(-14, "out / header / info is NULL");
+    if (which != 0 && which != 1) return fail(-13, "which must be 0 (plane) or 1 (fiber)");
+    if (g.nchunk != 1 || rank > 32) return fail(-50, "mask plan: rank <= 32 only");
+    long long P; int E, I2, I3, C0;
+    if ((rc = plan_dims(g, &P, &E, &I2, &I3, &C0)) != 0) return rc;
+    if (header_bytes < c2c_plan_header_bytes(P, E, I2, I3, C0)) return fail(-51, "mask plan: header buffer too small");
+    if (info[2] != 0 || info[5] != 0) return fail(-50, "mask plan not usable for this tensor");
+    if (info[1] > 0 && (!lists || lists_bytes < c2c_plan_lists_bytes(info[1], info[3]))) return fail(-51, "mask plan: lists buffer too small");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, 1, ws, ws_bytes)) != 0) return rc;
+    PlanView v;
+    c2c_plan_view(v, P, E, I2, I3, C0, const_cast<void*>(header), const_cast<void*>(lists), info[1]);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nsm = sm_count();
+    const bool gram = info[4] != 0, lst = info[1] > 0;
+    ContractArgs a = base_args(g, X, nullptr, A, ldr, rank, nullptr);
+    LeadInfo li; fill_lead(li, g, A);
+    cudaError_t e;
+    if (which == 0) {
+        if ((rc = launch_plane(g, a, false, w.T, st)) != 0) return rc;
+        const float* src = w.T;
+        if (gram) {
+            e = c2c_launch_trail_ctx_gram(v, A[ndim - 2], A[ndim - 1], rank, ldr, w.Dmat, nullptr, st, 0);
+            if (e == cudaSuccess) e = c2c_launch_plane_corr_gram(v, li, w.Dmat, w.T, w.Tw, rank, ldr, nullptr, nsm, st, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "plane_corr_gram launch");
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            src = w.Tw;
+        }
+        if (lst) {
+            const long long nB = g.E * ldr;
+            bmat_kernel<<<(int)((nB + 255) / 256), 256, 0, st>>>(A[ndim - 2], A[ndim - 1], g.I2, g.I3, ldr, w.Bmat, nullptr);
+            CKL("bmat launch");
+            e = c2c_launch_plane_corr_list(v, li, w.Bmat, src, w.Tw, rank, ldr, nullptr, nsm, st, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "plane_corr_list launch");
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            src = w.Tw;
+        }
+        CK(cudaMemcpyAsync(out, src, (size_t)g.P * ldr * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy T");
+    } else {
+        if ((rc = launch_fiber(g, a, false, w, st)) != 0) return rc;
+        const float* src = w.U;
+        if (gram) {
+            e = c2c_launch_lead_ctx_gram(v, li, rank, ldr, w.Ypart, w.Ymat, nullptr, nsm, st, 0);
+            if (e == cudaSuccess) e = c2c_launch_fiber_corr_gram(v, A[ndim - 2], A[ndim - 1], w.Ymat, w.U, w.Uw, rank, ldr, nullptr, st, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_gram launch");
+            g_launches.fetch_add(3, std::memory_order_relaxed);
+            src = w.Uw;
+        }
+        if (lst) {
+            e = c2c_launch_fiber_corr_list(v, li, A[ndim - 2], A[ndim - 1], src, w.Uw, w.cpart, w.cparts, rank, ldr, nullptr, nsm, st, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_list launch");
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            src = w.Uw;
+        }
+        CK(cudaMemcpyAsync(out, src, (size_t)g.E * ldr * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy U");
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,761 @@
+// Mask plan of the masked factorization: see c2c_plan.cuh for the model.  Three groups of kernels:
+//   plan_*            built once per (tensor, mask): separable model g / hs / hv, residual counts, offsets, the two lists
+//   *_ctx_gram, *_corr_gram   the contraction of the reconstruction over the model-missing set, as restricted Grams
+//   *_corr_list       the same contraction over the residual list (entries the separable model cannot express)
+// All of them are exact restatements of tensorly's imputation `tensor*mask + cp_to_tensor(cp, mask=1-mask)` followed by
+// unfolding_dot_khatri_rao (cell2cell/tensor/coupled_factorization.py:342-345): the same products, summed in another order.
+#include "c2c_plan.cuh"
+
+static inline size_t plan_align(size_t x) { return (x + 255) / 256 * 256; }
+
+size_t c2c_plan_header_bytes(long long P, int E, int I2, int I3, int C0)
+{
+    const long long nchunks = (P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK, ngroups = (E + 31) / 32;
+    return plan_align(C2C_PLAN_NCOUNTERS * sizeof(unsigned long long)) + plan_align((size_t)P) +
+           plan_align((size_t)C0 * I2 * sizeof(int)) + plan_align((size_t)C0 * I3 * sizeof(int)) +
+           plan_align((size_t)(P + 1) * sizeof(int)) + plan_align((size_t)(nchunks * ngroups + 1) * sizeof(int));
+}
+
+size_t c2c_plan_lists_bytes(long long n_resid, long long ell_rows)
+{
+    return plan_align((size_t)(n_resid > 0 ? n_resid : 1) * sizeof(uint16_t)) +
+           plan_align((size_t)(ell_rows > 0 ? ell_rows : 1) * 32 * sizeof(uint16_t));
+}
+
+void c2c_plan_view(PlanView& v, long long P, int E, int I2, int I3, int C0, void* header, void* lists, long long n_resid)
+{
+    v.P = P; v.E = E; v.I2 = I2; v.I3 = I3; v.C0 = C0; v.ppc0 = P / C0;
+    v.nchunks = (int)((P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK); v.ngroups = (E + 31) / 32;
+    char* h = (char*)header;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = h ? h + off : nullptr; off += plan_align(bytes); return p; };
+    v.counters = (unsigned long long*)take(C2C_PLAN_NCOUNTERS * sizeof(unsigned long long));
+    v.g = (uint8_t*)take((size_t)P);
+    v.hs = (int*)take((size_t)C0 * I2 * sizeof(int));
+    v.hv = (int*)take((size_t)C0 * I3 * sizeof(int));
+    v.row_off = (int*)take((size_t)(P + 1) * sizeof(int));
+    v.ell_off = (int*)take((size_t)((long long)v.nchunks * v.ngroups + 1) * sizeof(int));
+    char* l = (char*)lists;
+    v.csr_ent = (uint16_t*)l;
+    v.ell_ent = l ? (uint16_t*)(l + plan_align((size_t)(n_resid > 0 ? n_resid : 1) * sizeof(uint16_t))) : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase 1
+// ---------------------------------------------------------------------------------------------------------------------
+// a warp per plane: g[p], the row / column flags of its context (idempotent stores of 1), the missing count, the zero-fill check
+__global__ void __launch_bounds__(256)
+plan_fit_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, const PlanView v)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long nmiss = 0;
+    int bad = 0;
+    for (long long p = warp; p < v.P; p += nwarps) {
+        const int c = (int)(p / v.ppc0);
+        const uint8_t* mp = mask + (size_t)p * v.E;
+        const float* xp = X ? X + (size_t)p * v.E : nullptr;
+        bool any = false;
+        for (int v0 = 0; v0 < v.I3; v0 += 32) {
+            const int vv = v0 + lane;
+            bool colany = false;
+            for (int s = 0; s < v.I2; ++s) {
+                bool obs = false;
+                if (vv < v.I3) {
+                    const int e = s * v.I3 + vv;
+                    obs = __ldg(mp + e) != 0;
+                    if (!obs) {
+                        ++nmiss;
+                        if (xp && __ldg(xp + e) != 0.0f) bad = 1;
+                    }
+                }
+                const unsigned rowany = __ballot_sync(0xffffffffu, obs);
+                if (rowany && lane == 0 && v.hs[c * v.I2 + s] == 0) v.hs[c * v.I2 + s] = 1;
+                colany |= obs;
+            }
+            if (colany && v.hv[c * v.I3 + vv] == 0) v.hv[c * v.I3 + vv] = 1;
+            any |= colany;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) v.g[p] = any ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        if (nmiss) atomicAdd(v.counters + 0, nmiss);
+        if (bad) v.counters[2] = 1ull;
+    }
+}
+
+// residual = missing in the mask, observed by the model (the caller has checked g[p])
+__device__ __forceinline__ bool plan_resid_sv(const PlanView& v, const uint8_t* mp, int c, int s, int vv)
+{
+    return __ldg(mp + s * v.I3 + vv) == 0 && v.hs[c * v.I2 + s] != 0 && v.hv[c * v.I3 + vv] != 0;
+}
+
+// a warp per plane: residual entries of the plane -> row_off[p + 1]
+__global__ void __launch_bounds__(256)
+plan_count_rows_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = warp; p < v.P; p += nwarps) {
+        int n = 0;
+        if (v.g[p]) {
+            const int c = (int)(p / v.ppc0);
+            const uint8_t* mp = mask + (size_t)p * v.E;
+            for (int e = lane; e < v.E; e += 32) {
+                const int s = e / v.I3;
+                n += plan_resid_sv(v, mp, c, s, e - s * v.I3) ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        if (lane == 0) v.row_off[p + 1] = n;
+    }
+}
+
+// a warp per (chunk of 256 planes, group of 32 positions): depth of its ELL block = the longest list among the 32 positions
+__global__ void __launch_bounds__(256)
+plan_count_ell_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblocks = (long long)v.nchunks * v.ngroups;
+    for (long long b = warp; b < nblocks; b += nwarps) {
+        const int k = (int)(b / v.ngroups), gq = (int)(b - (long long)k * v.ngroups);
+        const int e = gq * 32 + lane;
+        int n = 0;
+        if (e < v.E) {
+            const int s = e / v.I3, vv = e - s * v.I3;
+            const long long p0 = (long long)k * C2C_PLAN_CHUNK;
+            const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
+            for (long long p = p0; p < p1; ++p)
+                if (v.g[p]) n += plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+        if (lane == 0) v.ell_off[b + 1] = n;
+    }
+}
+
+// in-place inclusive scan of a[1 .. n] (a[0] = 0) by one CTA of 1024 threads; returns the total to every thread
+__device__ unsigned long long plan_block_scan(int* a, long long n, unsigned long long* sh /*[1024]*/)
+{
+    const int t = threadIdx.x;
+    const long long seg = (n + 1023) / 1024;
+    const long long b = 1 + (long long)t * seg, e = (b + seg < n + 1) ? b + seg : n + 1;
+    unsigned long long s = 0;
+    for (long long i = b; i < e; ++i) s += (unsigned long long)a[i];
+    sh[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long x = t >= o ? sh[t - o] : 0ull;
+        __syncthreads();
+        sh[t] += x;
+        __syncthreads();
+    }
+    unsigned long long run = sh[t] - s;
+    for (long long i = b; i < e; ++i) { run += (unsigned long long)a[i]; a[i] = (int)run; }
+    const unsigned long long total = sh[1023];
+    __syncthreads();
+    if (t == 0) a[0] = 0;
+    return total;
+}
+
+__global__ void __launch_bounds__(1024)
+plan_scan_kernel(const PlanView v)
+{
+    __shared__ unsigned long long sh[1024];
+    const unsigned long long n_resid = plan_block_scan(v.row_off, v.P, sh);
+    const unsigned long long ell_rows = plan_block_scan(v.ell_off, (long long)v.nchunks * v.ngroups, sh);
+    int missing = 0;
+    for (long long i = threadIdx.x; i < v.P; i += 1024) missing |= v.g[i] == 0;
+    for (int i = threadIdx.x; i < v.C0 * v.I2; i += 1024) missing |= v.hs[i] == 0;
+    for (int i = threadIdx.x; i < v.C0 * v.I3; i += 1024) missing |= v.hv[i] == 0;
+    missing = __syncthreads_or(missing);
+    if (threadIdx.x == 0) {
+        v.counters[1] = n_resid;
+        v.counters[3] = ell_rows;
+        v.counters[4] = missing ? 1ull : 0ull;
+        v.counters[5] = (n_resid >= (1ull << 31) || ell_rows >= (1ull << 26)) ? 1ull : 0ull;
+    }
+}
+
+cudaError_t c2c_plan_scan(const float* X, const uint8_t* mask, const PlanView& v, int nsm, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(v.counters, 0, c2c_plan_header_bytes(v.P, v.E, v.I2, v.I3, v.C0), st);
+    if (e != cudaSuccess) return e;
+    long long grid = (v.P + 7) / 8;
+    if (grid > (long long)nsm * 16) grid = (long long)nsm * 16;
+    plan_fit_kernel<<<(unsigned)grid, 256, 0, st>>>(X, mask, v);
+    plan_count_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, v);
+    long long g2 = ((long long)v.nchunks * v.ngroups + 7) / 8;
+    if (g2 > (long long)nsm * 16) g2 = (long long)nsm * 16;
+    plan_count_ell_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(v);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase 2
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+plan_fill_csr_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = warp; p < v.P; p += nwarps) {
+        int off = v.row_off[p];
+        if (v.row_off[p + 1] == off) continue;
+        const int c = (int)(p / v.ppc0);
+        const uint8_t* mp = mask + (size_t)p * v.E;
+        for (int e0 = 0; e0 < v.E; e0 += 32) {
+            const int e = e0 + lane;
+            bool r = false;
+            if (e < v.E) { const int s = e / v.I3; r = plan_resid_sv(v, mp, c, s, e - s * v.I3); }
+            const unsigned bal = __ballot_sync(0xffffffffu, r);
+            if (r) v.csr_ent[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+            off += __popc(bal);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+plan_fill_ell_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblocks = (long long)v.nchunks * v.ngroups;
+    for (long long b = warp; b < nblocks; b += nwarps) {
+        const int base = v.ell_off[b], depth = v.ell_off[b + 1] - base;
+        if (depth == 0) continue;
+        const int k = (int)(b / v.ngroups), gq = (int)(b - (long long)k * v.ngroups);
+        const int e = gq * 32 + lane;
+        int n = 0;
+        if (e < v.E) {
+            const int s = e / v.I3, vv = e - s * v.I3;
+            const long long p0 = (long long)k * C2C_PLAN_CHUNK;
+            const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
+            for (long long p = p0; p < p1; ++p)
+                if (v.g[p] && plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv)) {
+                    v.ell_ent[((size_t)base + n) * 32 + lane] = (uint16_t)(p - p0);
+                    ++n;
+                }
+        }
+        for (; n < depth; ++n) v.ell_ent[((size_t)base + n) * 32 + lane] = (uint16_t)0xFFFF;
+    }
+}
+
+cudaError_t c2c_plan_fill(const uint8_t* mask, const PlanView& v, int nsm, cudaStream_t st)
+{
+    long long grid = (v.P + 7) / 8;
+    if (grid > (long long)nsm * 16) grid = (long long)nsm * 16;
+    plan_fill_csr_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, v);
+    long long g2 = ((long long)v.nchunks * v.ngroups + 7) / 8;
+    if (g2 > (long long)nsm * 16) g2 = (long long)nsm * 16;
+    plan_fill_ell_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gram form of the correction over the model-missing set
+// ---------------------------------------------------------------------------------------------------------------------
+// float4 of the Khatri-Rao row of plane p: columns 4 * quad .. 4 * quad + 3
+__device__ __forceinline__ float4 lead_quad(long long p, const LeadInfo& lead, int ldr, int quad)
+{
+    float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+    long long rem = p;
+    for (int k = lead.nl - 1; k >= 0; --k) {
+        const int d = lead.dim[k];
+        const long long q = rem / d;
+        const int i = (int)(rem - q * d);
+        rem = q;
+        const float4 f = *(reinterpret_cast<const float4*>(lead.fac[k] + (size_t)i * ldr) + quad);
+        w.x *= f.x; w.y *= f.y; w.z *= f.z; w.w *= f.w;
+    }
+    return w;
+}
+
+// CTA c < C0: D_c = G2_all o G3_miss + G2_miss o G3_obs  (= G2_all o G3_all - G2_obs o G3_obs, without the cancellation);
+// CTA C0: D = G2_all o G3_all.   G2_obs[q, r] = sum over the rows s with hs[c, s] = 1 of A2[s, q] A2[s, r], etc.
+__global__ void __launch_bounds__(256)
+trail_ctx_gram_kernel(const PlanView v, const float* __restrict__ A2, const float* __restrict__ A3, int R, int ldr,
+                      float* __restrict__ Dmat, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    const int c = blockIdx.x;
+    float* D = Dmat + (size_t)c * ldr * ldr;
+    for (int t = threadIdx.x; t < ldr * ldr; t += blockDim.x) {
+        const int q = t / ldr, r = t - q * ldr;
+        float d = 0.0f;
+        if (q < R && r < R) {
+            float g2o = 0.f, g2m = 0.f, g3o = 0.f, g3m = 0.f;
+            for (int s = 0; s < v.I2; ++s) {
+                const float x = A2[(size_t)s * ldr + q] * A2[(size_t)s * ldr + r];
+                if (c < v.C0 && v.hs[c * v.I2 + s]) g2o += x; else g2m += x;
+            }
+            for (int s = 0; s < v.I3; ++s) {
+                const float x = A3[(size_t)s * ldr + q] * A3[(size_t)s * ldr + r];
+                if (c < v.C0 && v.hv[c * v.I3 + s]) g3o += x; else g3m += x;
+            }
+            d = (g2o + g2m) * g3m + g2m * g3o;
+        }
+        D[t] = d;
+    }
+}
+
+cudaError_t c2c_launch_trail_ctx_gram(const PlanView& v, const float* A2, const float* A3, int R, int ldr, float* Dmat,
+                                      const int* done, cudaStream_t st, int pdl)
+{
+    return c2c_launch_ex(trail_ctx_gram_kernel, dim3(v.C0 + 1), dim3(256), 0, st, pdl, v, A2, A3, R, ldr, Dmat, done);
+}
+
+// CTA = (context c, part): a contiguous range of the planes of ONE context, so D_c and D_all sit in shared memory.
+// thread = (plane slot, column quad): the slot's Khatri-Rao row goes through shared memory, then 4 R FMAs.
+__global__ void __launch_bounds__(256)
+plane_corr_gram_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ Dmat, const float* __restrict__ T0,
+                       float* __restrict__ Tw, int R, int ldr, int parts, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    extern __shared__ __align__(16) float pcg_smem[];
+    const int q4 = ldr >> 2, LL = ldr * ldr;
+    const int npp = blockDim.x / q4;                                   // plane slots per pass
+    float* sD = pcg_smem;                                              // [ldr][ldr] D_c
+    float* sF = sD + LL;                                               // [ldr][ldr] D_all
+    float* sW = sF + LL;                                               // [npp][ldr]
+    const int c = blockIdx.x / parts, part = blockIdx.x - c * parts;
+    for (int t = threadIdx.x; t < LL; t += blockDim.x) {
+        sD[t] = Dmat[(size_t)c * LL + t];
+        sF[t] = Dmat[(size_t)v.C0 * LL + t];
+    }
+    const long long per = (v.ppc0 + parts - 1) / parts;
+    const long long p_begin = (long long)c * v.ppc0 + (long long)part * per;
+    long long p_end = p_begin + per;
+    if (p_end > (long long)(c + 1) * v.ppc0) p_end = (long long)(c + 1) * v.ppc0;
+    const int slot = threadIdx.x / q4, quad = threadIdx.x - slot * q4;
+    for (long long pb = p_begin; pb < p_end; pb += npp) {
+        const long long p = pb + slot;
+        const bool on = slot < npp && p < p_end;
+        __syncthreads();                                               // sD / sF ready; sW of the previous pass consumed
+        if (on) *(reinterpret_cast<float4*>(sW + (size_t)slot * ldr) + quad) = lead_quad(p, lead, ldr, quad);
+        __syncthreads();
+        if (on) {
+            float4 acc = __ldg(reinterpret_cast<const float4*>(T0 + (size_t)p * ldr) + quad);
+            const float* D = v.g[p] ? sD : sF;
+            const float* w = sW + (size_t)slot * ldr;
+            for (int q = 0; q < R; ++q) {
+                const float wq = w[q];
+                const float4 d = *(reinterpret_cast<const float4*>(D + (size_t)q * ldr) + quad);
+                acc.x = fmaf(wq, d.x, acc.x); acc.y = fmaf(wq, d.y, acc.y);
+                acc.z = fmaf(wq, d.z, acc.z); acc.w = fmaf(wq, d.w, acc.w);
+            }
+            *(reinterpret_cast<float4*>(Tw + (size_t)p * ldr) + quad) = acc;
+        }
+    }
+}
+
+cudaError_t c2c_launch_plane_corr_gram(const PlanView& v, const LeadInfo& lead, const float* Dmat, const float* T0, float* Tw,
+                                       int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
+{
+    int parts = (2 * nsm + v.C0 - 1) / v.C0;
+    const long long maxparts = (v.ppc0 + 63) / 64;
+    if (parts > maxparts) parts = (int)maxparts;
+    if (parts < 1) parts = 1;
+    const int q4 = ldr / 4, npp = 256 / q4;
+    const size_t smem = ((size_t)2 * ldr * ldr + (size_t)npp * ldr) * sizeof(float);
+    return c2c_launch_ex(plane_corr_gram_kernel, dim3((unsigned)(v.C0 * parts)), dim3(256), smem, st, pdl, v, lead, Dmat, T0, Tw, R,
+                         ldr, parts, done);
+}
+
+// CTA = (context c, part): Yo = sum over its planes with g = 1 of W[p] (x) W[p], Ym = the same over g = 0.
+// thread = (plane subgroup, 4 x 4 tile of the R x R matrix); the W rows of 64 planes at a time go through shared memory.
+#define C2C_LCG_BATCH 64
+__global__ void __launch_bounds__(256)
+lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int parts, float* __restrict__ Ypart, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    extern __shared__ __align__(16) float lcg_smem[];
+    const int q4 = ldr >> 2, ntile = q4 * q4, LL = ldr * ldr;
+    const int nsub = blockDim.x / ntile;                               // >= 4 (ntile <= 64)
+    float* sW = lcg_smem;                                              // [BATCH][ldr]
+    int* sg = reinterpret_cast<int*>(sW + (size_t)C2C_LCG_BATCH * ldr); // [BATCH]
+    float* sRed = reinterpret_cast<float*>(sg + C2C_LCG_BATCH);        // [nsub][2][LL]
+    const int c = blockIdx.x / parts, part = blockIdx.x - c * parts;
+    const long long per = (v.ppc0 + parts - 1) / parts;
+    const long long p_begin = (long long)c * v.ppc0 + (long long)part * per;
+    long long p_end = p_begin + per;
+    if (p_end > (long long)(c + 1) * v.ppc0) p_end = (long long)(c + 1) * v.ppc0;
+    const int sub = threadIdx.x / ntile, tile = threadIdx.x - sub * ntile;
+    const int tq = tile / q4, tr = tile - tq * q4;
+    float ao[16], am[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ao[i] = 0.0f; am[i] = 0.0f; }
+    for (long long pb = p_begin; pb < p_end; pb += C2C_LCG_BATCH) {
+        const int nb = (int)(p_end - pb < C2C_LCG_BATCH ? p_end - pb : C2C_LCG_BATCH);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nb * q4; t += blockDim.x) {
+            const int pl = t / q4, quad = t - pl * q4;
+            *(reinterpret_cast<float4*>(sW + (size_t)pl * ldr) + quad) = lead_quad(pb + pl, lead, ldr, quad);
+            if (quad == 0) sg[pl] = v.g[pb + pl];
+        }
+        __syncthreads();
+        if (sub < nsub) {
+            for (int pl = sub; pl < nb; pl += nsub) {
+                const float4 a = *(reinterpret_cast<const float4*>(sW + (size_t)pl * ldr) + tq);
+                const float4 b = *(reinterpret_cast<const float4*>(sW + (size_t)pl * ldr) + tr);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                if (sg[pl]) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ao[i * 4 + j] = fmaf(av[i], bv[j], ao[i * 4 + j]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) am[i * 4 + j] = fmaf(av[i], bv[j], am[i * 4 + j]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (sub < nsub) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int idx = (tq * 4 + i) * ldr + tr * 4 + j;
+                sRed[((size_t)sub * 2 + 0) * LL + idx] = ao[i * 4 + j];
+                sRed[((size_t)sub * 2 + 1) * LL + idx] = am[i * 4 + j];
+            }
+    }
+    __syncthreads();
+    float* out = Ypart + ((size_t)c * parts + part) * 2 * LL;
+    for (int t = threadIdx.x; t < 2 * LL; t += blockDim.x) {
+        float s = 0.0f;
+        for (int k = 0; k < nsub; ++k) s += sRed[(size_t)k * 2 * LL + t];
+        const int idx = t % LL, q = idx / ldr, r = idx - q * ldr;
+        out[t] = (q < R && r < R) ? s : 0.0f;
+    }
+}
+
+// Ymat[c] = sum of the parts' Yo of context c; Ymat[C0] = sum over all contexts and parts of Ym   (fixed order)
+__global__ void __launch_bounds__(256)
+ctx_gram_finalize_kernel(const float* __restrict__ Ypart, int C0, int parts, int LL, float* __restrict__ Ymat, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    const int c = blockIdx.x;
+    for (int t = threadIdx.x; t < LL; t += blockDim.x) {
+        float s = 0.0f;
+        if (c < C0) {
+            for (int k = 0; k < parts; ++k) s += Ypart[(((size_t)c * parts + k) * 2 + 0) * LL + t];
+        } else {
+            for (int cc = 0; cc < C0; ++cc)
+                for (int k = 0; k < parts; ++k) s += Ypart[(((size_t)cc * parts + k) * 2 + 1) * LL + t];
+        }
+        Ymat[(size_t)c * LL + t] = s;
+    }
+}
+
+int c2c_lead_ctx_parts(int C0, int nsm)
+{
+    int parts = (2 * nsm + C0 - 1) / C0;
+    return parts < 1 ? 1 : parts;
+}
+
+cudaError_t c2c_launch_lead_ctx_gram(const PlanView& v, const LeadInfo& lead, int R, int ldr, float* Ypart, float* Ymat,
+                                     const int* done, int nsm, cudaStream_t st, int pdl)
+{
+    const int parts = c2c_lead_ctx_parts(v.C0, nsm);
+    const int q4 = ldr / 4, ntile = q4 * q4, nsub = 256 / ntile, LL = ldr * ldr;
+    const size_t smem = (size_t)C2C_LCG_BATCH * ldr * sizeof(float) + C2C_LCG_BATCH * sizeof(int) + (size_t)nsub * 2 * LL * sizeof(float);
+    if (smem > 48 * 1024) {
+        const cudaError_t ea = cudaFuncSetAttribute(lead_ctx_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (ea != cudaSuccess) return ea;
+    }
+    cudaError_t e = c2c_launch_ex(lead_ctx_gram_kernel, dim3((unsigned)(v.C0 * parts)), dim3(256), smem, st, pdl, v, lead, R, ldr, parts,
+                                  Ypart, done);
+    if (e != cudaSuccess) return e;
+    return c2c_launch_ex(ctx_gram_finalize_kernel, dim3(v.C0 + 1), dim3(256), 0, st, pdl, (const float*)Ypart, v.C0, parts, LL, Ymat,
+                         done);
+}
+
+#define C2C_PLAN_DISPATCH(CALL)                                                                                          \
+    switch (ldr) {                                                                                                       \
+        case 4: CALL(4); break; case 8: CALL(8); break; case 12: CALL(12); break; case 16: CALL(16); break;              \
+        case 20: CALL(20); break; case 24: CALL(24); break; case 28: CALL(28); break; case 32: CALL(32); break;          \
+        default: return cudaErrorNotSupported;                                                                           \
+    }
+
+// thread = (position e, column quad): Uw[e, quad] = U0[e, quad] + sum_q B[e, q] * Z_e[q, quad],
+// Z_e = Y_missing + sum over the contexts c whose row s or column v the model misses of Y_c
+template <int NQ>
+__global__ void __launch_bounds__(256)
+fiber_corr_gram_kernel(const PlanView v, const float* __restrict__ A2, const float* __restrict__ A3, const float* __restrict__ Ymat,
+                       const float* __restrict__ U0, float* __restrict__ Uw, int R, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    constexpr int q4 = NQ / 4, LL = NQ * NQ;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)v.E * q4) return;
+    const int e = (int)(t / q4), quad = (int)(t - (long long)e * q4);
+    const int s = e / v.I3, vv = e - s * v.I3;
+    float b[NQ];
+#pragma unroll
+    for (int k = 0; k < q4; ++k) {
+        const float4 x = *(reinterpret_cast<const float4*>(A2 + (size_t)s * NQ) + k);
+        const float4 y = *(reinterpret_cast<const float4*>(A3 + (size_t)vv * NQ) + k);
+        b[4 * k] = x.x * y.x; b[4 * k + 1] = x.y * y.y; b[4 * k + 2] = x.z * y.z; b[4 * k + 3] = x.w * y.w;
+    }
+    float4 acc = __ldg(reinterpret_cast<const float4*>(U0 + (size_t)e * NQ) + quad);
+    for (int c = 0; c <= v.C0; ++c) {
+        if (c < v.C0 && v.hs[c * v.I2 + s] && v.hv[c * v.I3 + vv]) continue;
+        const float4* Y = reinterpret_cast<const float4*>(Ymat + (size_t)c * LL) + quad;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (q < R) {
+                const float4 y = Y[q * q4];
+                acc.x = fmaf(b[q], y.x, acc.x); acc.y = fmaf(b[q], y.y, acc.y);
+                acc.z = fmaf(b[q], y.z, acc.z); acc.w = fmaf(b[q], y.w, acc.w);
+            }
+        }
+    }
+    *(reinterpret_cast<float4*>(Uw + (size_t)e * NQ) + quad) = acc;
+}
+
+cudaError_t c2c_launch_fiber_corr_gram(const PlanView& v, const float* A2, const float* A3, const float* Ymat, const float* U0,
+                                       float* Uw, int R, int ldr, const int* done, cudaStream_t st, int pdl)
+{
+    const long long n = (long long)v.E * (ldr / 4);
+    const dim3 grid((unsigned)((n + 255) / 256));
+#define FCG_CALL(N) do { const cudaError_t e_ = c2c_launch_ex(fiber_corr_gram_kernel<N>, grid, dim3(256), 0, st, pdl, v, A2, A3, Ymat, U0, Uw, R, done); \
+                         if (e_ != cudaSuccess) return e_; } while (0)
+    C2C_PLAN_DISPATCH(FCG_CALL)
+#undef FCG_CALL
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the residual lists
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lead_weight32(unsigned p, const LeadInfo& lead, int ldr, int r)
+{
+    float w = 1.0f;
+    unsigned rem = p;
+    for (int k = lead.nl - 1; k >= 0; --k) {
+        const unsigned d = (unsigned)lead.dim[k];
+        const unsigned q = rem / d;
+        const unsigned i = rem - q * d;
+        rem = q;
+        w *= lead.fac[k][(size_t)i * ldr + r];
+    }
+    return w;
+}
+
+// a warp per plane with residual entries: lanes stride the plane's list, B rows from shared memory (SMEM_B) or L1
+template <int NQ, bool SMEM_B>
+__global__ void __launch_bounds__(256)
+plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ Bmat, const float* Tin,
+                       float* Tout, int R, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    extern __shared__ __align__(16) float pcl_smem[];
+    if (SMEM_B) {
+        const float4* src = reinterpret_cast<const float4*>(Bmat);
+        float4* dst = reinterpret_cast<float4*>(pcl_smem);
+        for (int i = threadIdx.x; i < v.E * (NQ / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const float* Bsrc = SMEM_B ? pcl_smem : Bmat;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool copy = Tin != Tout;
+    for (long long p = warp; p < v.P; p += nwarps) {
+        const int b0 = v.row_off[p], n = v.row_off[p + 1] - b0;
+        if (n == 0) {
+            if (copy && lane < NQ) Tout[(size_t)p * NQ + lane] = Tin[(size_t)p * NQ + lane];
+            continue;
+        }
+        const float wl = lane < R ? lead_weight32((unsigned)p, lead, NQ, lane) : 0.0f;
+        float w[NQ], acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { w[q] = __shfl_sync(0xffffffffu, wl, q); acc[q] = 0.0f; }
+        for (int i = lane; i < n; i += 32) {
+            const int e = v.csr_ent[(size_t)b0 + i];
+            const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)e * NQ);
+            float b[NQ];
+#pragma unroll
+            for (int k = 0; k < NQ / 4; ++k) {
+                const float4 x = b4[k];
+                b[4 * k] = x.x; b[4 * k + 1] = x.y; b[4 * k + 2] = x.z; b[4 * k + 3] = x.w;
+            }
+            float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
+            const float rec = r0 + r1;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, b[q], acc[q]);
+        }
+        float mine = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const float s = warp_sum(acc[q]);
+            if (lane == q) mine = s;
+        }
+        if (lane < NQ) Tout[(size_t)p * NQ + lane] = Tin[(size_t)p * NQ + lane] + mine;
+    }
+}
+
+cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, const float* Bmat, const float* Tin, float* Tout,
+                                       int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
+{
+    const size_t bbytes = (size_t)v.E * ldr * sizeof(float);
+    const bool smem_b = bbytes <= 100 * 1024;
+    long long grid = (v.P + 7) / 8;
+    if (grid > (long long)nsm * (smem_b ? 2 : 8)) grid = (long long)nsm * (smem_b ? 2 : 8);
+#define PCL_CALL(N)                                                                                                      \
+    do {                                                                                                                 \
+        cudaError_t e_;                                                                                                  \
+        if (smem_b) {                                                                                                    \
+            if (bbytes > 48 * 1024) {                                                                                    \
+                e_ = cudaFuncSetAttribute(plane_corr_list_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+                if (e_ != cudaSuccess) return e_;                                                                        \
+            }                                                                                                            \
+            e_ = c2c_launch_ex(plane_corr_list_kernel<N, true>, dim3((unsigned)grid), dim3(256), bbytes, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+        } else                                                                                                           \
+            e_ = c2c_launch_ex(plane_corr_list_kernel<N, false>, dim3((unsigned)grid), dim3(256), 0, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+        if (e_ != cudaSuccess) return e_;                                                                                \
+    } while (0)
+    C2C_PLAN_DISPATCH(PCL_CALL)
+#undef PCL_CALL
+    return cudaSuccess;
+}
+
+// CTA (i, j): 8 position groups (one per warp, 32 positions each, accumulators and B rows in registers) x a range of plane
+// chunks; the Khatri-Rao rows of a chunk are staged in shared memory once per CTA and read by all 8 warps.
+template <int NQ>
+__global__ void __launch_bounds__(256)
+fiber_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ A2, const float* __restrict__ A3,
+                       float* __restrict__ part, int R, int cpj, const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    __shared__ __align__(16) float sW[C2C_PLAN_CHUNK * NQ];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gq = blockIdx.x * 8 + wid;                               // this warp's position group
+    const int e = gq * 32 + lane;
+    const bool live = gq < v.ngroups && e < v.E;
+    float b[NQ], acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { b[q] = 0.0f; acc[q] = 0.0f; }
+    if (live) {
+        const int s = e / v.I3, vv = e - s * v.I3;
+#pragma unroll
+        for (int k = 0; k < NQ / 4; ++k) {
+            const float4 x = *(reinterpret_cast<const float4*>(A2 + (size_t)s * NQ) + k);
+            const float4 y = *(reinterpret_cast<const float4*>(A3 + (size_t)vv * NQ) + k);
+            b[4 * k] = x.x * y.x; b[4 * k + 1] = x.y * y.y; b[4 * k + 2] = x.z * y.z; b[4 * k + 3] = x.w * y.w;
+        }
+    }
+    const int k_begin = blockIdx.y * cpj;
+    const int k_end = k_begin + cpj < v.nchunks ? k_begin + cpj : v.nchunks;
+    for (int k = k_begin; k < k_end; ++k) {
+        const long long p0 = (long long)k * C2C_PLAN_CHUNK;
+        const int np = (int)(v.P - p0 < C2C_PLAN_CHUNK ? v.P - p0 : C2C_PLAN_CHUNK);
+        __syncthreads();
+        for (int t = threadIdx.x; t < np * NQ; t += blockDim.x) {
+            const int pl = t / NQ, q = t - pl * NQ;
+            sW[t] = q < R ? lead_weight32((unsigned)(p0 + pl), lead, NQ, q) : 0.0f;
+        }
+        __syncthreads();
+        if (gq < v.ngroups) {
+            const int base = v.ell_off[(size_t)k * v.ngroups + gq];
+            const int depth = v.ell_off[(size_t)k * v.ngroups + gq + 1] - base;
+            const uint16_t* ent = v.ell_ent + (size_t)base * 32 + lane;
+            for (int d = 0; d < depth; ++d) {
+                const unsigned pl = ent[(size_t)d * 32];
+                if (pl != 0xFFFFu) {
+                    const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)pl * NQ);
+                    float w[NQ];
+#pragma unroll
+                    for (int kk = 0; kk < NQ / 4; ++kk) {
+                        const float4 x = w4[kk];
+                        w[4 * kk] = x.x; w[4 * kk + 1] = x.y; w[4 * kk + 2] = x.z; w[4 * kk + 3] = x.w;
+                    }
+                    float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
+                    const float rec = r0 + r1;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, w[q], acc[q]);
+                }
+            }
+        }
+    }
+    if (live) {
+        float4* out = reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * v.E + e) * NQ);
+#pragma unroll
+        for (int k = 0; k < NQ / 4; ++k) out[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+    }
+}
+
+// Uout = Uin + sum of the plane-range partials, in a fixed order
+__global__ void __launch_bounds__(256)
+plan_reduce_kernel(const float* __restrict__ part, int nparts, long long n4, const float* Uin, float* Uout,
+                   const int* done)
+{
+    pdl_trigger();
+    pdl_wait();
+    if (run_done(done)) return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < nparts; ++c) {
+        const float4 x = reinterpret_cast<const float4*>(part)[(size_t)c * n4 + i];
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    }
+    const float4 u = reinterpret_cast<const float4*>(Uin)[i];
+    reinterpret_cast<float4*>(Uout)[i] = make_float4(u.x + s.x, u.y + s.y, u.z + s.z, u.w + s.w);
+}
+
+cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const LeadInfo& lead, const float* A2, const float* A3, const float* Uin,
+                                       float* Uout, float* part, int max_parts, int R, int ldr, const int* done, int nsm,
+                                       cudaStream_t st, int pdl)
+{
+    const int ni = (v.ngroups + 7) / 8;
+    int nj = (3 * nsm + ni - 1) / ni;                                  // ~3 CTAs per SM in all
+    if (nj > max_parts) nj = max_parts;
+    if (nj > v.nchunks) nj = v.nchunks;
+    if (nj < 1) nj = 1;
+    const int cpj = (v.nchunks + nj - 1) / nj;
+    nj = (v.nchunks + cpj - 1) / cpj;
+    const dim3 grid((unsigned)ni, (unsigned)nj);
+#define FCL_CALL(N) do { const cudaError_t e_ = c2c_launch_ex(fiber_corr_list_kernel<N>, grid, dim3(256), 0, st, pdl, v, lead, A2, A3, part, R, cpj, done); \
+                         if (e_ != cudaSuccess) return e_; } while (0)
+    C2C_PLAN_DISPATCH(FCL_CALL)
+#undef FCL_CALL
+    const long long n4 = (long long)v.E * ldr / 4;
+    return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, pdl, (const float*)part, nj, n4, Uin,
+                         Uout, done);
+}

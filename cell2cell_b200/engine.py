@@ -13,7 +13,8 @@ from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, li
 
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
            "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
-           "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "coupled_ncp_run", "build_ccc", "group_aggregate"]
+           "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "coupled_ncp_run", "build_ccc", "group_aggregate",
+           "MaskPlan", "mask_plan", "masked_contract_planned"]
 
 _vp = ctypes.c_void_p
 
@@ -234,6 +235,74 @@ def cp_normalize(factors, rank, weights=None):
         return w
 
 
+class MaskPlan:
+    """The mask plan of ``c2c_mask_plan_scan`` / ``_fill`` (include/c2c_b200.h): the tightest separable model
+    ``observed[p, s, v] = g[p] * hs[c(p), s] * hv[c(p), v]`` of the mask plus the residual missing entries as lists, built once
+    per (tensor, mask) and used by every masked factorization of that tensor.  ``usable`` is False when the tensor holds
+    non-zero values under zero mask bytes (the dense + correction form needs zeros there) or the lists would overflow."""
+
+    def __init__(self, X, mask):
+        _check_tensor(X, mask)
+        shape = tuple(int(s) for s in X.shape)
+        self.shape = shape
+        with torch.cuda.device(X.device):
+            nb = int(lib().c2c_mask_plan_header_bytes(len(shape), _shape_arr(shape)))
+            self.usable = nb > 0
+            self.header = self.lists = None
+            self.info = (ctypes.c_int64 * 8)()
+            if not self.usable:
+                return
+            self.header = torch.empty(nb, dtype=torch.uint8, device=X.device)
+            check(lib().c2c_mask_plan_scan(_ptr(X), _ptr(mask), len(shape), _shape_arr(shape), _ptr(self.header), nb, self.info,
+                                           _stream()), "c2c_mask_plan_scan")
+            self.usable = self.info[2] == 0 and self.info[5] == 0
+            if self.usable and self.info[1] > 0:
+                self.lists = torch.empty(int(self.info[6]), dtype=torch.uint8, device=X.device)
+                check(lib().c2c_mask_plan_fill(_ptr(mask), len(shape), _shape_arr(shape), _ptr(self.header), nb, self.info,
+                                               _ptr(self.lists), self.lists.numel(), _stream()), "c2c_mask_plan_fill")
+
+    n_missing = property(lambda self: int(self.info[0]))
+    n_residual = property(lambda self: int(self.info[1]))
+    model_missing = property(lambda self: bool(self.info[4]))
+
+    def args(self):
+        """(header, header_bytes, lists, lists_bytes, info) as the planned entry points take them."""
+        return (_ptr(self.header), self.header.numel(), _ptr(self.lists), 0 if self.lists is None else self.lists.numel(),
+                self.info)
+
+
+def mask_plan(X, mask):
+    """The plan of ``mask`` (cached on the mask tensor; rebuilt if the mask was written to since)."""
+    cached = getattr(mask, "_c2c_plan", None)
+    key = (X.data_ptr(), mask.data_ptr(), mask._version, X._version, tuple(X.shape))
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    plan = MaskPlan(X, mask)
+    mask._c2c_plan = (key, plan)
+    return plan
+
+
+def masked_contract_planned(X, mask, factors, rank, which, ws=None, plan=None):
+    """T (``which=0``, ``[P, ldr]``) or U (``which=1``, ``[E, ldr]``) of the imputed tensor -- observed entries of X, the
+    reconstruction of ``factors`` at the missing ones -- from the unmasked pass plus the mask plan's corrections."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        plan = plan or mask_plan(X, mask)
+        if ws is None or not ws.fits(X.shape, rank, True):
+            ws = Workspace(X.shape, rank, True, X.device)
+        n = int(np.prod(X.shape[:-2])) if which == 0 else int(X.shape[-2] * X.shape[-1])
+        out = torch.empty((n, ldr_of(rank)), dtype=torch.float32, device=X.device)
+        check(lib().c2c_masked_contract_planned(_ptr(X), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                                int(which), _ptr(out), ws.ptr, ws.nbytes, *plan.args(), _stream()),
+              "c2c_masked_contract_planned")
+        return out
+
+
+def _use_mask_plan():
+    import os
+    return os.environ.get("C2C_B200_NO_MASK_PLAN", "0") != "1"
+
+
 def ncp_run(X, mask, factors, rank, tf_type="non_negative_cp", n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error",
             check_every=10, norm_x2=None, ws=None, sync=True):
     """Run tensorly-semantics NCP on the device, updating the packed ``factors`` in place.
@@ -259,9 +328,24 @@ def ncp_run(X, mask, factors, rank, tf_type="non_negative_cp", n_iter_max=100, t
         nx2 = None
         if norm_x2 is not None:
             nx2 = torch.tensor([float(norm_x2)], dtype=torch.float64, device=X.device)
-        check(lib().c2c_ncp_run(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
-                                ALGO[tf_type], int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(nx2), _ptr(errors),
-                                _ptr(state), int(check_every), ws.ptr, ws.nbytes, _stream()), "c2c_ncp_run")
+        done = False
+        if mask is not None and tf_type == "non_negative_cp" and rank <= 32 and _use_mask_plan():
+            # masked multiplicative updates: the mask plan (built once per tensor) replaces every pass over the mask
+            plan = mask_plan(X, mask)
+            if plan.usable:
+                try:
+                    check(lib().c2c_ncp_run_planned(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors),
+                                                    ldr_of(rank), rank, int(n_iter_max), float(tol), CVG[cvg_criterion],
+                                                    _ptr(nx2), _ptr(errors), _ptr(state), int(check_every), ws.ptr, ws.nbytes,
+                                                    *plan.args(), _stream()), "c2c_ncp_run_planned")
+                    done = True
+                except C2CError as err:
+                    if getattr(err, "code", 0) != -50:      # -50: the plan path does not take this shape / rank
+                        raise
+        if not done:
+            check(lib().c2c_ncp_run(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                    ALGO[tf_type], int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(nx2), _ptr(errors),
+                                    _ptr(state), int(check_every), ws.ptr, ws.nbytes, _stream()), "c2c_ncp_run")
         if not sync:
             return errors, state
         st = state.cpu().numpy()

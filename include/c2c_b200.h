@@ -200,6 +200,42 @@ int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* c
                         int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
                         int check_every, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- mask plan: the masked factorization without a pass over the mask ---------------------------------------------------
+ * tensorly re-imputes the missing entries with the current reconstruction before every mode's MTTKRP
+ * (`tensor*mask + cp_to_tensor(cp, mask=1-mask)`, mirrored at cell2cell/tensor/coupled_factorization.py:342-345).  With zeros
+ * stored at the missing entries (what cell2cell holds: tensor.py:842-847, 933-946) that MTTKRP is the unmasked contraction of
+ * the tensor plus the contraction of the reconstruction over the MISSING set.  The mask of a how='outer' tensor
+ * (cell2cell/tensor/tensor.py:1083-1145) is separable -- observed[p, s, v] = g[p] * hs[c(p), s] * hv[c(p), v]: a gene pair
+ * absent from a context removes a plane, a cell type absent from it removes a row and a column of every plane of the context --
+ * and over such a set the sum collapses to products of R x R restricted Grams.  The plan, built once per (tensor, mask), holds
+ * the tightest separable model of any mask plus the residual entries (missing, but observed by the model) as lists.
+ *
+ * header: device buffer of c2c_mask_plan_header_bytes(shape) bytes (256-byte aligned).
+ * c2c_mask_plan_scan fills it and returns (synchronising the stream) info[8] (host):
+ *   [0] missing entries  [1] residual entries  [2] 1 if a non-zero value sits under a zero mask byte (plan not usable)
+ *   [3] list rows        [4] 1 if the separable model misses anything        [5] 1 on overflow (plan not usable)
+ *   [6] bytes of the `lists` device buffer c2c_mask_plan_fill needs          [7] library version
+ * X may be NULL (no zero-fill check).  c2c_mask_plan_fill writes the residual lists (nothing to do when info[1] == 0).
+ */
+size_t c2c_mask_plan_header_bytes(int ndim, const int64_t* shape /*host*/);
+int c2c_mask_plan_scan(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/, void* header,
+                       size_t header_bytes, int64_t* info /*host, 8*/, void* stream);
+int c2c_mask_plan_fill(const uint8_t* mask, int ndim, const int64_t* shape /*host*/, const void* header, size_t header_bytes,
+                       const int64_t* info /*host*/, void* lists, size_t lists_bytes, void* stream);
+/* c2c_ncp_run (multiplicative updates) for a masked tensor with its plan: per iteration the tensor is read twice, the mask
+ * never.  Returns -50 when the plan path does not apply (rank > 32, trailing modes too large for the fused updates, info[2] or
+ * info[5] set): call c2c_ncp_run instead.  ws: c2c_ncp_workspace_bytes(.., masked = 1). */
+int c2c_ncp_run_planned(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/, float* const* A /*host array*/,
+                        int ldr, int rank, int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors,
+                        int* state, int check_every, void* ws, size_t ws_bytes, const void* header, size_t header_bytes,
+                        const void* lists, size_t lists_bytes, const int64_t* info /*host*/, void* stream);
+/* c2c_plane_contract (which = 0, out = T [P x ldr]) / c2c_fiber_contract (which = 1, out = U [E x ldr]) of the imputed tensor:
+ * the unmasked pass over X plus the plan's corrections for the given factors. */
+int c2c_masked_contract_planned(const float* X, int ndim, const int64_t* shape /*host*/, const float* const* A /*host array*/,
+                                int ldr, int rank, int which, float* out, void* ws, size_t ws_bytes, const void* header,
+                                size_t header_bytes, const void* lists, size_t lists_bytes, const int64_t* info /*host*/,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif
