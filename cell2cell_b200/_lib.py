@@ -52,11 +52,15 @@ SIGNATURES = {
                                  _c.c_double, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),
     "c2c_hals_update": (_i, [_p, _p, _p, _i64, _i, _i, _i, _c.c_float, _p]),
     "c2c_recon_sums": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
+    "c2c_missing_rec_sumsq": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
     "c2c_cp_normalize": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _p, _p]),
     "c2c_ncp_run": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _i, _c.c_double, _i, _p, _p, _p, _i,
                          _p, _sz, _p]),
     "c2c_ncp_run_batched": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _c.POINTER(_i), _i, _i, _c.c_double, _i, _p, _p, _p, _i,
                                  _p, _sz, _p]),
+    "c2c_ncp_multi_workspace_bytes": (_sz, [_i, _c.POINTER(_i64), _c.POINTER(_i), _i]),
+    "c2c_ncp_run_multi": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _c.POINTER(_i), _i, _i, _c.c_double, _i, _p, _p, _p, _p,
+                               _p, _sz, _p]),
     "c2c_mask_plan_header_bytes": (_sz, [_i, _c.POINTER(_i64)]),
     "c2c_mask_plan_scan": (_i, [_p, _p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p]),
     "c2c_mask_plan_fill": (_i, [_p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p, _sz, _p]),

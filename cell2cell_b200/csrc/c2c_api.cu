@@ -20,6 +20,7 @@
 #include "c2c_sums.cuh"
 #include "c2c_corr.cuh"
 #include "c2c_plan.cuh"
+#include "c2c_multi.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -27,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #define C2C_VERSION 100
 #ifndef C2C_MMA_PLANE_LEAD
@@ -666,18 +668,18 @@ impute_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, lon
 __global__ void __launch_bounds__(256)
 recon_sums_generic_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask, long long P, int I2, int I3,
                           LeadInfo lead, const float* __restrict__ A2, const float* __restrict__ A3, int R, int ldr,
-                          double* __restrict__ sums)
+                          double* __restrict__ sums, int missing)
 {
     const long long E = (long long)I2 * I3, n = P * E;
     double v[5] = {0, 0, 0, 0, 0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if (mask && !mask[i]) continue;
+        if (mask && ((mask[i] != 0) == (missing != 0))) continue;
         const long long p = i / E; const int e = (int)(i - p * E);
         const int s = e / I3, c = e - s * I3;
         float rec = 0.0f;
         for (int q = 0; q < R; ++q)
             rec = fmaf(lead_weight_col(p, lead, ldr, q, -1) * A2[(size_t)s * ldr + q], A3[(size_t)c * ldr + q], rec);
-        const double x = X[i], d = x - (double)rec;
+        const double x = missing ? 0.0 : (double)X[i], d = x - (double)rec;
         v[0] += d; v[1] += d * d; v[2] += x; v[3] += x * x; v[4] += 1.0;
     }
     __shared__ double red[5][8];
@@ -998,21 +1000,16 @@ extern "C" int c2c_hals_update(float* A_mode, const float* M, const float* G, in
 // ---------------------------------------------------------------------------------------------------------------------
 // K6 final sums
 // ---------------------------------------------------------------------------------------------------------------------
-extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
-                              int ldr, int rank, double* out, void* ws, size_t ws_bytes, void* stream)
+// out[0..4] = the five sums over the observed entries; missing != 0: over the MISSING entries with x taken as 0, so that
+// out[1] = ||(1 - mask) * reconstruction||^2
+static int recon_sums_impl(const Geo& g, const Ws& w, const float* X, const uint8_t* mask, const float* const* A, int ldr, int rank,
+                           int missing, double* out, cudaStream_t st)
 {
-    Geo g; int rc;
-    if (!shape) return fail(-1, "shape is NULL");
-    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
-    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
-    if (!out) return fail(-14, "out is NULL");
-    Ws w;
-    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
     ContractArgs a = base_args(g, X, mask, A, ldr, rank, nullptr);
     a.sums = w.sums_part;
+    a.sums_missing = missing;
     if (g.nchunk > 1) {
-        recon_sums_generic_kernel<<<C2C_SUMS_BLOCKS, 256, 0, st>>>(X, mask, g.P, g.I2, g.I3, a.lead, a.A2, a.A3, rank, ldr, w.sums_part);
+        recon_sums_generic_kernel<<<C2C_SUMS_BLOCKS, 256, 0, st>>>(X, mask, g.P, g.I2, g.I3, a.lead, a.A2, a.A3, rank, ldr, w.sums_part, missing);
         CKL("recon_sums (generic) launch");
         sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, C2C_SUMS_BLOCKS, 5, 5, out);
         CKL("recon_sums reduce launch");
@@ -1028,7 +1025,7 @@ extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, con
             CKL("recon_sums reduce launch");
             return 0;
         }
-        if (e != cudaErrorNotSupported && e != cudaErrorInvalidValue) return cuda_fail(e, "recon_sums (stream) launch");
+        if (e != cudaErrorNotSupported) return cuda_fail(e, "recon_sums (stream) launch");
         (void)cudaGetLastError();
     }
     const int vec = g.vec_plane;
@@ -1041,6 +1038,37 @@ extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, con
     g_launches.fetch_add(1, std::memory_order_relaxed);
     sum_partials_kernel<<<5, 32, 0, st>>>(w.sums_part, grid, 5, 5, out);
     CKL("recon_sums reduce launch");
+    return 0;
+}
+
+extern "C" int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                              int ldr, int rank, double* out, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!out) return fail(-14, "out is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, mask != nullptr, ws, ws_bytes)) != 0) return rc;
+    return recon_sums_impl(g, w, X, mask, A, ldr, rank, 0, out, (cudaStream_t)stream);
+}
+
+// out[0] = ||(1 - mask) * reconstruction||^2: the squared norm of what tensorly's imputation `tensor*mask + cp_to_tensor(cp,
+// mask=1-mask)` writes into the tensor (coupled_factorization.py:342-343) -- the term by which the direct error of the coupled
+// factorization (error_calc without an MTTKRP, :420-431) exceeds the Gram form on the norm of the tensor as passed in
+extern "C" int c2c_missing_rec_sumsq(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, const float* const* A,
+                                     int ldr, int rank, double* out, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!out || !mask) return fail(-14, "out / mask is NULL");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, 1, ws, ws_bytes)) != 0) return rc;
+    if ((rc = recon_sums_impl(g, w, X, mask, A, ldr, rank, 1, w.scratch_d + 8, (cudaStream_t)stream)) != 0) return rc;
+    CK(cudaMemcpyAsync(out, w.scratch_d + 9, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "copy sum");
     return 0;
 }
 
@@ -1520,6 +1548,81 @@ extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shap
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// small tensors: a grid of independent factorizations, one CTA each (c2c_multi.cu)
+// ---------------------------------------------------------------------------------------------------------------------
+static int multi_check(Geo& g, int ndim, const int64_t* shape, const int* ranks, int nruns, size_t* smem_max, size_t* t_floats)
+{
+    int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if (!ranks || nruns < 1) return fail(-60, "multi-run: ranks is NULL or nruns < 1");
+    if ((rc = make_geo(g, ndim, shape, 1)) != 0) return rc;
+    if (g.I2 > 128 || g.I3 > 128) return fail(-61, "multi-run: trailing modes larger than 128 (%d x %d)", g.I2, g.I3);
+    if (g.P >= (1LL << 31)) return fail(-61, "multi-run: too many planes");
+    *smem_max = 0; *t_floats = 0;
+    for (int b = 0; b < nruns; ++b) {
+        if (ranks[b] < 1 || ranks[b] > 32) return fail(-61, "multi-run: rank %d of run %d not in 1..32", ranks[b], b);
+        const int ldr = ldr_of(ranks[b]);
+        const size_t sm = c2c_multi_smem_bytes(ndim, ldr, g.E, g.I2, g.I3);
+        if (sm > 200 * 1024) return fail(-61, "multi-run: %zu B of shared memory per run (> 200 KiB): tensor too large for this path", sm);
+        if (sm > *smem_max) *smem_max = sm;
+        *t_floats += align_up((size_t)g.P * ldr, 64);
+    }
+    return 0;
+}
+
+extern "C" size_t c2c_ncp_multi_workspace_bytes(int ndim, const int64_t* shape, const int* ranks, int nruns)
+{
+    Geo g; size_t smem, tf;
+    if (multi_check(g, ndim, shape, ranks, nruns, &smem, &tf) != 0) return 0;
+    return align_up((size_t)nruns * sizeof(MultiRun), 256) + tf * sizeof(float) + 256;
+}
+
+extern "C" int c2c_ncp_run_multi(const float* X, int ndim, const int64_t* shape, float* const* A, const int* ranks, int nruns,
+                                 int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
+                                 double* sums, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; size_t smem, tf; int rc;
+    if ((rc = multi_check(g, ndim, shape, ranks, nruns, &smem, &tf)) != 0) return rc;
+    if (!X || !A || !normX2 || !errors || !state) return fail(-10, "NULL argument");
+    if (((uintptr_t)X & 15) != 0) return fail(-25, "X must be 16-byte aligned");
+    if (cvg_criterion != C2C_CVG_ABS_REC_ERROR && cvg_criterion != C2C_CVG_REC_ERROR) return fail(-22, "unknown cvg_criterion %d", cvg_criterion);
+    if (n_iter_max < 1) return fail(-23, "n_iter_max < 1");
+    const size_t need = align_up((size_t)nruns * sizeof(MultiRun), 256) + tf * sizeof(float) + 256;
+    if (!ws || ws_bytes < need) return fail(-5, "workspace too small: need %zu bytes, got %zu (query c2c_ncp_multi_workspace_bytes)", need, ws_bytes);
+    if (((uintptr_t)ws & 255) != 0) return fail(-6, "workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<MultiRun> runs((size_t)nruns);
+    float* tbase = (float*)((char*)ws + align_up((size_t)nruns * sizeof(MultiRun), 256));
+    size_t toff = 0;
+    for (int b = 0; b < nruns; ++b) {
+        MultiRun& r = runs[(size_t)b];
+        memset(&r, 0, sizeof(r));
+        for (int k = 0; k < ndim; ++k) {
+            r.A[k] = A[(size_t)b * ndim + k];
+            if (!r.A[k] || ((uintptr_t)r.A[k] & 15) != 0) return fail(-11, "multi-run: factor %d of run %d is NULL or not 16-byte aligned", k, b);
+        }
+        r.rank = ranks[b]; r.ldr = ldr_of(ranks[b]);
+        r.T = tbase + toff; toff += align_up((size_t)g.P * r.ldr, 64);
+        r.errors = errors + (size_t)b * n_iter_max;
+        r.state = state + 2 * (size_t)b;
+        r.sums = sums ? sums + 5 * (size_t)b : nullptr;
+    }
+    CK(cudaMemcpyAsync(ws, runs.data(), (size_t)nruns * sizeof(MultiRun), cudaMemcpyHostToDevice, st), "copy run table");
+    CK(cudaMemsetAsync(state, 0, (size_t)nruns * 2 * sizeof(int), st), "memset state");
+    MultiArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = X; a.ndim = ndim;
+    for (int k = 0; k < ndim; ++k) a.shape[k] = (int)shape[k];
+    a.P = g.P; a.E = (int)g.E; a.I2 = g.I2; a.I3 = g.I3; a.runs = (const MultiRun*)ws; a.nruns = nruns;
+    a.n_iter_max = n_iter_max; a.tol = tol; a.cvg = cvg_criterion; a.normX2 = normX2;
+    a.eps = 1.1920928955078125e-07f;
+    const cudaError_t e = c2c_launch_ncp_multi(a, smem, st);
+    if (e != cudaSuccess) return cuda_fail(e, "ncp_multi launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // mask plan (c2c_plan.cu): built once per (tensor, mask), used by every masked factorization of that tensor
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" size_t c2c_mask_plan_header_bytes(int ndim, const int64_t* shape)
@@ -1750,6 +1853,16 @@ static int coupled_enqueue_iteration(CoupledCtx& c)
         } else {
             const int a = c.ma[k], b = c.mb[k];
             const long long I = c.s[0].g.shape[a];
+            if (k == c.nsteps - 1) {
+                // last update of the iteration: a masked tensor is re-imputed here for the last time; the squared norm of the
+                // imputed entries enters the direct error (coupled_error_kernel)
+                for (int side = 0; side < 2; ++side) {
+                    CoupledSide& sd = c.s[side];
+                    if (sd.mask == nullptr) continue;
+                    if ((rc = recon_sums_impl(sd.g, sd.w, sd.X, sd.mask, (const float* const*)sd.A, c.ldr, c.R, 1, sd.w.scratch_d + 4,
+                                              side == 0 ? st : st2)) != 0) return rc;
+                }
+            }
             if ((rc = coupled_mttkrp(c.s[0], a, c.R, c.ldr, done, st)) != 0) return rc;
             if ((rc = coupled_mttkrp(c.s[1], b, c.R, c.ldr, done, st2)) != 0) return rc;
             if ((rc = coupled_order(st2, st, c.ev21)) != 0) return rc;  // M2 and G2 are ready
@@ -1771,6 +1884,8 @@ static int coupled_enqueue_iteration(CoupledCtx& c)
     e.S1 = c.s[0].w.S; e.S2 = c.s[1].w.S; e.N1 = c.s[0].g.ndim; e.N2 = c.s[1].g.ndim; e.R = c.R; e.ldr = c.ldr;
     e.iprod = c.iprod; e.nx2_1 = c.nx2[0]; e.nx2_2 = c.nx2[1]; e.errors = c.errors; e.state = c.state;
     e.n_iter_max = c.n_iter_max; e.tol = c.tol; e.cvg = c.cvg; e.w1 = c.w1; e.w2 = c.w2;
+    e.miss2_1 = c.s[0].mask ? c.s[0].w.scratch_d + 5 : nullptr;
+    e.miss2_2 = c.s[1].mask ? c.s[1].w.scratch_d + 5 : nullptr;
     coupled_error_kernel<<<1, C2C_SMALL_THREADS, 0, st>>>(e);
     CKL("coupled_error launch");
     return 0;

@@ -34,6 +34,7 @@ struct ContractArgs {
     LeadInfo lead;
     float* out;                // plane_contract: T [P x ldr];  fiber_contract: partials [nparts x E x ldr]
     double* sums;              // recon_sums: per-CTA partial sums
+    int sums_missing;          // recon_sums: sum over the MISSING entries (mask == 0) with x taken as 0 -> sums[1] = ||(1 - m) rec||^2
     const int* done;           // device flag: non-zero => the run has converged, kernels return immediately (may be null)
 };
 

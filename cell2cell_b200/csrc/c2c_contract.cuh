@@ -148,8 +148,8 @@ plane_contract_kernel(const ContractArgs a)
                                     for (int j = 0; j < VEC; ++j) {
                                         const bool obs = (m[u] >> (8 * j)) & 1u;
                                         if (SUMS) {
-                                            if (obs) {
-                                                const double xv = x[u][j], d = (double)x[u][j] - (double)rec[j];
+                                            if (obs != (a.sums_missing != 0)) {
+                                                const double xv = a.sums_missing ? 0.0 : (double)x[u][j], d = xv - (double)rec[j];
                                                 s_d += d; s_dd += d * d; s_x += xv; s_xx += xv * xv; s_n += 1.0;
                                             }
                                         } else if (!obs) {

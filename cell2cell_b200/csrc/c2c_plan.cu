@@ -285,6 +285,7 @@ __device__ __forceinline__ float4 lead_quad(long long p, const LeadInfo& lead, i
 
 // CTA c < C0: D_c = G2_all o G3_miss + G2_miss o G3_obs  (= G2_all o G3_all - G2_obs o G3_obs, without the cancellation);
 // CTA C0: D = G2_all o G3_all.   G2_obs[q, r] = sum over the rows s with hs[c, s] = 1 of A2[s, q] A2[s, r], etc.
+// The two factors and the context's flags are staged in shared memory (the sums are latency chains otherwise).
 __global__ void __launch_bounds__(256)
 trail_ctx_gram_kernel(const PlanView v, const float* __restrict__ A2, const float* __restrict__ A3, int R, int ldr,
                       float* __restrict__ Dmat, const int* done)
@@ -292,7 +293,17 @@ trail_ctx_gram_kernel(const PlanView v, const float* __restrict__ A2, const floa
     pdl_trigger();
     pdl_wait();
     if (run_done(done)) return;
+    extern __shared__ __align__(16) float tcg_smem[];
+    float* s2 = tcg_smem;                                   // [I2][ldr]
+    float* s3 = s2 + (size_t)v.I2 * ldr;                    // [I3][ldr]
+    int* f2 = reinterpret_cast<int*>(s3 + (size_t)v.I3 * ldr);   // [I2] row observed in this context
+    int* f3 = f2 + v.I2;                                    // [I3]
     const int c = blockIdx.x;
+    for (int t = threadIdx.x; t < v.I2 * ldr; t += blockDim.x) s2[t] = A2[t];
+    for (int t = threadIdx.x; t < v.I3 * ldr; t += blockDim.x) s3[t] = A3[t];
+    for (int t = threadIdx.x; t < v.I2; t += blockDim.x) f2[t] = c < v.C0 ? v.hs[c * v.I2 + t] : 0;
+    for (int t = threadIdx.x; t < v.I3; t += blockDim.x) f3[t] = c < v.C0 ? v.hv[c * v.I3 + t] : 0;
+    __syncthreads();
     float* D = Dmat + (size_t)c * ldr * ldr;
     for (int t = threadIdx.x; t < ldr * ldr; t += blockDim.x) {
         const int q = t / ldr, r = t - q * ldr;
@@ -300,12 +311,12 @@ trail_ctx_gram_kernel(const PlanView v, const float* __restrict__ A2, const floa
         if (q < R && r < R) {
             float g2o = 0.f, g2m = 0.f, g3o = 0.f, g3m = 0.f;
             for (int s = 0; s < v.I2; ++s) {
-                const float x = A2[(size_t)s * ldr + q] * A2[(size_t)s * ldr + r];
-                if (c < v.C0 && v.hs[c * v.I2 + s]) g2o += x; else g2m += x;
+                const float x = s2[s * ldr + q] * s2[s * ldr + r];
+                if (f2[s]) g2o += x; else g2m += x;
             }
             for (int s = 0; s < v.I3; ++s) {
-                const float x = A3[(size_t)s * ldr + q] * A3[(size_t)s * ldr + r];
-                if (c < v.C0 && v.hv[c * v.I3 + s]) g3o += x; else g3m += x;
+                const float x = s3[s * ldr + q] * s3[s * ldr + r];
+                if (f3[s]) g3o += x; else g3m += x;
             }
             d = (g2o + g2m) * g3m + g2m * g3o;
         }
@@ -316,10 +327,15 @@ trail_ctx_gram_kernel(const PlanView v, const float* __restrict__ A2, const floa
 cudaError_t c2c_launch_trail_ctx_gram(const PlanView& v, const float* A2, const float* A3, int R, int ldr, float* Dmat,
                                       const int* done, cudaStream_t st, int pdl)
 {
-    return c2c_launch_ex(trail_ctx_gram_kernel, dim3(v.C0 + 1), dim3(256), 0, st, pdl, v, A2, A3, R, ldr, Dmat, done);
+    const size_t smem = (size_t)(v.I2 + v.I3) * ldr * sizeof(float) + (size_t)(v.I2 + v.I3) * sizeof(int);
+    if (smem > 48 * 1024) {
+        const cudaError_t ea = cudaFuncSetAttribute(trail_ctx_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (ea != cudaSuccess) return ea;
+    }
+    return c2c_launch_ex(trail_ctx_gram_kernel, dim3(v.C0 + 1), dim3(256), smem, st, pdl, v, A2, A3, R, ldr, Dmat, done);
 }
 
-// CTA = (context c, part): a contiguous range of the planes of ONE context, so D_c and D_all sit in shared memory.
+// CTA = (context c, batch): blockDim / (ldr / 4) consecutive planes of ONE context, so D_c and D_all sit in shared memory.
 // thread = (plane slot, column quad): the slot's Khatri-Rao row goes through shared memory, then 4 R FMAs.
 __global__ void __launch_bounds__(256)
 plane_corr_gram_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ Dmat, const float* __restrict__ T0,
@@ -330,59 +346,56 @@ plane_corr_gram_kernel(const PlanView v, const LeadInfo lead, const float* __res
     if (run_done(done)) return;
     extern __shared__ __align__(16) float pcg_smem[];
     const int q4 = ldr >> 2, LL = ldr * ldr;
-    const int npp = blockDim.x / q4;                                   // plane slots per pass
+    const int npp = blockDim.x / q4;                                   // plane slots
     float* sD = pcg_smem;                                              // [ldr][ldr] D_c
     float* sF = sD + LL;                                               // [ldr][ldr] D_all
     float* sW = sF + LL;                                               // [npp][ldr]
     const int c = blockIdx.x / parts, part = blockIdx.x - c * parts;
+    const int slot = threadIdx.x / q4, quad = threadIdx.x - slot * q4;
+    const long long p = (long long)c * v.ppc0 + (long long)part * npp + slot;
+    const bool on = slot < npp && p < (long long)(c + 1) * v.ppc0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int gp = 0;
+    if (on) {
+        acc = __ldg(reinterpret_cast<const float4*>(T0 + (size_t)p * ldr) + quad);
+        gp = v.g[p];
+        *(reinterpret_cast<float4*>(sW + (size_t)slot * ldr) + quad) = lead_quad(p, lead, ldr, quad);
+    }
     for (int t = threadIdx.x; t < LL; t += blockDim.x) {
         sD[t] = Dmat[(size_t)c * LL + t];
         sF[t] = Dmat[(size_t)v.C0 * LL + t];
     }
-    const long long per = (v.ppc0 + parts - 1) / parts;
-    const long long p_begin = (long long)c * v.ppc0 + (long long)part * per;
-    long long p_end = p_begin + per;
-    if (p_end > (long long)(c + 1) * v.ppc0) p_end = (long long)(c + 1) * v.ppc0;
-    const int slot = threadIdx.x / q4, quad = threadIdx.x - slot * q4;
-    for (long long pb = p_begin; pb < p_end; pb += npp) {
-        const long long p = pb + slot;
-        const bool on = slot < npp && p < p_end;
-        __syncthreads();                                               // sD / sF ready; sW of the previous pass consumed
-        if (on) *(reinterpret_cast<float4*>(sW + (size_t)slot * ldr) + quad) = lead_quad(p, lead, ldr, quad);
-        __syncthreads();
-        if (on) {
-            float4 acc = __ldg(reinterpret_cast<const float4*>(T0 + (size_t)p * ldr) + quad);
-            const float* D = v.g[p] ? sD : sF;
-            const float* w = sW + (size_t)slot * ldr;
-            for (int q = 0; q < R; ++q) {
-                const float wq = w[q];
-                const float4 d = *(reinterpret_cast<const float4*>(D + (size_t)q * ldr) + quad);
-                acc.x = fmaf(wq, d.x, acc.x); acc.y = fmaf(wq, d.y, acc.y);
-                acc.z = fmaf(wq, d.z, acc.z); acc.w = fmaf(wq, d.w, acc.w);
-            }
-            *(reinterpret_cast<float4*>(Tw + (size_t)p * ldr) + quad) = acc;
+    __syncthreads();
+    if (on) {
+        const float* D = gp ? sD : sF;
+        const float* w = sW + (size_t)slot * ldr;
+        for (int q = 0; q < R; ++q) {
+            const float wq = w[q];
+            const float4 d = *(reinterpret_cast<const float4*>(D + (size_t)q * ldr) + quad);
+            acc.x = fmaf(wq, d.x, acc.x); acc.y = fmaf(wq, d.y, acc.y);
+            acc.z = fmaf(wq, d.z, acc.z); acc.w = fmaf(wq, d.w, acc.w);
         }
+        *(reinterpret_cast<float4*>(Tw + (size_t)p * ldr) + quad) = acc;
     }
 }
 
 cudaError_t c2c_launch_plane_corr_gram(const PlanView& v, const LeadInfo& lead, const float* Dmat, const float* T0, float* Tw,
                                        int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
 {
-    int parts = (2 * nsm + v.C0 - 1) / v.C0;
-    const long long maxparts = (v.ppc0 + 63) / 64;
-    if (parts > maxparts) parts = (int)maxparts;
-    if (parts < 1) parts = 1;
+    (void)nsm;
     const int q4 = ldr / 4, npp = 256 / q4;
+    const long long parts = (v.ppc0 + npp - 1) / npp;
     const size_t smem = ((size_t)2 * ldr * ldr + (size_t)npp * ldr) * sizeof(float);
     return c2c_launch_ex(plane_corr_gram_kernel, dim3((unsigned)(v.C0 * parts)), dim3(256), smem, st, pdl, v, lead, Dmat, T0, Tw, R,
-                         ldr, parts, done);
+                         ldr, (int)parts, done);
 }
 
 // CTA = (context c, part): Yo = sum over its planes with g = 1 of W[p] (x) W[p], Ym = the same over g = 0.
-// thread = (plane subgroup, 4 x 4 tile of the R x R matrix); the W rows of 64 planes at a time go through shared memory.
-#define C2C_LCG_BATCH 64
+// thread = (plane subgroup, 4 x 4 tile of the R x R matrix); the W rows of a batch of planes (normally the CTA's whole share)
+// go through shared memory.
 __global__ void __launch_bounds__(256)
-lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int parts, float* __restrict__ Ypart, const int* done)
+lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int parts, int batch, float* __restrict__ Ypart,
+                     const int* done)
 {
     pdl_trigger();
     pdl_wait();
@@ -390,9 +403,9 @@ lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int 
     extern __shared__ __align__(16) float lcg_smem[];
     const int q4 = ldr >> 2, ntile = q4 * q4, LL = ldr * ldr;
     const int nsub = blockDim.x / ntile;                               // >= 4 (ntile <= 64)
-    float* sW = lcg_smem;                                              // [BATCH][ldr]
-    int* sg = reinterpret_cast<int*>(sW + (size_t)C2C_LCG_BATCH * ldr); // [BATCH]
-    float* sRed = reinterpret_cast<float*>(sg + C2C_LCG_BATCH);        // [nsub][2][LL]
+    float* sW = lcg_smem;                                              // [batch][ldr]
+    int* sg = reinterpret_cast<int*>(sW + (size_t)batch * ldr);        // [batch]
+    float* sRed = reinterpret_cast<float*>(sg + batch);                // [nsub][2][LL]
     const int c = blockIdx.x / parts, part = blockIdx.x - c * parts;
     const long long per = (v.ppc0 + parts - 1) / parts;
     const long long p_begin = (long long)c * v.ppc0 + (long long)part * per;
@@ -403,8 +416,8 @@ lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int 
     float ao[16], am[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { ao[i] = 0.0f; am[i] = 0.0f; }
-    for (long long pb = p_begin; pb < p_end; pb += C2C_LCG_BATCH) {
-        const int nb = (int)(p_end - pb < C2C_LCG_BATCH ? p_end - pb : C2C_LCG_BATCH);
+    for (long long pb = p_begin; pb < p_end; pb += batch) {
+        const int nb = (int)(p_end - pb < batch ? p_end - pb : batch);
         __syncthreads();
         for (int t = threadIdx.x; t < nb * q4; t += blockDim.x) {
             const int pl = t / q4, quad = t - pl * q4;
@@ -452,7 +465,8 @@ lead_ctx_gram_kernel(const PlanView v, const LeadInfo lead, int R, int ldr, int 
     }
 }
 
-// Ymat[c] = sum of the parts' Yo of context c; Ymat[C0] = sum over all contexts and parts of Ym   (fixed order)
+// Ymat[c] = sum of the parts' Yo of context c (blocks 0 .. C0 - 1);  Ymat[C0] = sum over all contexts and parts of Ym (the
+// remaining blocks: 8 matrix entries each, a warp per entry, lanes stride the partials, fixed shuffle tree)
 __global__ void __launch_bounds__(256)
 ctx_gram_finalize_kernel(const float* __restrict__ Ypart, int C0, int parts, int LL, float* __restrict__ Ymat, const int* done)
 {
@@ -460,17 +474,25 @@ ctx_gram_finalize_kernel(const float* __restrict__ Ypart, int C0, int parts, int
     pdl_wait();
     if (run_done(done)) return;
     const int c = blockIdx.x;
-    for (int t = threadIdx.x; t < LL; t += blockDim.x) {
-        float s = 0.0f;
-        if (c < C0) {
+    if (c < C0) {
+        for (int t = threadIdx.x; t < LL; t += blockDim.x) {
+            float s = 0.0f;
             for (int k = 0; k < parts; ++k) s += Ypart[(((size_t)c * parts + k) * 2 + 0) * LL + t];
-        } else {
-            for (int cc = 0; cc < C0; ++cc)
-                for (int k = 0; k < parts; ++k) s += Ypart[(((size_t)cc * parts + k) * 2 + 1) * LL + t];
+            Ymat[(size_t)c * LL + t] = s;
         }
-        Ymat[(size_t)c * LL + t] = s;
+        return;
     }
+    const int lane = threadIdx.x & 31;
+    const int t = (c - C0) * 8 + (threadIdx.x >> 5);
+    if (t >= LL) return;
+    float s = 0.0f;
+    for (int k = lane; k < C0 * parts; k += 32) s += Ypart[((size_t)k * 2 + 1) * LL + t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) Ymat[(size_t)C0 * LL + t] = s;
 }
+
+static int lead_ctx_batch(int ldr) { const int b = 16384 / ldr; return b > 512 ? 512 : b; }
 
 int c2c_lead_ctx_parts(int C0, int nsm)
 {
@@ -483,16 +505,19 @@ cudaError_t c2c_launch_lead_ctx_gram(const PlanView& v, const LeadInfo& lead, in
 {
     const int parts = c2c_lead_ctx_parts(v.C0, nsm);
     const int q4 = ldr / 4, ntile = q4 * q4, nsub = 256 / ntile, LL = ldr * ldr;
-    const size_t smem = (size_t)C2C_LCG_BATCH * ldr * sizeof(float) + C2C_LCG_BATCH * sizeof(int) + (size_t)nsub * 2 * LL * sizeof(float);
+    const long long per = (v.ppc0 + parts - 1) / parts;
+    int batch = lead_ctx_batch(ldr);
+    if (batch > per) batch = (int)(per < 1 ? 1 : per);
+    const size_t smem = (size_t)batch * ldr * sizeof(float) + (size_t)batch * sizeof(int) + (size_t)nsub * 2 * LL * sizeof(float);
     if (smem > 48 * 1024) {
-        const cudaError_t ea = cudaFuncSetAttribute(lead_ctx_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        const cudaError_t ea = cudaFuncSetAttribute(lead_ctx_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         if (ea != cudaSuccess) return ea;
     }
     cudaError_t e = c2c_launch_ex(lead_ctx_gram_kernel, dim3((unsigned)(v.C0 * parts)), dim3(256), smem, st, pdl, v, lead, R, ldr, parts,
-                                  Ypart, done);
+                                  batch, Ypart, done);
     if (e != cudaSuccess) return e;
-    return c2c_launch_ex(ctx_gram_finalize_kernel, dim3(v.C0 + 1), dim3(256), 0, st, pdl, (const float*)Ypart, v.C0, parts, LL, Ymat,
-                         done);
+    return c2c_launch_ex(ctx_gram_finalize_kernel, dim3((unsigned)(v.C0 + (LL + 7) / 8)), dim3(256), 0, st, pdl, (const float*)Ypart,
+                         v.C0, parts, LL, Ymat, done);
 }
 
 #define C2C_PLAN_DISPATCH(CALL)                                                                                          \
@@ -502,8 +527,9 @@ cudaError_t c2c_launch_lead_ctx_gram(const PlanView& v, const LeadInfo& lead, in
         default: return cudaErrorNotSupported;                                                                           \
     }
 
-// thread = (position e, column quad): Uw[e, quad] = U0[e, quad] + sum_q B[e, q] * Z_e[q, quad],
-// Z_e = Y_missing + sum over the contexts c whose row s or column v the model misses of Y_c
+// a warp per (position e, column quad); lanes take the contexts (and the "missing planes" matrix, index C0):
+// Uw[e, quad] = U0[e, quad] + sum_q B[e, q] * Z_e[q, quad],  Z_e = Y_missing + sum over the contexts c whose row s or column
+// v the model misses of Y_c.  Lane sums are combined by a fixed shuffle tree.
 template <int NQ>
 __global__ void __launch_bounds__(256)
 fiber_corr_gram_kernel(const PlanView v, const float* __restrict__ A2, const float* __restrict__ A3, const float* __restrict__ Ymat,
@@ -513,7 +539,8 @@ fiber_corr_gram_kernel(const PlanView v, const float* __restrict__ A2, const flo
     pdl_wait();
     if (run_done(done)) return;
     constexpr int q4 = NQ / 4, LL = NQ * NQ;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= (long long)v.E * q4) return;
     const int e = (int)(t / q4), quad = (int)(t - (long long)e * q4);
     const int s = e / v.I3, vv = e - s * v.I3;
@@ -524,8 +551,8 @@ fiber_corr_gram_kernel(const PlanView v, const float* __restrict__ A2, const flo
         const float4 y = *(reinterpret_cast<const float4*>(A3 + (size_t)vv * NQ) + k);
         b[4 * k] = x.x * y.x; b[4 * k + 1] = x.y * y.y; b[4 * k + 2] = x.z * y.z; b[4 * k + 3] = x.w * y.w;
     }
-    float4 acc = __ldg(reinterpret_cast<const float4*>(U0 + (size_t)e * NQ) + quad);
-    for (int c = 0; c <= v.C0; ++c) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = lane; c <= v.C0; c += 32) {
         if (c < v.C0 && v.hs[c * v.I2 + s] && v.hv[c * v.I3 + vv]) continue;
         const float4* Y = reinterpret_cast<const float4*>(Ymat + (size_t)c * LL) + quad;
 #pragma unroll
@@ -537,14 +564,22 @@ fiber_corr_gram_kernel(const PlanView v, const float* __restrict__ A2, const flo
             }
         }
     }
-    *(reinterpret_cast<float4*>(Uw + (size_t)e * NQ) + quad) = acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane == 0) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(U0 + (size_t)e * NQ) + quad);
+        *(reinterpret_cast<float4*>(Uw + (size_t)e * NQ) + quad) = make_float4(u.x + acc.x, u.y + acc.y, u.z + acc.z, u.w + acc.w);
+    }
 }
 
 cudaError_t c2c_launch_fiber_corr_gram(const PlanView& v, const float* A2, const float* A3, const float* Ymat, const float* U0,
                                        float* Uw, int R, int ldr, const int* done, cudaStream_t st, int pdl)
 {
-    const long long n = (long long)v.E * (ldr / 4);
-    const dim3 grid((unsigned)((n + 255) / 256));
+    const long long n = (long long)v.E * (ldr / 4);                    // warps
+    const dim3 grid((unsigned)((n + 7) / 8));
 #define FCG_CALL(N) do { const cudaError_t e_ = c2c_launch_ex(fiber_corr_gram_kernel<N>, grid, dim3(256), 0, st, pdl, v, A2, A3, Ymat, U0, Uw, R, done); \
                          if (e_ != cudaSuccess) return e_; } while (0)
     C2C_PLAN_DISPATCH(FCG_CALL)
@@ -569,9 +604,10 @@ __device__ __forceinline__ float lead_weight32(unsigned p, const LeadInfo& lead,
     return w;
 }
 
+#define C2C_PLAN_PRELOAD 8
 // a warp per plane with residual entries: lanes stride the plane's list, B rows from shared memory (SMEM_B) or L1
 template <int NQ, bool SMEM_B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ Bmat, const float* Tin,
                        float* Tout, int R, const int* done)
 {
@@ -600,21 +636,30 @@ plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __res
         float w[NQ], acc[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) { w[q] = __shfl_sync(0xffffffffu, wl, q); acc[q] = 0.0f; }
-        for (int i = lane; i < n; i += 32) {
-            const int e = v.csr_ent[(size_t)b0 + i];
-            const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)e * NQ);
-            float b[NQ];
+        for (int i0 = 0; i0 < n; i0 += 32 * C2C_PLAN_PRELOAD) {
+            int ev[C2C_PLAN_PRELOAD];                                   // the list reads of a batch are in flight together
 #pragma unroll
-            for (int k = 0; k < NQ / 4; ++k) {
-                const float4 x = b4[k];
-                b[4 * k] = x.x; b[4 * k + 1] = x.y; b[4 * k + 2] = x.z; b[4 * k + 3] = x.w;
+            for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
+                const int i = i0 + u * 32 + lane;
+                ev[u] = i < n ? (int)v.csr_ent[(size_t)b0 + i] : -1;
             }
-            float r0 = 0.0f, r1 = 0.0f;
 #pragma unroll
-            for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
-            const float rec = r0 + r1;
+            for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
+                if (ev[u] < 0) continue;
+                const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)ev[u] * NQ);
+                float b[NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, b[q], acc[q]);
+                for (int k = 0; k < NQ / 4; ++k) {
+                    const float4 x = b4[k];
+                    b[4 * k] = x.x; b[4 * k + 1] = x.y; b[4 * k + 2] = x.z; b[4 * k + 3] = x.w;
+                }
+                float r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
+                const float rec = r0 + r1;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, b[q], acc[q]);
+            }
         }
         float mine = 0.0f;
 #pragma unroll
@@ -631,7 +676,8 @@ cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, 
 {
     const size_t bbytes = (size_t)v.E * ldr * sizeof(float);
     const bool smem_b = bbytes <= 100 * 1024;
-    long long grid = (v.P + 7) / 8;
+    const int block = ldr <= 16 ? 512 : 256;                           // <= 64 registers per thread at ldr <= 16: 32 warps per SM
+    long long grid = (v.P * 32 + block - 1) / block;
     if (grid > (long long)nsm * (smem_b ? 2 : 8)) grid = (long long)nsm * (smem_b ? 2 : 8);
 #define PCL_CALL(N)                                                                                                      \
     do {                                                                                                                 \
@@ -641,9 +687,9 @@ cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, 
                 e_ = cudaFuncSetAttribute(plane_corr_list_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
                 if (e_ != cudaSuccess) return e_;                                                                        \
             }                                                                                                            \
-            e_ = c2c_launch_ex(plane_corr_list_kernel<N, true>, dim3((unsigned)grid), dim3(256), bbytes, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+            e_ = c2c_launch_ex(plane_corr_list_kernel<N, true>, dim3((unsigned)grid), dim3(block), bbytes, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
         } else                                                                                                           \
-            e_ = c2c_launch_ex(plane_corr_list_kernel<N, false>, dim3((unsigned)grid), dim3(256), 0, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+            e_ = c2c_launch_ex(plane_corr_list_kernel<N, false>, dim3((unsigned)grid), dim3(block), 0, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
         if (e_ != cudaSuccess) return e_;                                                                                \
     } while (0)
     C2C_PLAN_DISPATCH(PCL_CALL)
@@ -693,9 +739,14 @@ fiber_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __res
             const int base = v.ell_off[(size_t)k * v.ngroups + gq];
             const int depth = v.ell_off[(size_t)k * v.ngroups + gq + 1] - base;
             const uint16_t* ent = v.ell_ent + (size_t)base * 32 + lane;
-            for (int d = 0; d < depth; ++d) {
-                const unsigned pl = ent[(size_t)d * 32];
-                if (pl != 0xFFFFu) {
+            for (int d0 = 0; d0 < depth; d0 += C2C_PLAN_PRELOAD) {
+                unsigned pls[C2C_PLAN_PRELOAD];
+#pragma unroll
+                for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) pls[u] = d0 + u < depth ? (unsigned)ent[(size_t)(d0 + u) * 32] : 0xFFFFu;
+#pragma unroll
+                for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
+                    const unsigned pl = pls[u];
+                    if (pl == 0xFFFFu) continue;
                     const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)pl * NQ);
                     float w[NQ];
 #pragma unroll

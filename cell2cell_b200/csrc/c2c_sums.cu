@@ -125,7 +125,7 @@ static cudaError_t launch_one(const ContractArgs& a, int nquads, int grid_max, c
     long long grid = (a.P + batch - 1) / batch;
     if (grid > grid_max) grid = grid_max;
     const size_t smem = 2 * (size_t)batch * NQ * sizeof(float);
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) return cudaErrorNotSupported;
     recon_sums_stream_kernel<NQ, THREADS, U><<<(unsigned)grid, THREADS, smem, st>>>(a.X, a.lead, a.A2, a.A3, a.P, a.I2, a.I3, a.R,
                                                                                a.ldr, nquads, (int)nslots, a.sums);
     *grid_out = (int)grid;

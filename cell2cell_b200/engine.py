@@ -14,7 +14,7 @@ from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, li
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
            "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
            "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "coupled_ncp_run", "build_ccc", "group_aggregate",
-           "MaskPlan", "mask_plan", "masked_contract_planned"]
+           "missing_rec_sumsq", "MaskPlan", "mask_plan", "masked_contract_planned", "ncp_run_multi", "multi_run_cost"]
 
 _vp = ctypes.c_void_p
 
@@ -224,6 +224,19 @@ def recon_sums(X, mask, factors, rank, ws=None):
         return out.cpu().numpy()
 
 
+def missing_rec_sumsq(X, mask, factors, rank, ws=None, out=None):
+    """``||(1 - mask) * reconstruction||^2`` as a 1-element fp64 CUDA tensor (no synchronisation): the squared norm of the
+    entries tensorly's imputation writes -- see ``c2c_missing_rec_sumsq``."""
+    _check_tensor(X, mask)
+    with torch.cuda.device(X.device):
+        if ws is None or not ws.fits(X.shape, rank, True):
+            ws = Workspace(X.shape, rank, True, X.device)
+        out = torch.zeros(1, dtype=torch.float64, device=X.device) if out is None else out
+        check(lib().c2c_missing_rec_sumsq(_ptr(X), _ptr(mask), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), rank,
+                                          _ptr(out), ws.ptr, ws.nbytes, _stream()), "c2c_missing_rec_sumsq")
+        return out
+
+
 def cp_normalize(factors, rank, weights=None):
     """In-place ``cp_normalize`` of packed factors; returns the weights (fp32 ``[rank]`` CUDA tensor)."""
     dev = factors[0].device
@@ -386,6 +399,75 @@ def ncp_run_batched(X, factors, run_ranks, n_iter_max=100, tol=1e-6, cvg_criteri
         else:
             iters = st[2 + nruns:2 + 2 * nruns].astype(np.int64)
         return errors.cpu().numpy(), iters
+
+
+def multi_run_cost(shape, ranks, n_iter_max=100, n_sm=148):
+    """(seconds as a grid of one-CTA runs, seconds as whole-GPU factorizations of bins of runs): a coarse model used to choose
+    between ``ncp_run_multi`` and ``ncp_run`` / ``ncp_run_batched``, calibrated on B200 (gpurun_out r02c: 250 runs x 100
+    iterations, ranks 1-25: BALF 0.138 s, ASD 2.1 s as a grid of CTAs) -- a CTA does 2 N_X ldr FMAs per iteration at ~8 % of an
+    SM's FMA rate with 2 CTAs per SM; a whole-GPU iteration of a bin of <= 28 factor columns costs two HBM-speed passes but at
+    least ~110 us of launch-bound kernels."""
+    n_x = float(np.prod([int(s) for s in shape]))
+    per_cta = [2.0 * n_x * ldr_of(r) / (128 * 1.9e9 * 0.08) for r in ranks]
+    multi = max(n_iter_max * max(per_cta), n_iter_max * sum(per_cta) / n_sm)
+    bins = max(1, -(-int(sum(ranks)) // 28)) if len(ranks) > 1 else 1
+    whole = bins * n_iter_max * max(110e-6, 1.45 * 2.0 * n_x * 4 / 5.5e12 + 30e-6)
+    return multi, whole
+
+
+def ncp_run_multi(X, inits, n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error", norm_x2=None):
+    """Independent MU factorizations of a small (L2-resident) tensor as ONE kernel launch, a CTA per run
+    (``c2c_ncp_run_multi``).  ``inits``: one list of host ``[I_k, rank_b]`` arrays per run (any ranks <= 32).
+    Returns ``[(factors (host fp32 arrays), errors float64 [n_iter], n_iter, converged, sums [5]), ...]`` in the order given.
+    Raises ``C2CError`` with ``code == -61`` when the shape is outside this path."""
+    _check_tensor(X, None)
+    if cvg_criterion not in CVG:
+        raise C2CError("cvg_criterion %r is not one of %s" % (cvg_criterion, sorted(CVG)))
+    nruns, nd = len(inits), X.dim()
+    ranks = [int(np.asarray(f[0]).shape[1]) for f in inits]
+    # the kernel takes the runs in grid order: the most expensive first
+    order = sorted(range(nruns), key=lambda b: (-ranks[b], b))
+    shape = [int(s) for s in X.shape]
+    offs, total = [], 0
+    for b in order:
+        ldr = ldr_of(ranks[b])
+        row = []
+        for k in range(nd):
+            row.append(total)
+            total += shape[k] * ldr
+        offs.append(row)
+    host = np.zeros(total, dtype=np.float32)
+    for b, row in zip(order, offs):
+        ldr = ldr_of(ranks[b])
+        for k in range(nd):
+            f = np.abs(np.asarray(inits[b][k], dtype=np.float32))
+            host[row[k]:row[k] + shape[k] * ldr].reshape(shape[k], ldr)[:, :ranks[b]] = f
+    with torch.cuda.device(X.device):
+        flat = torch.from_numpy(host).to(X.device)
+        n_it = max(int(n_iter_max), 1)
+        ranks_arr = (ctypes.c_int * nruns)(*[ranks[b] for b in order])
+        nbytes = int(lib().c2c_ncp_multi_workspace_bytes(nd, _shape_arr(shape), ranks_arr, nruns))
+        if nbytes == 0:
+            check(-61, "c2c_ncp_multi_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+        errors = torch.zeros((nruns, n_it), dtype=torch.float64, device=X.device)
+        state = torch.zeros((nruns, 2), dtype=torch.int32, device=X.device)
+        sums = torch.zeros((nruns, 5), dtype=torch.float64, device=X.device)
+        nx2 = torch.tensor([float(norm_x2) if norm_x2 is not None else sumsq(X)], dtype=torch.float64, device=X.device)
+        base = flat.data_ptr()
+        ptrs = (_vp * (nruns * nd))(*[base + 4 * o for row in offs for o in row])
+        check(lib().c2c_ncp_run_multi(_ptr(X), nd, _shape_arr(shape), ptrs, ranks_arr, nruns, n_it, float(tol), CVG[cvg_criterion],
+                                      _ptr(nx2), _ptr(errors), _ptr(state), _ptr(sums), _ptr(ws), nbytes, _stream()),
+              "c2c_ncp_run_multi")
+        out_host = flat.cpu().numpy()
+        errs, st, sm = errors.cpu().numpy(), state.cpu().numpy(), sums.cpu().numpy()
+    res = [None] * nruns
+    for j, (b, row) in enumerate(zip(order, offs)):
+        ldr = ldr_of(ranks[b])
+        fs = [out_host[row[k]:row[k] + shape[k] * ldr].reshape(shape[k], ldr)[:, :ranks[b]].copy() for k in range(nd)]
+        n_iter = int(st[j, 0])
+        res[b] = (fs, errs[j, :n_iter].copy(), n_iter, bool(st[j, 1]), sm[j].copy())
+    return res
 
 
 def coupled_ncp_run(X1, mask1, factors1, X2, mask2, factors2, rank, shared_pairs, n_iter_max=100, tol=1e-6,

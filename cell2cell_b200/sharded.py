@@ -81,6 +81,9 @@ class DeviceOps:
     def recon_sums(self, X, mask, factors, ws):
         return engine.recon_sums(X, mask, factors, self.R, ws=ws)
 
+    def missing_rec_sumsq(self, X, mask, factors, ws, out=None):
+        return engine.missing_rec_sumsq(X, mask, factors, self.R, ws=ws, out=out)
+
 
 def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter_max=100, tol=1e-6, group=None, ops=None,
                                  cvg_criterion="abs_rec_error"):

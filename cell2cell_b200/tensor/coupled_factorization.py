@@ -179,6 +179,10 @@ def _coupled_mu(X1, X2, M1, M2, init1, init2, rank, shared_pairs, n_iter_max, to
     order = _update_order(s1.nd, s2.nd, shared_pairs)
     nx2 = torch.tensor([getattr(X, "_c2c_norm_x2", None) or ops.sumsq(X) for X in (X1, X2)], dtype=torch.float64, device=dev)
     iprod = torch.zeros(2, dtype=torch.float64, device=dev)
+    # masked tensors: squared norm of the entries the last imputation of the iteration writes.  tensorly's error_calc is
+    # called without an MTTKRP (coupled_factorization.py:420-431): the direct norm of (imputed tensor - reconstruction), whose
+    # ||imputed||^2 is ||mask * X||^2 plus this term
+    miss2 = torch.zeros(2, dtype=torch.float64, device=dev)
     err_dev = torch.zeros(2, dtype=torch.float64, device=dev)
     n_it = max(int(n_iter_max), 1)
     hist_dev = torch.zeros((n_it, 2), dtype=torch.float64, device=dev)
@@ -193,12 +197,16 @@ def _coupled_mu(X1, X2, M1, M2, init1, init2, rank, shared_pairs, n_iter_max, to
                 s2.updated(b)
             else:
                 last = k == len(order) - 1
+                if last:
+                    for j, sd in enumerate((s1, s2)):
+                        if sd.mask is not None:
+                            ops.missing_rec_sumsq(sd.X, sd.mask, sd.A, sd.ws, out=miss2[j:j + 1])
                 ops.mu_update_coupled(s1.A[a], s2.A[b], s1.mttkrp(a), s2.mttkrp(b), s1.gram(a)[0], s2.gram(b)[0],
                                       iprod if last else None)
                 s1.updated(a)
                 s2.updated(b)
         rn2 = torch.cat([s1.gram(-1)[1].reshape(1), s2.gram(-1)[1].reshape(1)]).to(torch.float64)
-        err_dev.copy_(torch.sqrt(torch.abs(nx2 + rn2 - 2.0 * iprod)) / torch.sqrt(nx2))
+        err_dev.copy_(torch.sqrt(torch.abs(nx2 + miss2 + rn2 - 2.0 * iprod)) / torch.sqrt(nx2))
 
     if cvg_criterion == "abs_rec_error":
         rule = lambda d: abs(d) < tol                                 # noqa: E731
@@ -275,6 +283,12 @@ def coupled_non_negative_parafac(tensor1, tensor2, rank, mode_mapping, mask1=Non
         raise ValueError("A mode can be shared only once")
     M1 = as_device_mask(mask1, X1)
     M2 = as_device_mask(mask2, X2)
+    # the reference multiplies by the mask before every use (:342-343): values under a zero mask byte never matter.  The
+    # device path needs zeros there (the error's imputed-entry term is accumulated with x taken as 0)
+    if M1 is not None:
+        X1 = X1 * M1
+    if M2 is not None:
+        X2 = X2 * M2
     w1, w2 = _balance_weights(X1.shape, X2.shape, shared_pairs, balance_errors)
     if not isinstance(init, str):
         raise ValueError("coupled factorization takes init='svd' or init='random'")

@@ -120,6 +120,35 @@ def _factorize_batch(X, runs, n_iter_max, tol, cvg_criterion="abs_rec_error", ch
     return out
 
 
+def _multi_eligible(X, ranks, n_iter_max):
+    """Small tensor, several runs: the one-CTA-per-run kernel beats whole-GPU kernels run after run (engine.multi_run_cost)."""
+    if len(ranks) < 2 or max(ranks) > 32 or X.dim() < 3 or max(int(X.shape[-1]), int(X.shape[-2])) > 128:
+        return False
+    if X.numel() * 4 > 96e6:                                 # the grid of CTAs streams the tensor from L2
+        return False
+    multi, whole = engine.multi_run_cost(X.shape, ranks, n_iter_max)
+    return multi < whole
+
+
+def _factorize_multi(X, runs, n_iter_max, tol, cvg_criterion="abs_rec_error"):
+    """The factorizations ``runs = [(rank, seed), ...]`` as ONE launch of the one-CTA-per-run kernel (``c2c_ncp_run_multi``).
+    Same results as the corresponding ``non_negative_parafac(init='random')`` calls, to rounding.  Returns
+    ``[(CPTensor, errors), ...]`` in the order of ``runs``; raises ``C2CError`` (code -61) if the shape is outside that path."""
+    inits = [initialize_factors(X, r, init="random", random_state=sd) for r, sd in runs]
+    res = engine.ncp_run_multi(X, inits, n_iter_max=int(n_iter_max), tol=float(tol) if tol else -1.0,
+                               cvg_criterion=cvg_criterion, norm_x2=getattr(X, "_c2c_norm_x2", None))
+    out = []
+    for (rank, _), (fs, errs, n_iter, _conv, sums) in zip(runs, res):
+        errs = np.array(errs, dtype=np.float64)
+        if len(errs):
+            errs[-1] = np.sqrt(sums[1]) / np.sqrt(sums[3])    # the kept error: directly accumulated (as _factorize does)
+        cp = CPTensor(np.ones(rank, dtype=np.float32), fs, device=X.device)
+        if len(errs):
+            cp.recon_sums_ = sums
+        out.append((cp, [np.float64(e) for e in errs]))
+    return out
+
+
 def _pack_runs(runs, capacity=28):
     """First-fit-decreasing packing of ``(rank, run)`` units into bins of at most ``capacity`` factor columns (a pass over
     the tensor costs about the same for 17 columns as for 28, so fuller bins mean fewer passes; past 28 columns the fiber pass
@@ -328,7 +357,15 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
     batchable = (tf_type == "non_negative_cp" and M is None and init == "random" and random_state is not None and
                  set(kwargs) <= {"return_errors", "cvg_criterion"} and X.dim() >= 3 and batch_runs)
     all_units = [(r, run) for r in range(1, upper_rank + 1) for run in range(runs)]
-    if batchable:
+    multi = batchable and upper_rank <= 32 and _multi_eligible(X, [r for r, _ in all_units], n_iter_max)
+    if multi:
+        # small tensor: every run is one CTA of a single launch; with several GPUs each takes a cost-balanced share
+        from ..parallel import world, lpt_schedule
+        _, size = world()
+        owner = lpt_schedule([engine.ldr_of(r) for r, _ in all_units], size)
+        units = [[u for u, w in zip(all_units, owner) if w == k] for k in range(size)]
+        units = [u for u in units if u]
+    elif batchable:
         units = _pack_runs([u for u in all_units if u[0] <= 32]) + [[u] for u in all_units if u[0] > 32]
     else:
         units = [[u] for u in all_units]
@@ -340,7 +377,14 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
 
     def one(unit):
         res = None
-        if len(unit) > 1:
+        if multi:
+            try:
+                res = _factorize_multi(X, [(r, random_state + run) for r, run in unit], n_iter_max, tol,
+                                       cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
+            except C2CError as err:
+                if getattr(err, "code", 0) != -61:
+                    raise
+        elif len(unit) > 1:
             try:
                 res = _factorize_batch(X, [(r, random_state + run) for r, run in unit], n_iter_max, tol,
                                        cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
@@ -354,6 +398,8 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
 
     def cost(unit):
         cols = sum(r for r, _ in unit)
+        if multi:
+            return float(sum(engine.ldr_of(r) for r, _ in unit))
         return (1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)) if len(unit) > 1 or cols <= 32 else cols / 16.0
 
     parts = run_units(units, one, cost=cost, gather="object", threads=host_threads)

@@ -140,7 +140,7 @@ class BaseTensor:
         kwargs = dict(kwargs or {})
         kwargs["return_errors"] = True
         from ..parallel import run_units
-        from .factorization import _factorize_batch, _pack_runs
+        from .factorization import _factorize_batch, _factorize_multi, _multi_eligible, _pack_runs
         from .._lib import C2CError
 
         def one(run):
@@ -166,7 +166,32 @@ class BaseTensor:
             except C2CError:                      # shape outside the fused update kernels: run by run on the device instead
                 return [(run,) + one(run) for _, run in unit]
 
-        if batchable:
+        multi = batchable_multi = False
+        if (batch_runs and runs > 1 and tf_type == "non_negative_cp" and self.mask is None and init == "random" and
+                random_state is not None and set(kwargs) <= {"return_errors", "cvg_criterion"} and int(rank) <= 32):
+            batchable_multi = _multi_eligible(self.tensor, [int(rank)] * runs, n_iter_max)
+
+        def one_share(unit):
+            try:
+                res = _factorize_multi(self.tensor, [(int(rank), random_state + run) for run in unit], n_iter_max, tol,
+                                       cvg_criterion=kwargs.get("cvg_criterion", "abs_rec_error"))
+                return [(run, float(errs[-1]), tf_) for run, (tf_, errs) in zip(unit, res)]
+            except C2CError as err:
+                if getattr(err, "code", 0) != -61:
+                    raise
+                return [(run,) + one(run) for run in unit]
+
+        if batchable_multi:
+            # small tensor: every run is one CTA of a single launch (per GPU of the job)
+            from ..parallel import world
+            _, size = world()
+            shares = [list(range(k, runs, size)) for k in range(size) if k < runs]
+            parts = run_units(shares, one_share, gather="object")
+            results = [(err, tf_) for _, err, tf_ in sorted((r for part in parts for r in part), key=lambda r: r[0])]
+            multi = True
+        if multi:
+            pass
+        elif batchable:
             parts = run_units(_pack_runs([(int(rank), run) for run in range(runs)]), one_bin, gather="object")
             results = [(err, tf_) for _, err, tf_ in sorted((r for part in parts for r in part), key=lambda r: r[0])]
         else:

@@ -150,7 +150,9 @@ int c2c_mu_update_coupled(float* A1_mode, float* A2_mode, const float* M1, const
  * a shared factor and both receive the update.  An unmasked tensor is read twice per iteration whatever the order (its
  * plane / fiber contractions are reused until a factor they depend on changes); a masked one once per mode.
  * errors: device double[2 * n_iter_max], errors[2 it + k] = Gram-form error of tensor k after iteration it
- * (tensorly error_calc, :473-485); the stop rule (:487-509) runs on (w1 e1 + w2 e2) / (w1 + w2).
+ * (tensorly error_calc, :420-431; for a masked tensor the direct form on the re-imputed tensor: the Gram form plus the
+ * squared norm of the imputed entries); the stop rule (:437-458) runs on (w1 e1 + w2 e2) / (w1 + w2).  A masked tensor must hold
+ * zeros at its missing entries.
  * state: device int[2] = {iterations done, converged}.  normX2: device double[2] (||X1||^2, ||X2||^2) or NULL.
  * ws1 / ws2: one workspace per tensor (c2c_ncp_workspace_bytes(shape_k, rank, mask_k != NULL)).  rank <= 32. */
 int c2c_coupled_ncp_run(const float* X1, const uint8_t* mask1, int ndim1, const int64_t* shape1 /*host*/, float* const* A1 /*host array*/,
@@ -170,6 +172,14 @@ int c2c_hals_update(float* A_mode, const float* M, const float* G, int64_t I, in
 int c2c_recon_sums(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
                    const float* const* A /*host array*/, int ldr, int rank, double* out,
                    void* ws, size_t ws_bytes, void* stream);
+
+/* out (device double) = ||(1 - mask) * reconstruction||^2: the squared norm of the entries tensorly's imputation
+ * `tensor*mask + cp_to_tensor(cp, mask=1-mask)` writes (coupled_factorization.py:342-343).  The coupled factorization's error is
+ * error_calc WITHOUT an MTTKRP (coupled_factorization.py:420-431), i.e. the direct norm of (imputed tensor - reconstruction):
+ * ||imputed||^2 = ||mask * X||^2 + this term. */
+int c2c_missing_rec_sumsq(const float* X, const uint8_t* mask, int ndim, const int64_t* shape /*host*/,
+                          const float* const* A /*host array*/, int ldr, int rank, double* out, void* ws, size_t ws_bytes,
+                          void* stream);
 
 /* ---- K8: cp_normalize (cell2cell/tensor/tensor.py:327): unit-norm columns in place, norms multiplied into
  * weights [rank] (device, fp32; input value = current weights, folded into factor 0 first). */
@@ -199,6 +209,21 @@ int c2c_ncp_run(const float* X, const uint8_t* mask, int ndim, const int64_t* sh
 int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shape, float* const* A, int ldr, const int* run_ranks, int nruns,
                         int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
                         int check_every, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- small tensors: a grid of independent factorizations, one CTA each ---------------------------------------------------
+ * The double loop of _multiple_runs_elbow_analysis (cell2cell/tensor/factorization.py:335-352) and the best-of-runs loop of
+ * compute_tensor_factorization (cell2cell/tensor/tensor.py:294-320) on tensors small enough to stay in L2 (BALF-sized: a few
+ * MB): every run is one CTA that runs ALL its iterations -- both contractions, the multiplicative updates of every mode, the
+ * Gram-form error and the stop rule (semantics of c2c_ncp_run, unmasked MU) -- with no launches or grid syncs in between; the
+ * grid is the list of runs (order = launch order: put the most expensive first).
+ * A: host array of nruns * ndim device pointers, A[b * ndim + k] = factor k of run b, [I_k x ldr_b] with ldr_b = ranks[b]
+ * rounded up to 4.  errors: device double[nruns * n_iter_max]; state: device int[2 * nruns] = {iterations, converged} per run;
+ * sums: device double[5 * nruns] (or NULL) = the c2c_recon_sums values of each run's final factors.  normX2: device double.
+ * Returns -61 when the shape is outside this path (trailing modes > 128, rank > 32, shared memory). */
+size_t c2c_ncp_multi_workspace_bytes(int ndim, const int64_t* shape /*host*/, const int* ranks /*host*/, int nruns);
+int c2c_ncp_run_multi(const float* X, int ndim, const int64_t* shape /*host*/, float* const* A /*host array*/,
+                      const int* ranks /*host*/, int nruns, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
+                      double* errors, int* state, double* sums, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- mask plan: the masked factorization without a pass over the mask ---------------------------------------------------
  * tensorly re-imputes the missing entries with the current reconstruction before every mode's MTTKRP

@@ -68,11 +68,12 @@ def combined_error(error1, error2, shape1, shape2, shared_pairs, balance_errors=
 
 def error_calc(tensor, norm_tensor, weights, factors):
     """tensorly.decomposition._cp.error_calc(sparsity=None, mask=None, mttkrp=None) as called at
-    coupled_factorization.py:473-485: Gram-form ||X - cp|| with the inner product taken through a fresh MTTKRP of the
-    last mode."""
-    m = o.mttkrp(tensor, None, factors, tensor.ndim - 1)
-    iprod = np.sum(np.sum(m * factors[-1], axis=0) * weights)
-    return np.sqrt(np.abs(norm_tensor ** 2 + o.cp_norm(weights, factors) ** 2 - 2 * iprod))
+    coupled_factorization.py:420-431: with no MTTKRP passed in, tensorly builds the full reconstruction and returns the
+    DIRECT norm ||tensor - cp||.  ``tensor`` is the array the loop has been re-imputing (observed entries of the input, the
+    reconstruction of the factors before the tensor's last update at the missing ones), ``norm_tensor`` the norm of the
+    tensor as passed in -- so for a masked tensor the value differs from the Gram form on ``norm_tensor`` by the squared
+    norm of the imputed entries."""
+    return np.sqrt(np.sum((tensor - o.cp_to_tensor(weights, factors)) ** 2))
 
 
 def coupled_non_negative_parafac(tensor1, tensor2, rank, mode_mapping, mask1=None, mask2=None, n_iter_max=100,

@@ -64,9 +64,13 @@ def _add_coupled_shim(tl):
                                                          random_state=random_state))
 
     def error_calc(tensor, norm_tensor, weights, factors, sparsity, mask, mttkrp=None):
+        # tensorly.decomposition._cp.error_calc: "If mttkrp=None or masking is being performed, then the full tensor must be
+        # constructed": the DIRECT norm of (tensor - reconstruction); the Gram form is used only when an MTTKRP is passed in.
+        # The reference calls it with mttkrp=None (coupled_factorization.py:420-431) on the tensor it has been re-imputing.
         assert not sparsity and mask is None
         if mttkrp is None:
-            mttkrp = o.mttkrp(tensor, None, factors, np.ndim(tensor) - 1)
+            low_rank = o.cp_to_tensor(weights, factors)
+            return np.sqrt(np.sum((np.asarray(tensor, dtype=np.float64) - low_rank) ** 2)), tensor, norm_tensor
         iprod = np.sum(np.sum(mttkrp * factors[-1], axis=0) * weights)
         return np.sqrt(np.abs(norm_tensor ** 2 + o.cp_norm(weights, factors) ** 2 - 2 * iprod)), tensor, norm_tensor
 

@@ -123,6 +123,14 @@ class NumpyOps:
             iprod[1] = float((M2.numpy() * new).sum())
         return A1
 
+    def missing_rec_sumsq(self, X, mask, factors, ws, out=None):
+        rec = o.cp_to_tensor(None, [f.numpy() for f in factors], mask=1 - mask.numpy().astype(np.float64))
+        val = torch.tensor([float((rec * rec).sum())], dtype=torch.float64)
+        if out is not None:
+            out.copy_(val)
+            return out
+        return val
+
     def recon_sums(self, X, mask, factors, ws):
         x = X.numpy().astype(np.float64)
         d = x - o.cp_to_tensor(None, [f.numpy() for f in factors])
