@@ -57,7 +57,10 @@ def test_multi_runs_stop_on_their_own():
         fs, errs, it, conv, sums = res[i]
         assert conv and it == len(errs) < 300
         assert abs(it - len(oerr)) <= 2, (it, len(oerr))
-        np.testing.assert_allclose(errs[:min(it, len(oerr)) - 1], oerr[:min(it, len(oerr)) - 1], rtol=1e-4, atol=3e-6)
+        # the Gram-form error cancels in fp32 once it is small (||X||^2 + ||rec||^2 - 2<X, rec> from fp32 factors): the
+        # SQUARED error carries an absolute uncertainty of a few fp32 eps, so that is what is compared
+        n = min(it, len(oerr)) - 1
+        np.testing.assert_allclose(errs[:n] ** 2, np.asarray(oerr[:n]) ** 2, rtol=2e-4, atol=5e-7)
 
 
 def test_elbow_and_best_of_runs_use_the_multi_kernel_and_agree_with_run_by_run():
