@@ -61,6 +61,10 @@ SIGNATURES = {
     "c2c_ncp_multi_workspace_bytes": (_sz, [_i, _c.POINTER(_i64), _c.POINTER(_i), _i]),
     "c2c_ncp_run_multi": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _c.POINTER(_i), _i, _i, _c.c_double, _i, _p, _p, _p, _p,
                                _p, _sz, _p]),
+    "c2c_shard_comm_bytes": (_sz, [_i, _c.POINTER(_i64), _i, _i]),
+    "c2c_enable_peer_access": (_i, [_i]),
+    "c2c_ncp_run_sharded": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _c.c_double, _i, _p, _p, _p, _i, _p, _sz,
+                                 _i, _i, _c.POINTER(_p), _sz, _c.c_uint, _p]),
     "c2c_mask_plan_header_bytes": (_sz, [_i, _c.POINTER(_i64)]),
     "c2c_mask_plan_scan": (_i, [_p, _p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p]),
     "c2c_mask_plan_fill": (_i, [_p, _i, _c.POINTER(_i64), _p, _sz, _c.POINTER(_i64), _p, _sz, _p]),

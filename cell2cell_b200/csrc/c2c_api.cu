@@ -21,6 +21,7 @@
 #include "c2c_corr.cuh"
 #include "c2c_plan.cuh"
 #include "c2c_multi.cuh"
+#include "c2c_xgpu.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -503,8 +504,10 @@ struct PassOpts {
     bool t_zeroed;             // plane_mma: T was cleared by the previous fiber_mma (else a memset is enqueued)
     float* zero_T;             // fiber_mma: buffer to clear for the next plane_mma, `zero_n` floats
     long long zero_n;
+    const XgComm* xg;          // context-sharded run: the partial U is summed over the ranks inside the reduce kernel (c2c_xgpu.cuh)
+    double* xg_S; const int* xg_state; int xg_N;
 };
-static const PassOpts kPlainPass = {0, false, nullptr, 0};
+static const PassOpts kPlainPass = {0, false, nullptr, 0, nullptr, nullptr, nullptr, 0};
 static int use_pdl() { static int v = -1; if (v < 0) v = env_int("C2C_B200_NO_PDL", 0) ? 0 : 1; return v; }
 
 // T[P x ldr] = plane contraction of Xh with the two trailing factors
@@ -632,6 +635,17 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         }
     }
     const long long n4 = g.E * a.ldr / 4;
+    if (po.xg != nullptr) {
+        FiberXgArgs fx;
+        fx.part = w.part; fx.nparts = (int)nparts; fx.n4 = n4; fx.R = a.R; fx.ldr = a.ldr; fx.N = po.xg_N; fx.nl = a.lead.nl;
+        fx.U = w.U; fx.S = po.xg_S; fx.state = po.xg_state; fx.done = a.done;
+        long long grid_x = (n4 + 31) / 32;
+        if (grid_x > 2LL * sm_count()) grid_x = 2LL * sm_count();
+        const cudaError_t e = c2c_launch_ex(fiber_reduce_xg_kernel, dim3((unsigned)grid_x), dim3(256), 0, st, legacy ? 0 : po.pdl, fx, *po.xg);
+        if (e != cudaSuccess) return cuda_fail(e, "fiber_reduce_xg launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     {
         const cudaError_t e = c2c_launch_ex(fiber_reduce2_kernel, dim3((unsigned)((n4 + 31) / 32)), dim3(256), 0, st, legacy ? 0 : po.pdl,
                                             (const float*)w.part, (int)nparts, n4, a.R, a.ldr, w.U, a.done);
@@ -1099,6 +1113,7 @@ struct RunCtx {
     bool corr;                 // masked run as unmasked dense passes + missing-entry corrections (c2c_corr.cu)
     bool plan;                 // ... with the corrections taken from a mask plan (c2c_plan.cu): Gram form + residual lists
     PlanView pv; long long n_resid; bool model_missing;
+    const XgComm* xg;          // context-sharded run over peer memory (c2c_xgpu.cuh); null: one GPU
 };
 
 static int update_mode(const RunCtx& c, int mode, bool last)
@@ -1139,13 +1154,23 @@ static int launch_lead_update(const RunCtx& c, int mode)
     const int block = cnt >= 1024 ? 1024 : 256;
     const int tpr = cnt >= 512 ? block : 32;                         // CTA per row / warp per row
     const int nrc = block / tpr;
-    long long rows = (I + 2LL * sm_count() - 1) / (2LL * sm_count());
+    const bool xg = c.xg != nullptr && mode >= 1;                    // replicated mode of a context-sharded run
+    // (the exchange inside lead_update_xg has every CTA wait for the peers' CTA of the same index: all of them resident)
+    const long long ctas = (xg && block == 1024) ? sm_count() : 2LL * sm_count();
+    long long rows = (I + ctas - 1) / ctas;
     rows = (rows + nrc - 1) / nrc * nrc;
     u.rows_per_cta = (int)rows;
     const long long grid = (I + rows - 1) / rows;
     const int njr = tpr / (c.ldr / 4);
     if (njr < 1) return fail(-30, "rank too large for the fused update");
     const size_t smem = (((size_t)(c.R * c.R + nrc * c.ldr) * sizeof(float) + 7) & ~(size_t)7) + (size_t)nrc * njr * c.ldr * sizeof(double);
+    if (xg) {
+        if (grid > C2C_XG_MAX_CTAS) return fail(-70, "sharded run: too many CTAs in an exchange");
+        const cudaError_t e = c2c_launch_ex(lead_update_xg_kernel, dim3((unsigned)grid), dim3(block), smem, c.st, c.pdl, u, tpr, *c.xg);
+        if (e != cudaSuccess) return cuda_fail(e, "lead_update_xg launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
     {
         const cudaError_t e = c2c_launch_ex(lead_update_kernel, dim3((unsigned)grid), dim3(block), smem, c.st, c.pdl, u, tpr);
         if (e != cudaSuccess) return cuda_fail(e, "lead_update launch");
@@ -1348,6 +1373,7 @@ static int enqueue_iteration(const RunCtx& c)
             PassOpts po = kPlainPass;
             po.pdl = c.pdl;
             if (c.mma_zero) { po.t_zeroed = true; po.zero_T = c.w.T; po.zero_n = g.P * c.ldr; }
+            if (c.xg != nullptr && mode == nlead) { po.xg = c.xg; po.xg_S = c.w.S; po.xg_state = c.state; po.xg_N = g.ndim; }
             if (mode < nlead) { if ((rc = launch_plane(g, a, masked, c.w.T, c.st, po)) != 0) return rc; }
             else              { if ((rc = launch_fiber(g, a, masked, c.w, c.st, po)) != 0) return rc; }
         }
@@ -1374,9 +1400,10 @@ static int plan_dims(const Geo& g, long long* P, int* E, int* I2, int* I3, int* 
 static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int64_t* shape, float* const* A, int ldr,
                         int rank, int algo, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
                         double* errors, int* state, int check_every, void* ws, size_t ws_bytes, void* stream,
-                        const int* run_ranks, int nruns, const PlanRef* plan = nullptr)
+                        const int* run_ranks, int nruns, const PlanRef* plan = nullptr, const XgComm* xg = nullptr)
 {
     RunCtx c; int rc;
+    c.xg = xg;
     const bool masked_ws = mask != nullptr;
     if (!shape) return fail(-1, "shape is NULL");
     if ((rc = make_geo(c.g, ndim, shape, rank)) != 0) return rc;
@@ -1447,6 +1474,9 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     // Grams of the initial factors (fused updates: into bank 1, bank 0 cleared for iteration 0); G for mode 0
     const bool fused = fused_updates(c);
     if (nruns > 1 && !fused) return fail(-28, "batched runs need the fused update kernels (rank <= 32, small trailing modes)");
+    if (xg != nullptr && (!fused || mask != nullptr || nruns > 1 || ndim < 4 || !normX2))
+        return fail(-71, "sharded run: unmasked multiplicative updates of a tensor with >= 2 leading modes at rank <= 32, "
+                         "with the norm of the WHOLE tensor given");
     const size_t bank = (size_t)ndim * ldr * ldr;
     if (fused) CK(cudaMemsetAsync(c.w.S, 0, bank * sizeof(double), st), "memset Gram bank");
     for (int k = 0; k < ndim; ++k) {
@@ -1545,6 +1575,54 @@ extern "C" int c2c_ncp_run_batched(const float* X, int ndim, const int64_t* shap
     if (total < 1 || total > 32) return fail(-26, "batched runs: the run ranks must add up to 1..32, got %lld", total);
     return ncp_run_impl(X, nullptr, ndim, shape, A, ldr, (int)total, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion,
                         normX2, errors, state, check_every, ws, ws_bytes, stream, run_ranks, nruns);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// one factorization sharded along the first mode over the GPUs of a box (c2c_xgpu.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" size_t c2c_shard_comm_bytes(int ndim, const int64_t* shape, int rank, int world)
+{
+    if (!shape || ndim < 4 || ndim > C2C_MAX_DIMS || rank < 1 || rank > 32 || world < 1 || world > C2C_XG_MAX_WORLD) return 0;
+    XgComm x;
+    xg_layout(x, ndim - 2, shape, (long long)shape[ndim - 2] * shape[ndim - 1], ldr_of(rank), world);
+    return (size_t)x.total;
+}
+
+extern "C" int c2c_enable_peer_access(int peer_device)
+{
+    int dev = -1;
+    CK(cudaGetDevice(&dev), "cudaGetDevice");
+    if (peer_device == dev) return 0;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, dev, peer_device), "cudaDeviceCanAccessPeer");
+    if (!can) return fail(-72, "device %d cannot access the memory of device %d", dev, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+    return 0;
+}
+
+extern "C" int c2c_ncp_run_sharded(const float* X_local, int ndim, const int64_t* local_shape, float* const* A, int ldr, int rank,
+                                   int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
+                                   int check_every, void* ws, size_t ws_bytes, int world, int me, void* const* comm, size_t comm_bytes,
+                                   unsigned int epoch_base, void* stream)
+{
+    if (!local_shape) return fail(-1, "shape is NULL");
+    if (world < 1 || world > C2C_XG_MAX_WORLD || me < 0 || me >= world) return fail(-73, "sharded run: world %d / rank %d out of range (<= %d GPUs)", world, me, C2C_XG_MAX_WORLD);
+    if (ndim < 4 || ndim > C2C_MAX_DIMS) return fail(-71, "sharded run: the tensor needs at least two leading modes (ndim >= 4)");
+    if (!comm) return fail(-73, "sharded run: comm is NULL");
+    XgComm x;
+    memset(&x, 0, sizeof(x));
+    xg_layout(x, ndim - 2, local_shape, (long long)local_shape[ndim - 2] * local_shape[ndim - 1], ldr, world);
+    if (comm_bytes < (size_t)x.total) return fail(-73, "sharded run: communication buffer too small: need %lld bytes, got %zu", x.total, comm_bytes);
+    x.me = me; x.epoch_base = epoch_base;
+    for (int g = 0; g < world; ++g) {
+        if (!comm[g]) return fail(-73, "sharded run: comm[%d] is NULL", g);
+        if (((uintptr_t)comm[g] & 255) != 0) return fail(-73, "sharded run: communication buffers must be 256-byte aligned");
+        x.peer[g] = (char*)comm[g];
+    }
+    return ncp_run_impl(X_local, nullptr, ndim, local_shape, A, ldr, rank, C2C_ALGO_MU, n_iter_max, tol, cvg_criterion, normX2, errors,
+                        state, check_every, ws, ws_bytes, stream, nullptr, 1, nullptr, &x);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

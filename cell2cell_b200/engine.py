@@ -14,7 +14,8 @@ from ._lib import AGG, ALGO, CVG, MAX_NDIM, MAX_RANK, SCORE, C2CError, check, li
 __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace", "sumsq", "mttkrp", "gram_hadamard",
            "plane_contract", "fiber_contract", "mttkrp_from_contraction", "launch_count", "set_mma_min_rank",
            "mu_update", "mu_update_coupled", "hals_update", "recon_sums", "cp_normalize", "ncp_run", "ncp_run_batched", "coupled_ncp_run", "build_ccc", "group_aggregate",
-           "missing_rec_sumsq", "MaskPlan", "mask_plan", "masked_contract_planned", "ncp_run_multi", "multi_run_cost"]
+           "missing_rec_sumsq", "MaskPlan", "mask_plan", "masked_contract_planned", "ncp_run_multi", "multi_run_cost",
+           "shard_comm_bytes", "ncp_run_sharded"]
 
 _vp = ctypes.c_void_p
 
@@ -468,6 +469,46 @@ def ncp_run_multi(X, inits, n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_err
         n_iter = int(st[j, 0])
         res[b] = (fs, errs[j, :n_iter].copy(), n_iter, bool(st[j, 1]), sm[j].copy())
     return res
+
+
+def shard_comm_bytes(local_shape, rank, world):
+    """Bytes of one rank's communication buffer for ``ncp_run_sharded`` (``c2c_shard_comm_bytes``)."""
+    n = int(lib().c2c_shard_comm_bytes(len(local_shape), _shape_arr(local_shape), int(rank), int(world)))
+    if n == 0:
+        check(-71, "c2c_shard_comm_bytes")
+    return n
+
+
+def ncp_run_sharded(X_local, factors, rank, comm, n_iter_max=100, tol=1e-6, cvg_criterion="abs_rec_error", check_every=10,
+                    norm_x2=None, ws=None):
+    """This rank's part of one MU factorization sharded along mode 0 (``c2c_ncp_run_sharded``): ``X_local`` is the slab,
+    ``factors[0]`` the local rows of the first factor, ``factors[1:]`` full replicated factors (packed, updated in place);
+    ``comm``: an object with ``world``, ``me``, ``peers`` (one uint8 CUDA tensor per rank, ``peers[me]`` local), ``nbytes`` and a
+    growing ``epoch`` (``sharded.PeerComm``); ``norm_x2``: 1-element fp64 CUDA tensor with the squared norm of the WHOLE tensor.
+    Returns ``(errors, n_iter, converged)``."""
+    _check_tensor(X_local, None)
+    if cvg_criterion not in CVG:
+        raise C2CError("cvg_criterion %r is not one of %s" % (cvg_criterion, sorted(CVG)))
+    for f, s in zip(factors, X_local.shape):
+        if f.shape != (s, ldr_of(rank)) or f.dtype != torch.float32 or not f.is_contiguous() or f.device != X_local.device:
+            raise C2CError("factors must be packed fp32 [I_n, ldr] tensors on the tensor's device (pack_factor)")
+    if norm_x2 is None or not isinstance(norm_x2, torch.Tensor):
+        raise C2CError("ncp_run_sharded needs norm_x2: the squared norm of the whole tensor as a 1-element fp64 CUDA tensor")
+    with torch.cuda.device(X_local.device):
+        ws = _ws_for(X_local, rank, None, ws)
+        n_it = max(int(n_iter_max), 1)
+        errors = torch.zeros(n_it, dtype=torch.float64, device=X_local.device)
+        state = torch.zeros(2, dtype=torch.int32, device=X_local.device)
+        ptrs = (_vp * comm.world)(*[t.data_ptr() for t in comm.peers])
+        base = int(comm.epoch)
+        comm.epoch = base + n_it + 2
+        check(lib().c2c_ncp_run_sharded(_ptr(X_local), X_local.dim(), _shape_arr(X_local.shape), _ptr_arr(factors), ldr_of(rank),
+                                        int(rank), int(n_iter_max), float(tol), CVG[cvg_criterion], _ptr(norm_x2), _ptr(errors),
+                                        _ptr(state), int(check_every), ws.ptr, ws.nbytes, int(comm.world), int(comm.me), ptrs,
+                                        int(comm.nbytes), base & 0x7fffffff, _stream()), "c2c_ncp_run_sharded")
+        st = state.cpu().numpy()
+        n_iter = int(st[0])
+        return errors[:n_iter].cpu().numpy(), n_iter, bool(st[1])
 
 
 def coupled_ncp_run(X1, mask1, factors1, X2, mask2, factors2, rank, shared_pairs, n_iter_max=100, tol=1e-6,

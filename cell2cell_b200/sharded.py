@@ -23,7 +23,7 @@ import torch
 from . import engine
 from .tensor.cp import CPTensor
 
-__all__ = ["shard_bounds", "DeviceOps", "sharded_non_negative_parafac"]
+__all__ = ["shard_bounds", "DeviceOps", "PeerComm", "sharded_non_negative_parafac"]
 
 
 def shard_bounds(n, world, rank):
@@ -85,19 +85,113 @@ class DeviceOps:
         return engine.missing_rec_sumsq(X, mask, factors, self.R, ws=ws, out=out)
 
 
+class PeerComm:
+    """The communication buffers of the fused sharded run (``c2c_ncp_run_sharded``): one zero-filled device buffer per rank,
+    mapped into every process of ``group`` through CUDA IPC (torch's own tensor sharing: ``cudaIpcGetMemHandle`` /
+    ``cudaIpcOpenMemHandle``), peer access enabled between the devices.  The kernels store into the peers' buffers and poll
+    flags in their own: no NCCL call on the data path.  ``epoch`` only grows, so the buffers are never cleared between runs."""
+
+    _cache = {}
+
+    def __init__(self, nbytes, device, group=None):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.me = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nbytes = int(nbytes)
+        self.device = device
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device)
+        self.peers = [self.buf]
+        if self.world > 1:
+            fn, args = reduce_tensor(self.buf)
+            objs = [None] * self.world
+            dist.all_gather_object(objs, (int(device.index), fn, args), group=group)
+            self.peers = []
+            with torch.cuda.device(device):
+                for r, (didx, f, a) in enumerate(objs):
+                    if r == self.me:
+                        self.peers.append(self.buf)
+                    else:
+                        engine.check(engine.lib().c2c_enable_peer_access(int(didx)), "c2c_enable_peer_access")
+                        self.peers.append(f(*a))
+            dist.barrier(group)                     # every rank has opened every buffer before anyone writes
+        self.epoch = 0
+
+    @classmethod
+    def get(cls, nbytes, device, group=None):
+        key = (id(group), str(device))
+        c = cls._cache.get(key)
+        if c is None or c.nbytes < nbytes:
+            c = cls(nbytes, device, group)
+            cls._cache[key] = c
+        return c
+
+    def failed(self):
+        """True if a wait on a peer gave up (the int at offset 0 of the local buffer)."""
+        return bool(self.buf[:4].view(torch.int32).item() != 0)
+
+
+def _fused_sharded(X_local, full_shape, rank, init_factors, n_iter_max, tol, group, cvg_criterion, world, me, lo, hi):
+    """The whole loop inside the library (``c2c_ncp_run_sharded``): two streaming passes over the local slab per iteration, the
+    cross-slab sums exchanged inside the update kernels through peer memory (csrc/c2c_xgpu.cuh)."""
+    import torch.distributed as dist
+    dev = X_local.device
+    nd = len(full_shape)
+    local_shape = (hi - lo,) + tuple(full_shape[1:])
+    with torch.cuda.device(dev):
+        A = [engine.pack_factor(np.abs(np.asarray(init_factors[0], dtype=np.float64))[lo:hi], rank, dev)]
+        A += [engine.pack_factor(np.abs(np.asarray(f, dtype=np.float64)), rank, dev) for f in init_factors[1:]]
+        nx2 = torch.tensor([engine.sumsq(X_local)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(nx2, op=dist.ReduceOp.SUM, group=group)
+        nbytes = engine.shard_comm_bytes(local_shape, rank, world)
+        comm = PeerComm.get(nbytes, dev, group)
+        ws = engine.Workspace(local_shape, rank, False, dev)
+        if world > 1:
+            dist.barrier(group)                     # the ranks' kernels start together (a wait on a peer gives up after ~5 s)
+        errs, n_iter, _ = engine.ncp_run_sharded(X_local, A, rank, comm, n_iter_max=n_iter_max, tol=tol,
+                                                 cvg_criterion=cvg_criterion, norm_x2=nx2, ws=ws)
+        if comm.failed():
+            raise engine.C2CError("sharded factorization: a wait on a peer GPU timed out; the results are invalid")
+        A0 = torch.zeros((full_shape[0], engine.ldr_of(rank)), dtype=torch.float32, device=dev)
+        A0[lo:hi] = A[0]
+        if world > 1:
+            dist.all_reduce(A0, op=dist.ReduceOp.SUM, group=group)   # assembles the context factor (disjoint rows)
+        factors = [engine.unpack_factor(A0, rank).cpu().numpy()] + [engine.unpack_factor(a, rank).cpu().numpy() for a in A[1:]]
+    return CPTensor(np.ones(rank, dtype=np.float32), factors, device=dev), [float(e) for e in errs]
+
+
 def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter_max=100, tol=1e-6, group=None, ops=None,
-                                 cvg_criterion="abs_rec_error"):
+                                 cvg_criterion="abs_rec_error", fused=None):
     """MU NCP of a tensor whose first mode is split over the ranks of ``group``.
 
     X_local: this rank's slab ``[c1 - c0, I_1, ...]`` (``shard_bounds(full_shape[0], world, rank)``), fp32, on the compute
     device.  init_factors: the FULL initial factors (host arrays, identical on every rank -- e.g. host-seeded random_cp).
-    Returns ``(CPTensor with the full factors, errors)`` on every rank."""
+    Returns ``(CPTensor with the full factors, errors)`` on every rank.
+
+    ``fused`` (default: whenever it applies -- CUDA, >= 4 modes, rank <= 32, <= 8 ranks, every rank owning a context): the
+    loop runs inside the library with the exchanges in the update kernels over peer memory; otherwise (and with ``ops`` given)
+    the iteration is driven from here with NCCL / gloo all-reduces between the single-step entry points."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     me = dist.get_rank(group) if dist.is_initialized() else 0
-    ops = ops or DeviceOps(rank)
     nd = len(full_shape)
     dev = X_local.device
+    can_fuse = (ops is None and dev.type == "cuda" and nd >= 4 and int(rank) <= 32 and world <= 8 and full_shape[0] >= world
+                and int(n_iter_max) >= 1)
+    if fused is None:
+        import os
+        fused = can_fuse and os.environ.get("C2C_B200_NO_FUSED_SHARDED", "0") != "1"
+    if fused:
+        if not can_fuse:
+            raise ValueError("the fused sharded run needs a CUDA tensor with >= 4 modes, rank <= 32 and <= 8 ranks")
+        lo, hi = shard_bounds(full_shape[0], world, me)
+        if X_local.shape[0] != hi - lo:
+            raise ValueError("X_local has %d slices of mode 0, expected %d" % (X_local.shape[0], hi - lo))
+        return _fused_sharded(X_local, tuple(int(s) for s in full_shape), int(rank), init_factors, int(n_iter_max), float(tol),
+                              group, cvg_criterion, world, me, lo, hi)
+    ops = ops or DeviceOps(rank)
     lo, hi = shard_bounds(full_shape[0], world, me)
     if X_local.shape[0] != hi - lo:
         raise ValueError("X_local has %d slices of mode 0, expected %d" % (X_local.shape[0], hi - lo))

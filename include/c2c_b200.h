@@ -225,6 +225,26 @@ int c2c_ncp_run_multi(const float* X, int ndim, const int64_t* shape /*host*/, f
                       const int* ranks /*host*/, int nruns, int n_iter_max, double tol, int cvg_criterion, const double* normX2,
                       double* errors, int* state, double* sums, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- one factorization sharded along the first (context) mode over the GPUs of a box --------------------------------------
+ * BASELINE config 4 / SURVEY section 8(e) row 3; the reference has no multi-process factorization (its loop is tensorly's,
+ * cell2cell/tensor/factorization.py:91-104), the arithmetic is c2c_ncp_run's.  Every rank (one process per GPU) calls
+ * c2c_ncp_run_sharded with ITS slab X_local[c_lo:c_hi, ...] (local_shape[0] = c_hi - c_lo), A[0] = the local rows of the
+ * context factor, A[1..] = full copies of the other factors (identical on every rank), normX2 = ||X||^2 of the WHOLE tensor.
+ * Per iteration each rank makes the two streaming passes over its slab; the sums that cross slabs (the context factor's Gram,
+ * the partial M of the other leading modes, the partial U) are exchanged inside the update kernels through peer memory:
+ * comm[g] = rank g's communication buffer as mapped in this process (comm[me] local; the others opened from CUDA IPC handles
+ * after c2c_enable_peer_access), each c2c_shard_comm_bytes(...) bytes, zero-filled once when allocated, 256-byte aligned.
+ * epoch_base: any value larger than the last epoch_base + n_iter_max used with these buffers (same on every rank).  Every rank
+ * must enqueue the call at about the same time (a wait on a peer gives up after ~5 s and sets the int at offset 0 of the local
+ * buffer; the results are then invalid).  Replicated factors, errors and the stop decision come out bit-identical on every
+ * rank.  Unmasked multiplicative updates, ndim >= 4, rank <= 32, world <= 8; -71 when the shape is outside this path. */
+size_t c2c_shard_comm_bytes(int ndim, const int64_t* shape /*host; mode 0 unused*/, int rank, int world);
+int c2c_enable_peer_access(int peer_device);
+int c2c_ncp_run_sharded(const float* X_local, int ndim, const int64_t* local_shape /*host*/, float* const* A /*host array*/, int ldr,
+                        int rank, int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
+                        int check_every, void* ws, size_t ws_bytes, int world, int me, void* const* comm /*host array*/,
+                        size_t comm_bytes, unsigned int epoch_base, void* stream);
+
 /* ---- mask plan: the masked factorization without a pass over the mask ---------------------------------------------------
  * tensorly re-imputes the missing entries with the current reconstruction before every mode's MTTKRP
  * (`tensor*mask + cp_to_tensor(cp, mask=1-mask)`, mirrored at cell2cell/tensor/coupled_factorization.py:342-345).  With zeros
