@@ -120,6 +120,19 @@ def synth_host(shape, seed, pinned=True):
     return t.pin_memory() if pinned else t
 
 
+def use_all_host_cores():
+    """The CPU legs use every host core through BLAS whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1, which
+    made the round-1 reference arm of the N > 1 runs single-threaded).  Returns the BLAS thread count now in force."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    threadpool_limits(limits=n)                    # process-wide from here on (not used as a context manager)
+    return max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+
+
 def cpu_iterations(x64, rank, n_iter, seed):
     """n_iter MU iterations of the oracle from a host-seeded random init; returns seconds."""
     from oracle import ncp_oracle as o
@@ -133,8 +146,7 @@ def run_reference(args, rank_id, world):
     wl = WORKLOADS[args.workload]
     if rank_id != 0:
         return
-    from threadpoolctl import threadpool_info
-    threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+    threads = use_all_host_cores()
     x64 = synth_host(wl["shape"], 1, pinned=False).numpy().astype(np.float64)
     iters = args.ref_iters
     for _ in range(args.warmup if args.ref_warm else 0):
@@ -172,6 +184,193 @@ def time_kernel(fn, reps):
     b.record()
     torch.cuda.synchronize()
     return a.elapsed_time(b) / reps * 1e-3
+
+
+def median_run_ms(fn, reps=3):
+    """Median device milliseconds of `fn()` (CUDA events on the current stream, a synchronize on both sides)."""
+    import torch
+    out = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        out.append(a.elapsed_time(b))
+    return float(np.median(out))
+
+
+def sharded_record(X, shape, iters, rank_id, world, dev):
+    """One MU factorization of the atlas tensor sharded along the context mode over the `world` GPUs (strong scaling): rank 10
+    and rank 20 (BASELINE config 4), iterations/s of c2c_ncp_run_sharded with its exchanges inside the update kernels over peer
+    memory; device time, max over ranks.  Every rank uses the slab of its own replica (a view: mode 0 is outermost)."""
+    import torch
+    import torch.distributed as dist
+    from cell2cell_b200 import engine
+    from cell2cell_b200.sharded import PeerComm, shard_bounds
+    lo, hi = shard_bounds(shape[0], world, rank_id)
+    Xl = X[lo:hi]
+    local_shape = tuple(Xl.shape)
+    nx2 = torch.tensor([engine.sumsq(X)], dtype=torch.float64, device=dev)
+    rec = {"scaling": "strong", "n_gpus": world, "contexts_per_gpu": [shard_bounds(shape[0], world, r)[1] - shard_bounds(shape[0], world, r)[0] for r in range(world)],
+           "exchange": "inside lead_update_xg / fiber_reduce_xg: NVLink stores into every peer's buffer + release flags, sums in rank "
+                       "order (2 exchanges per iteration: partial M of the LR mode + context Gram, partial U); no NCCL on the data path"}
+    for R in (10, 20):
+        comm = PeerComm.get(engine.shard_comm_bytes(local_shape, 32, world), dev)
+        ws = engine.Workspace(local_shape, R, False, dev)
+
+        def factors(seed):
+            rs = np.random.RandomState(seed)
+            fs = [rs.random_sample((s, R)).astype(np.float32) for s in shape]
+            return [engine.pack_factor(fs[0][lo:hi], R, dev)] + [engine.pack_factor(f, R, dev) for f in fs[1:]]
+
+        def run(seed, n):
+            f = factors(seed)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            errs, n_iter, _ = engine.ncp_run_sharded(Xl, f, R, comm, n_iter_max=n, tol=-1.0, check_every=0, norm_x2=nx2, ws=ws)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            assert not comm.failed(), "a wait on a peer GPU timed out"
+            return float(t[0]), float(errs[-1])
+        run(1, 10)
+        times, err = [], None
+        for rep in range(5):
+            t, err = run(50 + rep, iters)
+            times.append(t)
+        med = float(np.median(times))
+        rec["rank%d" % R] = {"iterations_per_s": iters / med, "ms_per_iteration": 1e3 * med / iters,
+                              "calls": [round(iters / t, 1) for t in times], "final_rec_error": err}
+        del ws
+    return rec
+
+
+def masked_record(X, shape, rank, dev):
+    """The masked iteration (north_star's fused masked MTTKRP) on the atlas shape -- 20 % random missing entries, and the
+    structured mask how='outer' produces (a cell type missing from every 3rd context + 2 % of the planes) -- and on the ASD
+    config built by InteractionTensor(how='outer') at full size.  Roofline on the ALGORITHMIC bytes of SURVEY section 8(d):
+    4 modes x N_X x 5 B (tensor + mask byte per mode) per iteration."""
+    import torch
+    from cell2cell_b200 import engine
+    from cell2cell_b200.synthetic import synthetic_case
+    from cell2cell_b200.tensor import InteractionTensor
+    pk = peaks()[0]
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = {"algorithmic_bytes_per_iteration": "4 modes x N_X x 5 B", "peak_gbs": pk,
+           "passes_made": "2 reads of the tensor, 0 of the mask (mask plan: Gram-form corrections for the separable part, "
+                          "lists for the residual entries, built once per tensor)"}
+
+    def measure(Xm, mask, R, n=50):
+        n_x = Xm.numel()
+        ws = engine.Workspace(tuple(Xm.shape), R, True, dev)
+        nx2 = engine.sumsq(Xm)
+        t0 = time.perf_counter()
+        plan = engine.mask_plan(Xm, mask)
+        torch.cuda.synchronize()
+        t_plan = time.perf_counter() - t0
+        mk = lambda sd: [engine.pack_factor(np.random.RandomState(sd + k).random_sample((s, R)).astype(np.float32), R, dev)  # noqa: E731
+                         for k, s in enumerate(Xm.shape)]
+        engine.ncp_run(Xm, mask, mk(1), R, n_iter_max=5, tol=-1.0, check_every=0, norm_x2=nx2, ws=ws)
+        fs = [mk(10), mk(20), mk(30)]
+        it = iter(fs)
+        ms = median_run_ms(lambda: engine.ncp_run(Xm, mask, next(it), R, n_iter_max=n, tol=-1.0, check_every=0, norm_x2=nx2,
+                                                  ws=ws, sync=False)) / n
+        gbs = 4 * n_x * 5 / (ms * 1e-3) / 1e9
+        return {"shape": list(Xm.shape), "rank": R, "missing_fraction": 1.0 - float(mask.float().mean().item()),
+                "plan": {"usable": bool(plan.usable), "separable_part": bool(plan.model_missing), "residual_entries": plan.n_residual,
+                         "build_s": round(t_plan, 4)},
+                "ms_per_iteration": ms, "iterations_per_s": 1e3 / ms, "achieved_gbs": gbs, "frac": gbs / pk}
+
+    mask = (torch.rand(shape, generator=g, device=dev) > 0.2).to(torch.uint8)
+    Xm = X * mask
+    out["atlas_random20"] = measure(Xm, mask, rank)
+    mask.fill_(1)
+    mask[2::3, ..., 5, :] = 0
+    mask[2::3, ..., :, 5] = 0
+    mask[torch.rand(shape[:-2], generator=g, device=dev) < 0.02] = 0
+    torch.mul(X, mask, out=Xm)
+    out["atlas_structured"] = measure(Xm, mask, rank)
+    out["atlas_structured_rank20"] = measure(Xm, mask, 20)
+    del Xm, mask
+    mats, ppi, kw = synthetic_case("asd")
+    t = InteractionTensor(mats, ppi, device=dev, **kw)
+    out["asd_outer_built"] = measure(t.tensor, t.mask, rank, n=100)
+    out["asd_outer_built"]["built_by"] = "InteractionTensor(how='outer', expression_gmean, complexes) on synthetic_case('asd')"
+    return out
+
+
+def small_record(dev, iters):
+    """BASELINE configs 1-2 (L2-resident tensors): the elbow analysis through the public API -- ranks 1..25 x 10 runs, `iters`
+    fixed iterations each -- as ONE launch of the one-CTA-per-run kernel (c2c_ncp_run_multi)."""
+    import torch
+    from cell2cell_b200.synthetic import synthetic_lowrank_tensor
+    from cell2cell_b200.tensor import PreBuiltTensor
+    out = {}
+    for name in ("balf", "toy"):
+        shape = WORKLOADS[name]["shape"]
+        x = torch.from_numpy(synthetic_lowrank_tensor(shape, rank=5, noise=0.05, seed=1)).to(dev)
+        t = PreBuiltTensor(x, order_names=[list(range(s)) for s in shape])
+        kw = dict(init="random", n_iter_max=iters, tol=-1.0, output_fig=False, automatic_elbow=False)
+        t.elbow_rank_selection(upper_rank=2, runs=2, random_state=1, **kw)
+        torch.cuda.synchronize()
+        walls = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            _, loss = t.elbow_rank_selection(upper_rank=25, runs=10, random_state=888 + rep, **kw)
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        w = float(np.median(walls))
+        out[name] = {"shape": list(shape), "elbow_sweep_wall_s": w, "runs": 250, "iterations_per_run": iters,
+                     "aggregate_iterations_per_s": 250 * iters / w, "loss_rank1": float(loss[0][1]), "loss_last": float(loss[-1][1])}
+    return out
+
+
+def build_record(dev, no_cpu):
+    """K1 at the atlas shape with how='outer' (scores + mask written): the kernel alone (CUDA events inside engine.build_ccc)
+    against the HBM write roofline, the whole InteractionTensor(...) call, and the numpy / pandas restatement of the
+    reference's build (oracle/build_oracle.py) on the first 3 contexts, extrapolated."""
+    import torch
+    from cell2cell_b200 import engine
+    from cell2cell_b200.synthetic import CONFIGS, synthetic_contexts, synthetic_ppi
+    from cell2cell_b200.tensor import InteractionTensor
+    cfg = CONFIGS["atlas"]
+    ppi = synthetic_ppi(cfg["L"], 2 * cfg["L"])
+    mats = synthetic_contexts(cfg["C"], 2 * cfg["L"], cfg["K"])
+    kw = dict(how="outer", communication_score="expression_gmean", complex_sep="&", complex_agg_method="min", verbose=False)
+    InteractionTensor(mats, ppi, device=dev, **kw)
+    torch.cuda.synchronize()
+    engine.BUILD_EVENTS = []
+    walls = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        t = InteractionTensor(mats, ppi, device=dev, **kw)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+    kern = [a.elapsed_time(b) for a, b in engine.BUILD_EVENTS]
+    engine.BUILD_EVENTS = None
+    n_x = t.tensor.numel()
+    ms = float(np.median(kern))
+    pk = peaks()[0]
+    rec = {"shape": list(t.tensor.shape), "how": "outer", "kernel_ms": ms, "bytes_written": 5 * n_x,
+           "achieved_gbs": 5 * n_x / (ms * 1e-3) / 1e9, "frac": 5 * n_x / (ms * 1e-3) / 1e9 / pk, "peak_gbs": pk,
+           "whole_call_s": float(np.median(walls)),
+           "note": "kernel: gather + complex aggregation + scores for every sender x receiver pair, 4 B score + 1 B mask per entry"}
+    if not no_cpu:
+        from oracle.build_oracle import interaction_tensor_oracle
+        n_c = 3
+        t0 = time.perf_counter()
+        interaction_tensor_oracle([m.astype(np.float64) for m in mats[:n_c]], ppi, **{k: v for k, v in kw.items() if k != "verbose"})
+        dt = time.perf_counter() - t0
+        rec["cpu_port"] = {"seconds_for_%d_contexts" % n_c: dt, "extrapolated_s": dt * cfg["C"] / n_c, "kind": "port",
+                           "note": "oracle/build_oracle.py (numpy / pandas restatement; the reference's own loop took 125 s here in round 1)"}
+    return rec
 
 
 def run_ours(args, rank_id, local_rank, world):
@@ -258,22 +457,37 @@ def run_ours(args, rank_id, local_rank, world):
                  "note": "independent (rank, seed) factorizations spread over the GPUs, fixed iteration count (tol = -1)"}
         del t
 
-    # ---- config 4's own rank (20): the tensor-pipe passes --------------------------------------------------------------------
+    # ---- config 4's own rank (20): the tensor-pipe passes (median of 5 timed calls, its own roofline) -------------------------
     r20 = None
-    if args.workload == "atlas":
+    if args.workload == "atlas" and rank_id == 0:
         ws20 = engine.Workspace(shape, 20, False, dev)
-        f20 = [[engine.pack_factor(np.random.RandomState(7 + k).random_sample((s, 20)).astype(np.float32), 20, dev) for s in shape]
-               for k in range(2)]
-        engine.ncp_run(X, None, f20[0], 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20)
+        mk20 = lambda sd: [engine.pack_factor(np.random.RandomState(sd + k).random_sample((s, 20)).astype(np.float32), 20, dev)  # noqa: E731
+                           for k, s in enumerate(shape)]
+        engine.ncp_run(X, None, mk20(7), 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20)
         torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        engine.ncp_run(X, None, f20[1], 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20, sync=False)
-        a1.record()
-        torch.cuda.synchronize()
-        r20 = {"rank": 20, "iterations_per_s_per_gpu": iters / (a0.elapsed_time(a1) * 1e-3),
-               "passes": "plane_mma / fiber_mma (TMA + tcgen05.mma kind::tf32, 3-term split)"}
-        del ws20, f20
+        t20 = []
+        for rep in range(5):
+            f20 = mk20(100 + 10 * rep)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            engine.ncp_run(X, None, f20, 20, n_iter_max=iters, tol=-1.0, check_every=0, norm_x2=norm_x2, ws=ws20, sync=False)
+            a1.record()
+            torch.cuda.synchronize()
+            t20.append(a0.elapsed_time(a1) * 1e-3)
+        f20 = mk20(7)
+        T20 = torch.empty((int(np.prod(shape[:-2])), 20), dtype=torch.float32, device=dev)
+        U20 = torch.empty((shape[-2] * shape[-1], 20), dtype=torch.float32, device=dev)
+        tp20 = time_kernel(lambda: engine.plane_contract(X, None, f20, 20, ws=ws20, out=T20), 20)
+        tf20 = time_kernel(lambda: engine.fiber_contract(X, None, f20, 20, ws=ws20, out=U20), 20)
+        med = float(np.median(t20))
+        pk = peaks()[0]
+        r20 = {"rank": 20, "iterations_per_s_per_gpu": iters / med, "calls": [round(iters / t, 1) for t in t20],
+               "passes": "plane_mma / fiber_mma (TMA + tcgen05.mma kind::tf32, 3-term split)",
+               "roofline": {"bound": "hbm", "kernel": "fiber_mma<32>", "achieved": n_x * 4 / tf20 / 1e9, "peak": pk, "unit": "GB/s",
+                            "frac": n_x * 4 / tf20 / 1e9 / pk, "plane_mma_ms": tp20 * 1e3, "fiber_mma_ms": tf20 * 1e3,
+                            "plane_mma_frac": n_x * 4 / tp20 / 1e9 / pk,
+                            "iteration_frac_of_2_pass_traffic": 2 * n_x * 4 * iters / med / 1e9 / pk}}
+        del ws20, f20, T20, U20
 
     # ---- Coupled Tensor Component Analysis: the atlas tensor + a second one sharing contexts / senders / receivers ------------
     coupled = None
@@ -297,6 +511,17 @@ def run_ours(args, rank_id, local_rank, world):
                    "stream_gbs": 2 * 4 * (n_x + X2.numel()) * iters / csec / 1e9,
                    "note": "c2c_coupled_ncp_run, whole call (workspaces, initial Grams, graph capture included)"}
         del X2, A1, A2
+
+    # ---- ONE factorization sharded along the context mode over the N GPUs (BASELINE config 4; strong scaling) -----------------
+    sharded = None
+    if args.workload == "atlas" and args.sharded:
+        sharded = sharded_record(X, shape, iters, rank_id, world, dev)
+
+    masked = small = build = None
+    if rank_id == 0 and args.workload == "atlas" and args.extras:
+        masked = masked_record(X, shape, rank, dev)
+        small = small_record(dev, iters)
+        build = build_record(dev, args.no_cpu)
 
     # ---- per-kernel roofline (rank 0 only reports) ---------------------------------------------------------------------
     f = fresh_factors(1)
@@ -342,9 +567,11 @@ def run_ours(args, rank_id, local_rank, world):
                      "frac": n_x * 4 / worst / 1e9 / peak, "traffic": ncu_traffic(name), "peak_kind": "of " + peak_kind,
                      "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
                      "plane_contract_gbs": n_x * 4 / t_plane / 1e9, "fiber_contract_gbs": n_x * 4 / t_fiber / 1e9,
-                     "iteration": {"algorithmic_bytes": 4 * n_x * 4, "achieved_gbs": 4 * n_x * 4 * value / world / 1e9,
-                                   "frac_of_4_pass_roofline": 4 * n_x * 4 * value / world / 1e9 / peak,
-                                   "passes_made": 2}},
+                     "iteration": {"passes_made": 2, "bytes_moved": 2 * n_x * 4,
+                                   "achieved_gbs": 2 * n_x * 4 * value / world / 1e9,
+                                   "frac": 2 * n_x * 4 * value / world / 1e9 / peak,
+                                   "algorithmic_bytes_4_pass": 4 * n_x * 4,
+                                   "algorithmic_speedup_vs_4_pass_roofline": 4 * n_x * 4 * value / world / 1e9 / peak}},
         "final_rec_error": final_err,
     }
     if elbow is not None:
@@ -353,9 +580,11 @@ def run_ours(args, rank_id, local_rank, world):
         line["rank20"] = r20
     if coupled is not None:
         line["coupled"] = coupled
+    for key, rec in (("sharded", sharded), ("masked", masked), ("small_tensors", small), ("build", build)):
+        if rec is not None:
+            line[key] = rec
     if not args.no_cpu:
-        from threadpoolctl import threadpool_info
-        threads = max([d.get("num_threads", 1) for d in threadpool_info()] + [1])
+        threads = use_all_host_cores()
         x64 = x_host.numpy().astype(np.float64)
         n_it = args.ref_iters
         tcpu = cpu_iterations(x64, rank, n_it, 888)
@@ -445,6 +674,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-coupled", dest="coupled", action="store_false", help="skip the coupled-factorization line")
     ap.add_argument("--no-elbow", dest="elbow", action="store_false", help="skip the elbow-sweep wall time (second BASELINE metric)")
+    ap.add_argument("--no-sharded", dest="sharded", action="store_false", help="skip the context-sharded factorization record")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the masked / small-tensor / build records")
     ap.add_argument("--elbow-ranks", type=int, default=25)
     ap.add_argument("--elbow-runs", type=int, default=10)
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],

@@ -63,6 +63,11 @@ SIGNATURES = {
                                _p, _sz, _p]),
     "c2c_shard_comm_bytes": (_sz, [_i, _c.POINTER(_i64), _i, _i]),
     "c2c_enable_peer_access": (_i, [_i]),
+    "c2c_comm_alloc": (_i, [_sz, _c.POINTER(_p), _c.POINTER(_c.c_ubyte)]),
+    "c2c_comm_open": (_i, [_c.POINTER(_c.c_ubyte), _c.POINTER(_p)]),
+    "c2c_comm_close": (_i, [_p]),
+    "c2c_comm_free": (_i, [_p]),
+    "c2c_comm_probe": (_i, [_i, _i, _c.POINTER(_p), _sz, _c.c_uint, _c.c_float, _p, _p]),
     "c2c_ncp_run_sharded": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _c.c_double, _i, _p, _p, _p, _i, _p, _sz,
                                  _i, _i, _c.POINTER(_p), _sz, _c.c_uint, _p]),
     "c2c_mask_plan_header_bytes": (_sz, [_i, _c.POINTER(_i64)]),

@@ -1602,6 +1602,79 @@ extern "C" int c2c_enable_peer_access(int peer_device)
     return 0;
 }
 
+// Communication buffers that the library allocates itself (cudaMalloc, zero-filled) so that they can be exported with
+// cudaIpcGetMemHandle and opened by the peer processes with THEIR device current (cudaIpcMemLazyEnablePeerAccess maps the
+// memory for peer access from the opening device, the way NCCL opens its own P2P buffers).
+extern "C" int c2c_comm_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out /*host, 64 bytes*/)
+{
+    if (!ptr_out || !handle_out || bytes == 0) return fail(-74, "c2c_comm_alloc: bad arguments");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes), "cudaMalloc (communication buffer)");
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &h, sizeof(h));
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int c2c_comm_open(const unsigned char* handle /*host, 64 bytes*/, void** ptr_out)
+{
+    if (!handle || !ptr_out) return fail(-74, "c2c_comm_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    *ptr_out = p;
+    return 0;
+}
+
+extern "C" int c2c_comm_close(void* ptr)
+{
+    if (ptr) CK(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle");
+    return 0;
+}
+
+extern "C" int c2c_comm_free(void* ptr)
+{
+    if (ptr) CK(cudaFree(ptr), "cudaFree (communication buffer)");
+    return 0;
+}
+
+// One exchange over the buffers (a store into every peer, a flag, a wait, a sum): checks the mapping before a run relies on it.
+// out[0] = sum over the ranks of (rank + 1) * value as seen in the local buffer.
+__global__ void xg_probe_kernel(XgComm x, unsigned int epoch, float value, float* out)
+{
+    float* mine = reinterpret_cast<float*>(x.peer[x.me] + x.off_u);
+    if ((int)threadIdx.x < x.world) reinterpret_cast<float*>(x.peer[threadIdx.x] + x.off_u)[x.me] = (x.me + 1) * value;
+    xg_signal(x, x.off_flags_u, 0, epoch);
+    xg_wait(x, x.off_flags_u, 0, -1, epoch);
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int g = 0; g < x.world; ++g) s += __ldcg(mine + g);
+        out[0] = s;
+    }
+}
+
+extern "C" int c2c_comm_probe(int world, int me, void* const* comm, size_t comm_bytes, unsigned int epoch, float value, float* out,
+                              void* stream)
+{
+    if (world < 1 || world > C2C_XG_MAX_WORLD || me < 0 || me >= world || !comm || !out) return fail(-73, "c2c_comm_probe: bad arguments");
+    XgComm x;
+    memset(&x, 0, sizeof(x));
+    const int64_t shape[4] = {1, 1, 8, 8};
+    xg_layout(x, 2, shape, 64, 4, world);
+    if (comm_bytes < (size_t)x.total) return fail(-73, "c2c_comm_probe: buffer too small (%lld bytes needed)", x.total);
+    x.me = me;
+    for (int g = 0; g < world; ++g) x.peer[g] = (char*)comm[g];
+    xg_probe_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(x, epoch, value, out);
+    CKL("xg_probe launch");
+    return 0;
+}
+
 extern "C" int c2c_ncp_run_sharded(const float* X_local, int ndim, const int64_t* local_shape, float* const* A, int ldr, int rank,
                                    int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
                                    int check_every, void* ws, size_t ws_bytes, int world, int me, void* const* comm, size_t comm_bytes,

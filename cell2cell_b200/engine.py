@@ -18,6 +18,7 @@ __all__ = ["require_cuda", "ldr_of", "pack_factor", "unpack_factor", "Workspace"
            "shard_comm_bytes", "ncp_run_sharded"]
 
 _vp = ctypes.c_void_p
+BUILD_EVENTS = None       # set to a list to collect (start, end) CUDA events of every c2c_build_ccc launch (bench.py)
 
 
 def require_cuda(device=None):
@@ -483,7 +484,7 @@ def ncp_run_sharded(X_local, factors, rank, comm, n_iter_max=100, tol=1e-6, cvg_
                     norm_x2=None, ws=None):
     """This rank's part of one MU factorization sharded along mode 0 (``c2c_ncp_run_sharded``): ``X_local`` is the slab,
     ``factors[0]`` the local rows of the first factor, ``factors[1:]`` full replicated factors (packed, updated in place);
-    ``comm``: an object with ``world``, ``me``, ``peers`` (one uint8 CUDA tensor per rank, ``peers[me]`` local), ``nbytes`` and a
+    ``comm``: an object with ``world``, ``me``, ``ptrs`` (every rank's buffer as mapped here, ``ptrs[me]`` local), ``nbytes`` and a
     growing ``epoch`` (``sharded.PeerComm``); ``norm_x2``: 1-element fp64 CUDA tensor with the squared norm of the WHOLE tensor.
     Returns ``(errors, n_iter, converged)``."""
     _check_tensor(X_local, None)
@@ -499,7 +500,7 @@ def ncp_run_sharded(X_local, factors, rank, comm, n_iter_max=100, tol=1e-6, cvg_
         n_it = max(int(n_iter_max), 1)
         errors = torch.zeros(n_it, dtype=torch.float64, device=X_local.device)
         state = torch.zeros(2, dtype=torch.int32, device=X_local.device)
-        ptrs = (_vp * comm.world)(*[t.data_ptr() for t in comm.peers])
+        ptrs = (_vp * comm.world)(*[int(p) for p in comm.ptrs])
         base = int(comm.epoch)
         comm.epoch = base + n_it + 2
         check(lib().c2c_ncp_run_sharded(_ptr(X_local), X_local.dim(), _shape_arr(X_local.shape), _ptr_arr(factors), ldr_of(rank),
@@ -565,8 +566,15 @@ def build_ccc(expr, expr_off, expr_ld, cell_col, a_first, a_count, b_first, b_co
              up(sub_rows if len(sub_rows) else np.zeros(1, np.int32), np.int32)]
         X = torch.empty((C, L, K, K), dtype=torch.float32, device=dev)
         mask = torch.empty((C, L, K, K), dtype=torch.uint8, device=dev) if with_mask else None
+        ev = None
+        if BUILD_EVENTS is not None:                 # bench.py: CUDA events around the kernel alone (uploads are before `a`)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         check(lib().c2c_build_ccc(_ptr(d_expr), *[_ptr(t) for t in d], C, L, K, SCORE[score], AGG[agg], _ptr(X), _ptr(mask),
                                   _stream()), "c2c_build_ccc")
+        if ev is not None:
+            ev[1].record()
+            BUILD_EVENTS.append(ev)
         return X, mask
 
 

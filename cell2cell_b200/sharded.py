@@ -85,38 +85,58 @@ class DeviceOps:
         return engine.missing_rec_sumsq(X, mask, factors, self.R, ws=ws, out=out)
 
 
+class _RawCuda:
+    """A device pointer as a ``__cuda_array_interface__`` object (torch wraps it without copying)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class PeerComm:
-    """The communication buffers of the fused sharded run (``c2c_ncp_run_sharded``): one zero-filled device buffer per rank,
-    mapped into every process of ``group`` through CUDA IPC (torch's own tensor sharing: ``cudaIpcGetMemHandle`` /
-    ``cudaIpcOpenMemHandle``), peer access enabled between the devices.  The kernels store into the peers' buffers and poll
-    flags in their own: no NCCL call on the data path.  ``epoch`` only grows, so the buffers are never cleared between runs."""
+    """The communication buffers of the fused sharded run (``c2c_ncp_run_sharded``): one zero-filled device buffer per rank
+    (``c2c_comm_alloc``), exported as a CUDA IPC handle, exchanged through ``group`` and opened by every peer process with its
+    own device current (``c2c_comm_open``: mapped for peer access over NVLink).  The kernels store into the peers' buffers and
+    poll flags in their own: no NCCL call on the data path.  ``epoch`` only grows, so the buffers are never cleared between
+    runs.  One exchange is run over the mapping when it is made (``c2c_comm_probe``)."""
 
     _cache = {}
 
     def __init__(self, nbytes, device, group=None):
+        import ctypes
         import torch.distributed as dist
-        from torch.multiprocessing.reductions import reduce_tensor
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.me = dist.get_rank(group) if dist.is_initialized() else 0
         self.nbytes = int(nbytes)
         self.device = device
-        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
-        torch.cuda.synchronize(device)
-        self.peers = [self.buf]
-        if self.world > 1:
-            fn, args = reduce_tensor(self.buf)
-            objs = [None] * self.world
-            dist.all_gather_object(objs, (int(device.index), fn, args), group=group)
-            self.peers = []
-            with torch.cuda.device(device):
-                for r, (didx, f, a) in enumerate(objs):
+        lib = engine.lib()
+        with torch.cuda.device(device):
+            ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+            engine.check(lib.c2c_comm_alloc(self.nbytes, ctypes.byref(ptr), handle), "c2c_comm_alloc")
+            self.local = int(ptr.value)
+            self.buf = torch.as_tensor(_RawCuda(self.local, self.nbytes), device=device)
+            self.ptrs = [self.local]
+            self.epoch = 1
+            if self.world > 1:
+                objs = [None] * self.world
+                dist.all_gather_object(objs, (int(device.index), bytes(handle)), group=group)
+                self.ptrs = []
+                for r, (didx, h) in enumerate(objs):
                     if r == self.me:
-                        self.peers.append(self.buf)
-                    else:
-                        engine.check(engine.lib().c2c_enable_peer_access(int(didx)), "c2c_enable_peer_access")
-                        self.peers.append(f(*a))
-            dist.barrier(group)                     # every rank has opened every buffer before anyone writes
-        self.epoch = 0
+                        self.ptrs.append(self.local)
+                        continue
+                    engine.check(lib.c2c_enable_peer_access(int(didx)), "c2c_enable_peer_access")
+                    p = ctypes.c_void_p()
+                    engine.check(lib.c2c_comm_open((ctypes.c_ubyte * 64)(*h), ctypes.byref(p)), "c2c_comm_open")
+                    self.ptrs.append(int(p.value))
+                dist.barrier(group)                     # every rank has opened every buffer before anyone writes
+                out = torch.zeros(1, dtype=torch.float32, device=device)
+                arr = (ctypes.c_void_p * self.world)(*self.ptrs)
+                engine.check(lib.c2c_comm_probe(self.world, self.me, arr, self.nbytes, self.epoch, 3.0, ctypes.c_void_p(out.data_ptr()),
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "c2c_comm_probe")
+                self.epoch += 2
+                got, want = float(out.item()), 3.0 * self.world * (self.world + 1) / 2
+                if got != want or self.failed():
+                    raise engine.C2CError("peer-memory exchange between the GPUs failed its probe (%r != %r)" % (got, want))
 
     @classmethod
     def get(cls, nbytes, device, group=None):

@@ -240,6 +240,16 @@ int c2c_ncp_run_multi(const float* X, int ndim, const int64_t* shape /*host*/, f
  * rank.  Unmasked multiplicative updates, ndim >= 4, rank <= 32, world <= 8; -71 when the shape is outside this path. */
 size_t c2c_shard_comm_bytes(int ndim, const int64_t* shape /*host; mode 0 unused*/, int rank, int world);
 int c2c_enable_peer_access(int peer_device);
+/* Communication buffers owned by the library (the one exception to "caller-owned buffers": CUDA IPC exports cudaMalloc
+ * allocations): c2c_comm_alloc returns a zero-filled device buffer and its 64-byte cudaIpcMemHandle_t; a peer process opens it
+ * with ITS device current (c2c_comm_open), closes it with c2c_comm_close; the owner frees it with c2c_comm_free.
+ * c2c_comm_probe runs one exchange over the mapped buffers (every rank must call it; out[0] = value * world (world + 1) / 2). */
+int c2c_comm_alloc(size_t bytes, void** ptr_out /*host*/, unsigned char* handle_out /*host, 64 bytes*/);
+int c2c_comm_open(const unsigned char* handle /*host, 64 bytes*/, void** ptr_out /*host*/);
+int c2c_comm_close(void* ptr);
+int c2c_comm_free(void* ptr);
+int c2c_comm_probe(int world, int me, void* const* comm /*host array*/, size_t comm_bytes, unsigned int epoch, float value,
+                   float* out, void* stream);
 int c2c_ncp_run_sharded(const float* X_local, int ndim, const int64_t* local_shape /*host*/, float* const* A /*host array*/, int ldr,
                         int rank, int n_iter_max, double tol, int cvg_criterion, const double* normX2, double* errors, int* state,
                         int check_every, void* ws, size_t ws_bytes, int world, int me, void* const* comm /*host array*/,
