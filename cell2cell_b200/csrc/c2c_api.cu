@@ -22,6 +22,7 @@
 #include "c2c_plan.cuh"
 #include "c2c_multi.cuh"
 #include "c2c_xgpu.cuh"
+#include "c2c_metrics.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -1096,6 +1097,21 @@ extern "C" int c2c_cp_normalize(float* const* A, int ndim, const int64_t* shape,
         cp_normalize_kernel<<<1, C2C_SMALL_THREADS, 0, (cudaStream_t)stream>>>(A[k], shape[k], rank, ldr, weights, k == 0 ? 1 : 0);
         CKL("cp_normalize launch");
     }
+    return 0;
+}
+
+extern "C" int c2c_corrindex_pairs(const double* F, int n, int64_t rows, int rank, const int64_t* seg_off, int nseg, int method,
+                                   double tol, double* out, int* status, void* stream)
+{
+    if (!F || !seg_off || !out || !status) return fail(-1, "NULL argument");
+    if (n < 1 || rows < 1) return fail(-2, "need at least one decomposition and one row");
+    if (rank < 1 || rank > C2C_MAX_RANK) return fail(-3, "rank must be in 1..%d", C2C_MAX_RANK);
+    if (nseg < 1 || method < 0 || method > 3) return fail(-4, "bad block count / method");
+    int launches = 0;
+    const cudaError_t e = c2c_launch_corrindex_pairs(F, n, rows, rank, (const long long*)seg_off, nseg, method, tol, out, status,
+                                                     (cudaStream_t)stream, &launches);
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "corrindex_pairs launch");
     return 0;
 }
 

@@ -250,6 +250,33 @@ def cp_normalize(factors, rank, weights=None):
         return w
 
 
+_CORR_METHODS = {"stacked": 0, "max_score": 1, "min_score": 2, "avg_score": 3}
+
+
+def corrindex_pairs(stacked, mode_sizes, method="stacked", tol=5e-16, device=None):
+    """CorrIndex of every pair of ``n`` decompositions in one launch (``c2c_corrindex_pairs``; metrics.py:131-179).
+
+    stacked: ``[n, S, R]`` float64 (numpy or torch), every decomposition's factor matrices stacked along the rows;
+    mode_sizes: the row counts of the stacked matrices (sum = S).  Returns the symmetric ``[n, n]`` float64 numpy matrix."""
+    dev = require_cuda(device)
+    with torch.cuda.device(dev):
+        F = torch.as_tensor(stacked).to(device=dev, dtype=torch.float64).contiguous()
+        n, S, R = (int(v) for v in F.shape)
+        sizes = [int(v) for v in mode_sizes]
+        if sum(sizes) != S:
+            raise ValueError("mode sizes do not add up to the stacked row count")
+        offs = [0, S] if method == "stacked" else list(np.concatenate([[0], np.cumsum(sizes)]))
+        seg = torch.as_tensor(np.asarray(offs, dtype=np.int64)).to(dev)
+        out = torch.empty((n, n), dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(lib().c2c_corrindex_pairs(_ptr(F), n, S, R, _ptr(seg), len(offs) - 1, _CORR_METHODS[method], float(tol), _ptr(out),
+                                        _ptr(status), _stream()), "c2c_corrindex_pairs")
+        res = out.cpu().numpy()
+        if int(status.item()) != 0:
+            raise ValueError("Column norms must be non-zero")
+        return res
+
+
 class MaskPlan:
     """The mask plan of ``c2c_mask_plan_scan`` / ``_fill`` (include/c2c_b200.h): the tightest separable model
     ``observed[p, s, v] = g[p] * hs[c(p), s] * hv[c(p), v]`` of the mask plus the residual missing entries as lists, built once

@@ -1,12 +1,14 @@
 """CorrIndex similarity between decompositions (Sobhani et al. 2022), for ``elbow_rank_selection(metric='similarity')``.
 
-Same functions as cell2cell/tensor/metrics.py:12-179; the inputs are the small factor matrices (sum(I_n) x R), so this is
-host numpy.
+Same functions as cell2cell/tensor/metrics.py:12-179.  The reference scores the ``n (n - 1) / 2`` pairs of a rank's runs one by
+one on the host (normalise, stack, ``|X1^T X2|``, row / column maxima); here the runs' factor matrices are stacked into one
+``[n, S, R]`` device array and ONE launch of ``corrindex_pairs_kernel`` (csrc/c2c_metrics.cu, fp64, a CTA per pair) scores
+them all.  Argument checks and error messages are the reference's.
 """
-from itertools import combinations
-
 import numpy as np
 import pandas as pd
+
+from .. import engine
 
 __all__ = ["correlation_index", "pairwise_correlation_index"]
 
@@ -14,51 +16,44 @@ _METHODS = ("stacked", "max_score", "min_score", "avg_score")
 
 
 def _as_list(factors):
-    return list(factors.values()) if hasattr(factors, "values") else list(factors)
+    fs = list(factors.values()) if hasattr(factors, "values") else list(factors)
+    return [np.asarray(getattr(a, "values", a), dtype=np.float64) for a in fs]
 
 
-def _score(x1, x2, tol):
-    c = np.abs(np.conj(np.asarray(x1).T) @ np.asarray(x2))
-    n = c.shape[0] + c.shape[1]
-    s = (np.sum(np.abs(c.max(axis=1) - 1)) + np.sum(np.abs(c.max(axis=0) - 1))) / n
-    return 0 if s < tol else s
-
-
-def correlation_index(factors_1, factors_2, tol=5e-16, method="stacked"):
-    """CorrIndex in [0, 1] (0 = same decomposition up to column scaling and permutation) (metrics.py:12-97)."""
-    f1 = [np.asarray(a, dtype=float) for a in _as_list(factors_1)]
-    f2 = [np.asarray(a, dtype=float) for a in _as_list(factors_2)]
-    for fs in (f1, f2):
+def _stack(decompositions, method):
+    """[n, S, R] float64 + the mode sizes, after the reference's shape checks (metrics.py:55-75)."""
+    sets = [_as_list(f) for f in decompositions]
+    for fs in sets:
         if len({a.shape[1] for a in fs}) != 1:
             raise ValueError("Factors should be a list of loading matrices of the same rank")
     if method not in _METHODS:
         raise ValueError("The `method` must be either option among {}".format(list(_METHODS)))
-    if method == "stacked":
-        f1, f2 = [np.concatenate(f1, 0)], [np.concatenate(f2, 0)]
-    for a, b in zip(f1, f2):
-        if a.shape != b.shape:
+    first = sets[0]
+    for fs in sets[1:]:
+        if method == "stacked":
+            ok = sum(a.shape[0] for a in fs) == sum(a.shape[0] for a in first) and fs[0].shape[1] == first[0].shape[1]
+        else:
+            ok = len(fs) == len(first) and all(a.shape == b.shape for a, b in zip(fs, first))
+        if not ok:
             raise ValueError("Factor matrices should be of the same shapes")
-    scores = []
-    for a, b in zip(f1, f2):
-        na, nb = np.linalg.norm(a, axis=0), np.linalg.norm(b, axis=0)
-        if np.any(na == 0) or np.any(nb == 0):
-            raise ValueError("Column norms must be non-zero")
-        scores.append(_score(a / na, b / nb, tol))
+    sizes = [a.shape[0] for a in first]
     if method == "stacked":
-        return scores[0]
-    if method == "max_score":
-        return np.max(scores)
-    if method == "min_score":
-        return np.min(scores)
-    return np.mean(scores)
+        sizes = [sum(sizes)]
+    return np.stack([np.concatenate(fs, 0) for fs in sets], 0), sizes
+
+
+def correlation_index(factors_1, factors_2, tol=5e-16, method="stacked"):
+    """CorrIndex in [0, 1] (0 = same decomposition up to column scaling and permutation) (metrics.py:12-97)."""
+    stacked, sizes = _stack([factors_1, factors_2], method)
+    score = float(engine.corrindex_pairs(stacked, sizes, method=method, tol=tol)[0, 1])
+    return 0 if score == 0.0 else score
 
 
 def pairwise_correlation_index(factors, tol=5e-16, method="stacked"):
     """Symmetric DataFrame of CorrIndex scores between all pairs of decompositions (metrics.py:131-179)."""
     n = len(factors)
-    scores = pd.DataFrame(np.zeros((n, n)), index=range(n), columns=range(n))
-    for p1, p2 in combinations(range(n), 2):
-        s = correlation_index(factors[p1], factors[p2], tol=tol, method=method)
-        scores.at[p1, p2] = s
-        scores.at[p2, p1] = s
-    return scores
+    if n < 2:
+        return pd.DataFrame(np.zeros((n, n)), index=range(n), columns=range(n))
+    stacked, sizes = _stack(list(factors), method)
+    scores = engine.corrindex_pairs(stacked, sizes, method=method, tol=tol)
+    return pd.DataFrame(scores, index=range(n), columns=range(n))

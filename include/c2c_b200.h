@@ -186,6 +186,15 @@ int c2c_missing_rec_sumsq(const float* X, const uint8_t* mask, int ndim, const i
 int c2c_cp_normalize(float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
                      float* weights, void* stream);
 
+/* ---- CorrIndex of every pair of n decompositions (cell2cell/tensor/metrics.py:12-179: correlation_index,
+ * _compute_correlation_index, pairwise_correlation_index; called per rank from cell2cell/tensor/factorization.py:360-369).
+ * F: device double [n][rows][rank], the factor matrices of each decomposition stacked along the rows; seg_off: device
+ * int64 [nseg + 1] row offsets of the blocks scored separately ({0, rows} for method 'stacked', the mode offsets
+ * otherwise); method: 0 stacked, 1 max_score, 2 min_score, 3 avg_score; out: device double [n][n] (symmetric, zero
+ * diagonal); *status (device int, zeroed by the caller) becomes 1 when a column norm is zero (the reference raises). */
+int c2c_corrindex_pairs(const double* F, int n, int64_t rows, int rank, const int64_t* seg_off, int nseg, int method,
+                        double tol, double* out, int* status, void* stream);
+
 /* ---- whole factorization (tensorly non_negative_parafac / non_negative_parafac_hals semantics) --------------------
  * Factors A hold the initial values on entry (K7: host-seeded random or svd init is done by the caller) and the result
  * on exit.  errors: device double[n_iter_max] (tensorly's rec_errors); state: device int[2] = {iterations done,

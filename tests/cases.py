@@ -158,3 +158,87 @@ def coupled_inputs(name, seed=11):
             masks[k] = m
             out[k] = out[k] * m
     return out[0], out[1], masks[0], masks[1]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Factorization-side API goldens (tests/golden/make_golden_ncp.py): the reference's own drivers on the oracle primitives
+# ----------------------------------------------------------------------------------------------------------------------
+def _lowrank32(shape, rank, seed, noise=0.05):
+    rs = np.random.RandomState(seed)
+    fs = [rs.gamma(1.0, 1.0, size=(s, rank)) for s in shape]
+    letters = "abcdefgh"[: len(shape)]
+    x = np.einsum(",".join(l + "r" for l in letters) + "->" + letters, *fs, optimize=True)
+    x = x / x.mean() + noise * rs.random_sample(x.shape)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+_FIX = dict(n_iter_max=30, tol=-1.0, verbose=False)
+NCP_API_CASES = {
+    # BaseTensor.compute_tensor_factorization (tensor.py:216-362) through the reference's PreBuiltTensor
+    "factorize_best_of_3": dict(kind="factorize", shape=(5, 40, 6, 6), masked=False,
+                                kwargs=dict(rank=4, tf_type="non_negative_cp", init="random", random_state=3, runs=3, **_FIX)),
+    "factorize_masked": dict(kind="factorize", shape=(5, 40, 6, 6), masked=True,
+                             kwargs=dict(rank=3, tf_type="non_negative_cp", init="svd", random_state=1, runs=2, **_FIX)),
+    "factorize_unordered": dict(kind="factorize", shape=(6, 30, 8, 8), masked=False,
+                                kwargs=dict(rank=5, init="random", random_state=9, var_ordered_factors=False, **_FIX)),
+    "factorize_raw_loadings": dict(kind="factorize", shape=(6, 30, 8, 8), masked=False,
+                                   kwargs=dict(rank=3, init="random", random_state=2, normalize_loadings=False, **_FIX)),
+    "factorize_hals": dict(kind="factorize", shape=(5, 40, 6, 6), masked=False,
+                           kwargs=dict(rank=3, tf_type="non_negative_cp_hals", init="random", random_state=4, **_FIX)),
+    "factorize_3way_stop_rule": dict(kind="factorize", shape=(30, 8, 7), masked=False,
+                                     kwargs=dict(rank=3, init="random", random_state=6, n_iter_max=200, tol=1e-5, verbose=False)),
+    # elbow drivers (factorization.py:186-373)
+    "elbow_single": dict(kind="elbow_single", shape=(5, 40, 6, 6), masked=False,
+                         kwargs=dict(upper_rank=5, init="random", random_state=5, **_FIX)),
+    "elbow_single_masked": dict(kind="elbow_single", shape=(5, 40, 6, 6), masked=True,
+                                kwargs=dict(upper_rank=4, init="random", random_state=2, **_FIX)),
+    "elbow_multi_error": dict(kind="elbow_multi", shape=(5, 40, 6, 6), masked=False,
+                              kwargs=dict(upper_rank=5, runs=3, init="random", random_state=5, metric="error", **_FIX)),
+    "elbow_multi_masked": dict(kind="elbow_multi", shape=(5, 40, 6, 6), masked=True,
+                               kwargs=dict(upper_rank=3, runs=2, init="random", random_state=7, metric="error", **_FIX)),
+    "elbow_multi_similarity": dict(kind="elbow_multi", shape=(5, 40, 6, 6), masked=False,
+                                   kwargs=dict(upper_rank=4, runs=3, init="random", random_state=5, metric="similarity", **_FIX)),
+}
+
+
+def ncp_api_inputs(name, seed=21):
+    """(x fp32, mask uint8 or None, order_names) of ``NCP_API_CASES[name]``; a masked tensor holds zeros under its mask."""
+    case = NCP_API_CASES[name]
+    shape = case["shape"]
+    x = _lowrank32(shape, 4, seed, noise=0.1)
+    names = [["n%d_%d" % (k, i) for i in range(s)] for k, s in enumerate(shape)]
+    mask = None
+    if case["masked"]:
+        rs = np.random.RandomState(seed + 1)
+        mask = (rs.rand(*shape) > 0.1).astype(np.uint8)
+        mask[1, :, 2] = 0
+        x = x * mask
+    return x, mask, names
+
+
+NCP_FULL_CASES = {
+    # BASELINE config 3 at full size: 13 x 1900 x 17 x 17, how='outer'-like mask (+ 2 % arbitrary entries), rank 10
+    "config3_asd_masked": dict(shape=(13, 1900, 17, 17), true_rank=5, data_seed=3, rank=10, seed=888, n_iter=60, masked=True),
+    # BASELINE config 4 at full size and its own rank: 60 x 2000 x 40 x 40, rank 20 (tensor-pipe passes)
+    "config4_atlas_rank20": dict(shape=(60, 2000, 40, 40), true_rank=6, data_seed=5, rank=20, seed=888, n_iter=10, masked=False),
+    # BASELINE config 5 family: K = 30 (in-plane row not a multiple of 4 floats: the VEC = 2 kernels), C and L scaled
+    "config5_k30_rank12": dict(shape=(22, 870, 30, 30), true_rank=5, data_seed=7, rank=12, seed=888, n_iter=30, masked=False),
+    "config5_k30_rank30": dict(shape=(22, 870, 30, 30), true_rank=5, data_seed=7, rank=30, seed=889, n_iter=15, masked=False),
+}
+
+
+def ncp_golden_inputs(name):
+    """(x fp32, mask uint8 or None) of ``NCP_FULL_CASES[name]``."""
+    case = NCP_FULL_CASES[name]
+    shape = case["shape"]
+    x = _lowrank32(shape, case["true_rank"], case["data_seed"])
+    mask = None
+    if case["masked"]:
+        rs = np.random.RandomState(case["data_seed"] + 1)
+        mask = np.ones(shape, dtype=np.uint8)
+        mask[2::3, :, 5, :] = 0          # a cell type missing from every 3rd context (sender rows and receiver columns)
+        mask[2::3, :, :, 5] = 0
+        mask[rs.rand(shape[0], shape[1]) < 0.05] = 0   # gene pairs missing from a context: whole planes
+        mask[rs.rand(*shape) < 0.02] = 0               # arbitrary user-masked entries
+        x = x * mask
+    return x, mask

@@ -1,10 +1,11 @@
-"""Host-side pieces of elbow_rank_selection: Kneedle restatement, smooth_curve and CorrIndex (against the reference's own
-functions when /root/reference is present), and the seeded synthetic generators."""
+"""Host-side pieces of elbow_rank_selection: Kneedle restatement and smooth_curve, the CorrIndex oracle (each against the
+reference's own functions when /root/reference is present), and the seeded synthetic generators.  The product's CorrIndex is
+a device kernel: its parity test is tests/test_gpu_metrics.py."""
 import numpy as np
 import pytest
 
 from cell2cell_b200.tensor.elbow import kneedle_elbow, smooth_curve
-from cell2cell_b200.tensor.metrics import correlation_index, pairwise_correlation_index
+from oracle.metrics_oracle import correlation_index, pairwise_correlation_index
 from oracle.ref_harness import load_reference, reference_available
 
 
@@ -43,12 +44,14 @@ def test_corrindex_invariances_and_reference():
     s = correlation_index(fs, hs)
     assert 0 < s <= 1
     df = pairwise_correlation_index([fs, gs, hs])
-    assert df.shape == (3, 3) and df.at[0, 2] == df.at[2, 0] == s
+    assert df.shape == (3, 3) and df[0, 2] == df[2, 0] == s
     if reference_available():
         ref = load_reference()
         d = lambda l: dict(zip(range(len(l)), l))
         for m in ("stacked", "max_score", "min_score", "avg_score"):
-            assert correlation_index(fs, hs, method=m) == pytest.approx(ref.metrics.correlation_index(d(fs), d(hs), method=m), rel=1e-12)
+            assert correlation_index(fs, hs, method=m) == pytest.approx(ref.metrics.correlation_index(d(fs), d(hs), method=m), rel=1e-14)
+        want = ref.metrics.pairwise_correlation_index([d(fs), d(gs), d(hs)]).values
+        np.testing.assert_allclose(df, want, rtol=1e-14, atol=0)
 
 
 def test_synthetic_generators_are_seeded():
