@@ -235,10 +235,11 @@ def sharded_record(X, shape, iters, rank_id, world, dev):
             errs, n_iter, _ = engine.ncp_run_sharded(Xl, f, R, comm, n_iter_max=n, tol=-1.0, check_every=0, norm_x2=nx2, ws=ws)
             b.record()
             torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b) * 1e-3], dtype=torch.float64, device=dev)
+            t = torch.tensor([a.elapsed_time(b) * 1e-3, 1.0 if comm.failed() else 0.0], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            assert not comm.failed(), "a wait on a peer GPU timed out"
+            if float(t[1]) != 0.0:                       # agreed on by every rank: all of them leave together
+                raise RuntimeError("a wait on a peer GPU timed out")
             return float(t[0]), float(errs[-1])
         run(1, 10)
         times, err = [], None
@@ -373,6 +374,40 @@ def build_record(dev, no_cpu):
     return rec
 
 
+def config5_record(dev, world, iters, upper_rank=30, runs=20):
+    """BASELINE config 5: spatial windows 500 x 1000 x 30 x 30 (1.8 GB), elbow sweep ranks 1..30 x 20 seeds spread over the GPUs
+    of the job (independent (rank, seed) units, no data-path collective).  Every rank builds the same replica on its device
+    from host-seeded rank-5 factors (uploading 8 x 1.8 GB from one host would only measure the host)."""
+    import torch
+    import torch.distributed as dist
+    from cell2cell_b200.tensor import PreBuiltTensor
+    shape = WORKLOADS["spatial"]["shape"]
+    rs = np.random.RandomState(1)
+    fs = [torch.as_tensor(rs.gamma(1.0, 1.0, size=(s, 5)).astype(np.float32)).to(dev) for s in shape]
+    lead = (fs[0][:, None, :] * fs[1][None, :, :]).reshape(-1, 5)
+    trail = (fs[2][:, None, :] * fs[3][None, :, :]).reshape(-1, 5)
+    X = (lead @ trail.T).view(shape)
+    X /= X.mean()
+    X += 0.05 * torch.rand(shape, generator=torch.Generator(device=dev).manual_seed(1), device=dev)
+    t = PreBuiltTensor(X, order_names=[list(range(s)) for s in shape])
+    kw = dict(init="random", n_iter_max=iters, tol=-1.0, output_fig=False, automatic_elbow=False)
+    t.elbow_rank_selection(upper_rank=2, runs=2, random_state=1, **dict(kw, n_iter_max=5))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, loss = t.elbow_rank_selection(upper_rank=upper_rank, runs=runs, random_state=888, **kw)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    total_iters = upper_rank * runs * iters
+    return {"shape": list(shape), "upper_rank": upper_rank, "runs": runs, "iterations_per_run": iters, "n_gpus": world,
+            "wall_s": wall, "aggregate_iterations_per_s": total_iters / wall,
+            "loss_rank1": float(loss[0][1]), "loss_last": float(loss[-1][1]),
+            "note": "elbow_rank_selection through the public API; units spread over the GPUs by parallel.run_units"}
+
+
 def run_ours(args, rank_id, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -424,7 +459,7 @@ def run_ours(args, rank_id, local_rank, world):
     names = [list(range(s)) for s in shape]
 
     def api_step(seed):
-        t = PreBuiltTensor(x_host, order_names=names, device=dev)
+        t = PreBuiltTensor(x_host, order_names=names, device=dev, shared_upload=world > 1)
         t.compute_tensor_factorization(rank=rank, init="random", random_state=seed, n_iter_max=iters, tol=-1.0)
         return t
     for s in range(max(1, args.warmup // 3)):
@@ -515,13 +550,24 @@ def run_ours(args, rank_id, local_rank, world):
     # ---- ONE factorization sharded along the context mode over the N GPUs (BASELINE config 4; strong scaling) -----------------
     sharded = None
     if args.workload == "atlas" and args.sharded:
-        sharded = sharded_record(X, shape, iters, rank_id, world, dev)
+        try:
+            sharded = sharded_record(X, shape, iters, rank_id, world, dev)
+        except Exception as exc:            # noqa: BLE001 -- PeerComm raises on every rank together; the headline line survives
+            sharded = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300]), "n_gpus": world}
+            barrier()
+
+    # ---- BASELINE config 5 (spatial windows, elbow r1-30 x 20 seeds): on the 8-GPU job, or when asked for ---------------------
+    config5 = None
+    if args.workload == "atlas" and (args.config5 == "on" or (args.config5 == "auto" and world >= 8)):
+        config5 = config5_record(dev, world, iters)
 
     masked = small = build = None
-    if rank_id == 0 and args.workload == "atlas" and args.extras:
-        masked = masked_record(X, shape, rank, dev)
-        small = small_record(dev, iters)
-        build = build_record(dev, args.no_cpu)
+    if world == 1 and args.workload == "atlas" and args.extras:       # single-GPU records: reported by the N = 1 line only
+        from cell2cell_b200.parallel import local_only
+        with local_only():            # rank 0 alone does these: the API calls inside must not enter a collective
+            masked = masked_record(X, shape, rank, dev)
+            small = small_record(dev, iters)
+            build = build_record(dev, args.no_cpu)
 
     # ---- per-kernel roofline (rank 0 only reports) ---------------------------------------------------------------------
     f = fresh_factors(1)
@@ -559,7 +605,10 @@ def run_ours(args, rank_id, local_rank, world):
                    "multi_gpu": "independent (rank, seed) factorizations per GPU, no collective"},
         "e2e": {"value": world * e2e_steps * iters / e2e_sec, "unit": "iterations/s", "h2d_bytes_per_step": n_x * 4,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_sec / e2e_steps,
-                "api": "PreBuiltTensor(pinned host fp32).compute_tensor_factorization(rank, init='random', n_iter_max=%d, tol=-1)" % iters},
+                "api": "PreBuiltTensor(pinned host fp32%s).compute_tensor_factorization(rank, init='random', n_iter_max=%d, tol=-1)" % (
+                    ", shared_upload=True" if world > 1 else "", iters),
+                **({"upload": "the N replicas of the host tensor cost ONE host-to-device transfer of it per step in total: every "
+                              "rank uploads 1/N, an NCCL all-gather over NVLink assembles the replicas"} if world > 1 else {})},
         "gpu_launches": int(launches),
         "clocks": my_clk,
         "per_gpu_ms_per_step": [round(1e3 * float(v) / args.steps, 3) for v in per_rank],
@@ -580,7 +629,8 @@ def run_ours(args, rank_id, local_rank, world):
         line["rank20"] = r20
     if coupled is not None:
         line["coupled"] = coupled
-    for key, rec in (("sharded", sharded), ("masked", masked), ("small_tensors", small), ("build", build)):
+    for key, rec in (("sharded", sharded), ("config5_elbow_sweep", config5), ("masked", masked), ("small_tensors", small),
+                     ("build", build)):
         if rec is not None:
             line[key] = rec
     if not args.no_cpu:
@@ -674,6 +724,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-coupled", dest="coupled", action="store_false", help="skip the coupled-factorization line")
     ap.add_argument("--no-elbow", dest="elbow", action="store_false", help="skip the elbow-sweep wall time (second BASELINE metric)")
+    ap.add_argument("--config5", default="auto", choices=["auto", "on", "off"],
+                    help="elbow sweep of BASELINE config 5 (500x1000x30x30, r1-30 x 20 seeds): auto = on the 8-GPU job only")
     ap.add_argument("--no-sharded", dest="sharded", action="store_false", help="skip the context-sharded factorization record")
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the masked / small-tensor / build records")
     ap.add_argument("--elbow-ranks", type=int, default=25)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "c2c_recon_sums": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
     "c2c_missing_rec_sumsq": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
     "c2c_cp_normalize": (_i, [_c.POINTER(_p), _i, _c.POINTER(_i64), _i, _i, _p, _p]),
+    "c2c_admm_update": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _c.c_double, _i, _c.c_double, _p, _p]),
     "c2c_corrindex_pairs": (_i, [_p, _i, _i64, _i, _p, _i, _i, _c.c_double, _p, _p, _p]),
     "c2c_ncp_run": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _i, _c.c_double, _i, _p, _p, _p, _i,
                          _p, _sz, _p]),

@@ -23,6 +23,7 @@
 #include "c2c_multi.cuh"
 #include "c2c_xgpu.cuh"
 #include "c2c_metrics.cuh"
+#include "c2c_admm.cuh"
 #include "../../include/c2c_b200.h"
 
 #include <atomic>
@@ -1097,6 +1098,20 @@ extern "C" int c2c_cp_normalize(float* const* A, int ndim, const int64_t* shape,
         cp_normalize_kernel<<<1, C2C_SMALL_THREADS, 0, (cudaStream_t)stream>>>(A[k], shape[k], rank, ldr, weights, k == 0 ? 1 : 0);
         CKL("cp_normalize launch");
     }
+    return 0;
+}
+
+extern "C" int c2c_admm_update(float* A_mode, double* X64, double* dual, double* aux, const float* M, const float* G, int64_t I,
+                               int rank, int ldr, int constraint, double param, int n_inner, double tol, double* out, void* stream)
+{
+    if (!A_mode || !X64 || !dual || !aux || !M || !G || !out) return fail(-1, "NULL argument");
+    if (I < 1 || rank < 1 || rank > C2C_MAX_RANK || ldr != ldr_of(rank)) return fail(-2, "bad I / rank / ldr");
+    if (constraint < 0 || constraint > 3) return fail(-3, "constraint must be 0 (none), 1 (non_negative), 2 (l1_reg) or 3 (l2_square_reg)");
+    if (n_inner < 1) return fail(-4, "n_inner must be >= 1");
+    const cudaError_t e = c2c_launch_admm_update(A_mode, X64, dual, aux, M, G, I, rank, ldr, constraint, param, n_inner, tol, out,
+                                                 (cudaStream_t)stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "admm_update launch");
     return 0;
 }
 

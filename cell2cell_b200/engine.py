@@ -250,6 +250,23 @@ def cp_normalize(factors, rank, weights=None):
         return w
 
 
+ADMM_CONSTRAINTS = {None: 0, "non_negative": 1, "l1_reg": 2, "l2_square_reg": 3}
+
+
+def admm_update(A, X64, dual, aux, M, G, rank, constraint=None, param=0.0, n_inner=10, tol=1e-6, out=None):
+    """One mode's ADMM update of ``constrained_parafac`` in place (``c2c_admm_update``): ``A`` packed fp32 ``[I, ldr]``,
+    ``X64`` / ``dual`` / ``aux`` fp64 ``[I, rank]``, ``M`` packed MTTKRP, ``G`` the ``[ldr, ldr]`` Hadamard-Gram.  Returns the
+    device ``double[2]`` = (this mode's constraint-error term, inner iterations made)."""
+    dev = A.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(2, dtype=torch.float64, device=dev)
+        check(lib().c2c_admm_update(_ptr(A), _ptr(X64), _ptr(dual), _ptr(aux), _ptr(M), _ptr(G), int(A.shape[0]), int(rank),
+                                    ldr_of(rank), ADMM_CONSTRAINTS[constraint], float(param), int(n_inner), float(tol), _ptr(out),
+                                    _stream()), "c2c_admm_update")
+        return out
+
+
 _CORR_METHODS = {"stacked": 0, "max_score": 1, "min_score": 2, "avg_score": 3}
 
 

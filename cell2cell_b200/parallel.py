@@ -12,12 +12,32 @@ no collective on the data path.
 import numpy as np
 import torch
 
-__all__ = ["world", "lpt_schedule", "run_units"]
+__all__ = ["world", "lpt_schedule", "run_units", "local_only"]
+
+_local_only = 0
+
+
+class local_only:
+    """``with local_only():`` -- inside, this process is a world of one for ``run_units`` / ``world`` even when
+    ``torch.distributed`` is initialised: work that only SOME ranks do (a report on rank 0, a per-rank side computation) must
+    not enter a collective the other ranks never join."""
+
+    def __enter__(self):
+        global _local_only
+        _local_only += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _local_only
+        _local_only -= 1
+        return False
 
 
 def world():
     """(rank, world_size) of the initialised default process group, else (0, 1)."""
     import torch.distributed as dist
+    if _local_only:
+        return 0, 1
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1

@@ -23,7 +23,8 @@ import torch
 from . import engine
 from .tensor.cp import CPTensor
 
-__all__ = ["shard_bounds", "DeviceOps", "PeerComm", "sharded_non_negative_parafac"]
+__all__ = ["shard_bounds", "DeviceOps", "PeerComm", "sharded_non_negative_parafac", "build_sharded_interaction_tensor",
+           "compute_sharded_tensor_factorization"]
 
 
 def shard_bounds(n, world, rank):
@@ -117,26 +118,38 @@ class PeerComm:
             self.ptrs = [self.local]
             self.epoch = 1
             if self.world > 1:
+                # A failure on ONE rank must not leave the others waiting in a collective it never joins: every step below ends
+                # in an all-reduce of a success flag (which is also the barrier the protocol needs), and all ranks raise together.
+                def agree(ok, what):
+                    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                    if int(flag.item()) == 0:
+                        raise engine.C2CError("peer-memory setup failed on some rank: " + what)
+
                 objs = [None] * self.world
                 dist.all_gather_object(objs, (int(device.index), bytes(handle)), group=group)
                 self.ptrs = []
-                for r, (didx, h) in enumerate(objs):
-                    if r == self.me:
-                        self.ptrs.append(self.local)
-                        continue
-                    engine.check(lib.c2c_enable_peer_access(int(didx)), "c2c_enable_peer_access")
-                    p = ctypes.c_void_p()
-                    engine.check(lib.c2c_comm_open((ctypes.c_ubyte * 64)(*h), ctypes.byref(p)), "c2c_comm_open")
-                    self.ptrs.append(int(p.value))
-                dist.barrier(group)                     # every rank has opened every buffer before anyone writes
+                problem = None
+                try:
+                    for r, (didx, h) in enumerate(objs):
+                        if r == self.me:
+                            self.ptrs.append(self.local)
+                            continue
+                        engine.check(lib.c2c_enable_peer_access(int(didx)), "c2c_enable_peer_access")
+                        p = ctypes.c_void_p()
+                        engine.check(lib.c2c_comm_open((ctypes.c_ubyte * 64)(*h), ctypes.byref(p)), "c2c_comm_open")
+                        self.ptrs.append(int(p.value))
+                except Exception as exc:                      # noqa: BLE001 -- reported through the agreement below
+                    problem = exc
+                # every rank has opened every buffer before anyone writes
+                agree(problem is None, "mapping the peers' buffers (CUDA IPC / peer access)%s" % ("" if problem is None else ": %s" % problem))
                 out = torch.zeros(1, dtype=torch.float32, device=device)
                 arr = (ctypes.c_void_p * self.world)(*self.ptrs)
-                engine.check(lib.c2c_comm_probe(self.world, self.me, arr, self.nbytes, self.epoch, 3.0, ctypes.c_void_p(out.data_ptr()),
-                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "c2c_comm_probe")
+                rc = lib.c2c_comm_probe(self.world, self.me, arr, self.nbytes, self.epoch, 3.0, ctypes.c_void_p(out.data_ptr()),
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
                 self.epoch += 2
                 got, want = float(out.item()), 3.0 * self.world * (self.world + 1) / 2
-                if got != want or self.failed():
-                    raise engine.C2CError("peer-memory exchange between the GPUs failed its probe (%r != %r)" % (got, want))
+                agree(rc == 0 and got == want and not self.failed(), "the probe exchange (%r != %r)" % (got, want))
 
     @classmethod
     def get(cls, nbytes, device, group=None):
@@ -172,7 +185,10 @@ def _fused_sharded(X_local, full_shape, rank, init_factors, n_iter_max, tol, gro
             dist.barrier(group)                     # the ranks' kernels start together (a wait on a peer gives up after ~5 s)
         errs, n_iter, _ = engine.ncp_run_sharded(X_local, A, rank, comm, n_iter_max=n_iter_max, tol=tol,
                                                  cvg_criterion=cvg_criterion, norm_x2=nx2, ws=ws)
-        if comm.failed():
+        failed = torch.tensor([1 if comm.failed() else 0], dtype=torch.int32, device=dev)
+        if world > 1:
+            dist.all_reduce(failed, op=dist.ReduceOp.MAX, group=group)     # every rank raises, or none does
+        if int(failed.item()):
             raise engine.C2CError("sharded factorization: a wait on a peer GPU timed out; the results are invalid")
         A0 = torch.zeros((full_shape[0], engine.ldr_of(rank)), dtype=torch.float32, device=dev)
         A0[lo:hi] = A[0]
@@ -314,3 +330,55 @@ def sharded_non_negative_parafac(X_local, full_shape, rank, init_factors, n_iter
             errors = hist
     factors = [ops.unpack(A_full0).cpu().numpy()] + [ops.unpack(a).cpu().numpy() for a in A[1:]]
     return CPTensor(np.ones(rank, dtype=np.float32), factors, device=dev if dev.type == "cuda" else None), errors
+
+
+def build_sharded_interaction_tensor(rnaseq_matrices, ppi_data, group=None, **kwargs):
+    """This rank's context slab of ``InteractionTensor(rnaseq_matrices, ppi_data, **kwargs)`` (tensor
+    build row): every rank resolves the same genes / cells / LR pairs from the names of ALL contexts (host side, cheap) and
+    uploads and builds only the contexts ``shard_bounds(C, world, rank)`` -- the reference's loop over contexts
+    (tensor.py:1126-1129) has no cross-context dependency.  The result feeds ``compute_sharded_tensor_factorization``."""
+    import torch.distributed as dist
+    from .tensor import InteractionTensor
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    me = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_bounds(len(rnaseq_matrices), world, me)
+    return InteractionTensor(rnaseq_matrices, ppi_data, context_slab=(lo, hi), **kwargs)
+
+
+def compute_sharded_tensor_factorization(interaction_tensor, rank, init="random", random_state=None, n_iter_max=100, tol=10e-7,
+                                         normalize_loadings=True, var_ordered_factors=True, group=None):
+    """``compute_tensor_factorization`` (tensor.py:216-362, tf_type='non_negative_cp', one run) for a tensor whose context mode
+    is spread over the ranks of ``group``: ``interaction_tensor`` holds this rank's slab (``build_sharded_interaction_tensor``).
+    Sets ``tl_object``, ``norm_tl_object``, ``factors`` (the FULL factor DataFrames, identical on every rank),
+    ``explained_variance_ratio_`` and ``rank`` on it and returns the error history.  Host-seeded random init only (an svd init
+    needs the unfoldings of the whole tensor); unmasked tensors (how='inner')."""
+    from collections import OrderedDict
+    import pandas as pd
+    from .tensor.cp import random_factors
+    from .tensor.tensor import _cp_normalize
+    t = interaction_tensor
+    if t.mask is not None:
+        raise NotImplementedError("the context-sharded factorization takes unmasked tensors (how='inner')")
+    if init != "random":
+        raise NotImplementedError("the context-sharded factorization takes init='random' (host-seeded, identical on every rank)")
+    full_c = int(getattr(t, "full_contexts", t.tensor.shape[0]))
+    full_shape = (full_c,) + tuple(int(s) for s in t.tensor.shape[1:])
+    init_factors = random_factors(full_shape, rank, random_state)
+    cp, errors = sharded_non_negative_parafac(t.tensor, full_shape, rank, init_factors, n_iter_max=n_iter_max, tol=tol, group=group)
+    t.tl_object = cp
+    names = [list(getattr(t, "full_context_names", t.order_names[0]))] + [list(n) for n in t.order_names[1:]]
+    labels = t.order_labels or ["Contexts", "Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
+    if normalize_loadings:
+        t.norm_tl_object = _cp_normalize(cp)
+        weights, factors = t.norm_tl_object
+        weights = np.asarray(weights)
+        order = weights.argsort()[::-1] if var_ordered_factors else np.arange(rank)
+        factors = [np.asarray(f)[:, order] for f in factors]
+        t.explained_variance_ratio_ = weights[order] / sum(weights)
+    else:
+        factors = [np.asarray(f) for f in cp.factors]
+        t.explained_variance_ratio_ = None
+    cols = ["Factor {}".format(i) for i in range(1, rank + 1)]
+    t.factors = OrderedDict(zip(labels, [pd.DataFrame(f, index=idx, columns=cols) for f, idx in zip(factors, names)]))
+    t.rank = rank
+    return errors

@@ -18,17 +18,48 @@ from .._lib import C2CError
 from .cp import CPTensor, initialize_factors
 from .elbow import kneedle_elbow
 
-__all__ = ["non_negative_parafac", "non_negative_parafac_hals", "_compute_tensor_factorization", "_compute_elbow",
+__all__ = ["non_negative_parafac", "non_negative_parafac_hals", "parafac", "constrained_parafac", "_compute_tensor_factorization", "_compute_elbow",
            "_run_elbow_analysis", "_multiple_runs_elbow_analysis", "_compute_norm_error", "normalized_error",
            "as_device_tensor", "as_device_mask"]
 
 
-def as_device_tensor(tensor, device=None):
-    """fp32 contiguous CUDA view / copy of ``tensor`` (numpy or torch, any float or int dtype)."""
+def _shared_upload(host, dev, group=None):
+    """The SAME host tensor on every rank of ``group`` -> an fp32 replica on every GPU with ONE host-to-device transfer of
+    it in total: rank k uploads the k-th of ``world`` near-equal pieces, then an NCCL all-gather over NVLink assembles the
+    replicas.  N simultaneous full uploads share the host's memory / PCIe root (measured: 8 x 768 MB copies take 2.6 x one
+    copy); the all-gather moves the same bytes at NVLink speed instead."""
+    import torch.distributed as dist
+    world, me = dist.get_world_size(group), dist.get_rank(group)
+    flat = host.reshape(-1)
+    n = flat.numel()
+    piece = -(-n // world)
+    piece = -(-piece // 4) * 4                      # keeps every piece, and the replica's base, 16-byte aligned
+    full = torch.empty(piece * world, dtype=torch.float32, device=dev)
+    lo, hi = min(me * piece, n), min((me + 1) * piece, n)
+    mine = full[me * piece:(me + 1) * piece]
+    if hi > lo:
+        mine[:hi - lo].copy_(flat[lo:hi], non_blocking=True)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n].view(host.shape)
+
+
+def as_device_tensor(tensor, device=None, shared_upload=False, group=None):
+    """fp32 contiguous CUDA view / copy of ``tensor`` (numpy or torch, any float or int dtype).
+
+    ``shared_upload=True`` (with ``torch.distributed`` initialised on NCCL): the caller states that every rank of ``group``
+    passes the same host tensor -- the replicas of an elbow sweep or of best-of-runs -- and the upload is split over the ranks
+    (``_shared_upload``)."""
     if isinstance(tensor, torch.Tensor) and tensor.is_cuda and device is None:
         dev = tensor.device
     else:
         dev = engine.require_cuda(device)
+    if shared_upload:
+        import torch.distributed as dist
+        host = tensor if isinstance(tensor, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(tensor)))
+        if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and not host.is_cuda
+                and host.dtype == torch.float32 and dist.get_backend(group) == "nccl"):
+            with torch.cuda.device(dev):
+                return _shared_upload(host.contiguous(), dev, group)
     if isinstance(tensor, torch.Tensor):
         t = tensor.to(device=dev, dtype=torch.float32)
     else:
@@ -278,6 +309,111 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", svd="truncated_svd", norma
     return cp
 
 
+_ADMM_UNSUPPORTED = ("l2_reg", "unimodality", "normalize", "simplex", "normalized_sparsity", "soft_sparsity", "smoothness",
+                     "monotonicity", "hard_sparsity")
+
+
+def _mode_constraint(mode, non_negative, l1_reg, l2_square_reg):
+    """tensorly ``proximal_operator``'s per-mode selection: scalar = every mode, dict / list = the modes named; one per mode."""
+    found = []
+    for name, val in (("non_negative", non_negative), ("l1_reg", l1_reg), ("l2_square_reg", l2_square_reg)):
+        if val is None:
+            continue
+        v = val.get(mode) if isinstance(val, dict) else (val[mode] if isinstance(val, (list, tuple)) else val)
+        if v is None or v is False:
+            continue
+        found.append((name, 0.0 if name == "non_negative" else float(v)))
+    if len(found) > 1:
+        raise ValueError("You selected two constraints for the same mode. Consider to check your input")
+    return found[0] if found else (None, 0.0)
+
+
+def constrained_parafac(tensor, rank, n_iter_max=100, n_iter_max_inner=10, init="svd", svd="truncated_svd", tol_outer=1e-8,
+                        tol_inner=1e-6, random_state=None, verbose=0, return_errors=False, cvg_criterion="abs_rec_error",
+                        fixed_modes=None, non_negative=None, l1_reg=None, l2_reg=None, l2_square_reg=None, unimodality=None,
+                        normalize=None, simplex=None, normalized_sparsity=None, soft_sparsity=None, smoothness=None,
+                        monotonicity=None, hard_sparsity=None):
+    """tensorly ``constrained_parafac`` (AO-ADMM) on the device -- reached from cell2cell with
+    ``tf_type='constrained_parafac'`` (factorization.py:128-136; no mask and no ``tol`` are passed on that path).
+
+    The tensor work is the two streaming passes of the NCP path (``T`` serves the leading modes, ``U`` the two trailing
+    ones: two reads of the tensor per outer iteration); a mode's whole inner ADMM loop -- Cholesky of ``G + rho I``, the
+    row solves, the proximal step, the dual update and the stop rule -- is ONE single-CTA kernel (``c2c_admm_update``,
+    csrc/c2c_admm.cu) with the factor, dual and split variables kept in fp64 on the device.  Constraints: ``non_negative``,
+    ``l1_reg``, ``l2_square_reg`` (scalar, dict or list per mode, one per mode) or none; the rest of tensorly's proximal
+    family raises ``NotImplementedError``."""
+    given = dict(l2_reg=l2_reg, unimodality=unimodality, normalize=normalize, simplex=simplex,
+                 normalized_sparsity=normalized_sparsity, soft_sparsity=soft_sparsity, smoothness=smoothness,
+                 monotonicity=monotonicity, hard_sparsity=hard_sparsity)
+    for name in _ADMM_UNSUPPORTED:
+        if given[name] is not None:
+            raise NotImplementedError("constrained_parafac(%s=...) is not supported by the B200 path (non_negative, l1_reg, "
+                                      "l2_square_reg are)" % name)
+    if fixed_modes:
+        raise NotImplementedError("constrained_parafac(fixed_modes=...) is not supported by the B200 path")
+    if cvg_criterion not in ("abs_rec_error", "rec_error"):
+        raise TypeError("Unknown convergence criterion")
+    rank = int(rank)
+    X = as_device_tensor(tensor)
+    if X.dim() < 3:
+        raise C2CError("the B200 path factorizes tensors of order >= 3")
+    nd, shape, dev = X.dim(), tuple(X.shape), X.device
+    cons = [_mode_constraint(m, non_negative, l1_reg, l2_square_reg) for m in range(nd)]
+    if isinstance(init, str) and init == "svd":
+        # initialize_constrained_parafac: left singular vectors, mode 0 scaled by the singular values -- what svd_factors
+        # returns with non_negative=False
+        host = initialize_factors(X, rank, init="svd", svd=svd, random_state=random_state, non_negative=False)
+    else:
+        host = initialize_factors(X, rank, init=init, svd=svd, random_state=random_state, non_negative=False)
+
+    def prox_host(f, name, param):
+        if name == "non_negative":
+            return np.clip(f, 0, None)
+        if name == "l1_reg":
+            return np.sign(f) * np.maximum(np.abs(f) - param, 0)
+        if name == "l2_square_reg":
+            return f / (1 + 2 * param)
+        return f
+    host = [prox_host(np.asarray(f, dtype=np.float64), *cons[m]) for m, f in enumerate(host)]
+    factors = [engine.pack_factor(f.astype(np.float32), rank, dev) for f in host]
+    x64 = [torch.as_tensor(np.ascontiguousarray(f)).to(dev) for f in host]
+    duals = [torch.zeros_like(f) for f in x64]
+    auxs = [torch.zeros_like(f) for f in x64]
+    ws = engine.Workspace(shape, rank, False, dev)
+    gws = engine.Workspace(shape, rank, False, dev)
+    nx2 = torch.tensor(getattr(X, "_c2c_norm_x2", None) or engine.sumsq(X), dtype=torch.float64, device=dev)
+    cerr = torch.zeros((nd, 2), dtype=torch.float64, device=dev)
+    errors = []
+    G, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=0, ws=gws, as_tensor=True)
+    for it in range(int(n_iter_max)):
+        TU = Mk = None
+        for mode in range(nd):
+            if mode == 0:
+                TU = engine.plane_contract(X, None, factors, rank, ws=ws)
+            elif mode == nd - 2:
+                TU = engine.fiber_contract(X, None, factors, rank, ws=ws)
+            Mk = engine.mttkrp_from_contraction(TU, shape, factors, rank, mode)
+            engine.admm_update(factors[mode], x64[mode], duals[mode], auxs[mode], Mk, G, rank, constraint=cons[mode][0],
+                               param=cons[mode][1], n_inner=n_iter_max_inner, tol=tol_inner, out=cerr[mode])
+            G, rn2 = engine.gram_hadamard(factors, shape, rank, skip_mode=(mode + 1) % nd, ws=gws, as_tensor=True,
+                                          changed_mode=mode)
+        iprod = (Mk[:, :rank].double() * x64[-1]).sum()
+        both = torch.stack([torch.sqrt(torch.abs(nx2 + rn2[0] - 2.0 * iprod)) / torch.sqrt(nx2), cerr[:, 0].sum()]).cpu()
+        errors.append(float(both[0]))
+        if verbose:
+            print("iteration {}, reconstruction error: {}, constraints error: {}".format(it, errors[-1], float(both[1])))
+        if tol_outer and it >= 1:
+            dec = errors[-2] - errors[-1]
+            if float(both[1]) < tol_outer:
+                break
+            if (abs(dec) < tol_outer) if cvg_criterion == "abs_rec_error" else (dec < tol_outer):
+                break
+    cp = CPTensor(np.ones(rank, dtype=np.float32), [f.cpu().numpy() for f in x64], device=dev)
+    if return_errors:
+        return cp, [np.float64(e) for e in errors]
+    return cp
+
+
 def _compute_tensor_factorization(tensor, rank, tf_type="non_negative_cp", init="svd", svd="truncated_svd",
                                   random_state=None, mask=None, n_iter_max=100, tol=10e-7, verbose=False, **kwargs):
     """Same contract as the reference's ``_compute_tensor_factorization`` (factorization.py:14-143)."""
@@ -300,8 +436,11 @@ def _compute_tensor_factorization(tensor, rank, tf_type="non_negative_cp", init=
                                 random_state=random_state, mask=mask, n_iter_max=n_iter_max, tol=tol, verbose=verbose,
                                 return_errors=True, **kwargs)
     elif tf_type == "constrained_parafac":
-        raise NotImplementedError("tf_type='constrained_parafac' (tensorly's AO-ADMM) is outside the B200 hot path "
-                                  "(non_negative_cp, non_negative_cp_hals, parafac)")
+        # factorization.py:128-136: neither `mask` nor `tol` reach tensorly on this path (tol_outer keeps its default)
+        kwargs.pop("return_errors", None)
+        cp_tf, errors = constrained_parafac(tensor=tensor, rank=rank, init="random" if mask is not None else init, svd=svd,
+                                            random_state=random_state, n_iter_max=n_iter_max, verbose=verbose,
+                                            return_errors=True, **kwargs)
     else:
         raise ValueError("Not a valid tf_type.")
     if return_errors:

@@ -386,7 +386,11 @@ def _to_f32(df):
 
 
 def _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction, communication_score, complex_sep, complex_agg_method,
-           upper_letter_comparison, interaction_columns, group_ppi_by, group_ppi_method, device):
+           upper_letter_comparison, interaction_columns, group_ppi_by, group_ppi_method, device, context_slab=None):
+    """``context_slab=(lo, hi)``: the gene / cell / LR-pair selection is made over ALL contexts (names only, host side), but
+    only the matrices of contexts ``lo..hi-1`` are uploaded and only that slab ``[hi - lo, L, K, K]`` of the tensor is built
+    -- the contexts are independent (the reference loops over them, tensor.py:1126-1129), so a rank of a context-sharded
+    factorization builds exactly its own shard."""
     if communication_score not in _SCORES:
         raise ValueError("Not a valid communication_score")
     if how not in ("inner", "outer", "outer_genes", "outer_cells"):
@@ -403,6 +407,11 @@ def _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction, communication
     ppi = bi.filter_lr_pairs(ppi_data, genes, complex_sep, upper_letter_comparison, interaction_columns)
     col_a, col_b = interaction_columns
     lig, rec = ppi[col_a].tolist(), ppi[col_b].tolist()
+    if context_slab is not None:
+        lo, hi = (int(v) for v in context_slab)
+        if not 0 <= lo < hi <= len(tables):
+            raise ValueError("context_slab %r is not a non-empty range of the %d contexts" % (context_slab, len(tables)))
+        tables, columns, rnaseq_matrices = tables[lo:hi], columns[lo:hi], rnaseq_matrices[lo:hi]
     C, L, K = len(tables), len(lig), len(cells)
     idx = bi.resolve(tables, columns, genes, cells, lig, rec)
     mats = [_to_f32(df) for df in rnaseq_matrices]
@@ -434,14 +443,15 @@ def _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction, communication
 def build_context_ccc_tensor(rnaseq_matrices, ppi_data, how="inner", outer_fraction=0.0,
                              communication_score="expression_product", complex_sep=None, upper_letter_comparison=True,
                              interaction_columns=("A", "B"), group_ppi_by=None, group_ppi_method="gmean", verbose=True,
-                             device=None):
+                             device=None, context_slab=None):
     """Same contract as the reference's ``build_context_ccc_tensor`` (tensor.py:973-1146): returns
     ``(tensor, genes, cells, ppi_names, mask)`` -- tensor fp32 ``[C, L, K, K]`` and mask uint8 (None for how='inner') as
     CUDA tensors.  The matrices are used as given: protein complexes must already be rows (``InteractionTensor`` adds
-    them), and -- as in the reference -- only the PPI names are upper-cased by ``upper_letter_comparison``."""
+    them), and -- as in the reference -- only the PPI names are upper-cased by ``upper_letter_comparison``.
+    ``context_slab=(lo, hi)`` (not in the reference) builds only those contexts' slab of the same tensor."""
     tables = [bi.plain_rows(list(df.index)) for df in rnaseq_matrices]
     return _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction, communication_score, complex_sep, "min",
-                  upper_letter_comparison, interaction_columns, group_ppi_by, group_ppi_method, device)
+                  upper_letter_comparison, interaction_columns, group_ppi_by, group_ppi_method, device, context_slab)
 
 
 class InteractionTensor(BaseTensor):
@@ -451,7 +461,10 @@ class InteractionTensor(BaseTensor):
     def __init__(self, rnaseq_matrices, ppi_data, order_labels=None, context_names=None, how="inner", outer_fraction=0.0,
                  communication_score="expression_mean", complex_sep=None, complex_agg_method="min",
                  upper_letter_comparison=True, interaction_columns=("A", "B"), group_ppi_by=None,
-                 group_ppi_method="gmean", device=None, verbose=True):
+                 group_ppi_method="gmean", device=None, verbose=True, context_slab=None):
+        """``context_slab=(lo, hi)`` (not in the reference): this object holds only the slab of contexts ``lo..hi-1`` of the
+        tensor the full list would give -- same genes, cells, LR pairs and values -- e.g. one rank's shard of a
+        context-sharded factorization (``cell2cell_b200.sharded``); ``full_contexts`` keeps the full context count."""
         if group_ppi_by is not None:
             assert group_ppi_by in ppi_data.columns, \
                 "Using {} for grouping PPIs is not possible. Not present among columns in ppi_data".format(group_ppi_by)
@@ -471,9 +484,14 @@ class InteractionTensor(BaseTensor):
         tensor, genes, cells, ppi_names, mask = _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction,
                                                        communication_score, complex_sep, complex_agg_method,
                                                        upper_letter_comparison, interaction_columns, group_ppi_by,
-                                                       group_ppi_method, device)
+                                                       group_ppi_method, device, context_slab)
         if context_names is None:
             context_names = ["C-" + str(i) for i in range(1, len(rnaseq_matrices) + 1)]
+        self.full_contexts = len(rnaseq_matrices)
+        self.full_context_names = list(context_names)
+        self.context_slab = None if context_slab is None else (int(context_slab[0]), int(context_slab[1]))
+        if context_slab is not None:
+            context_names = list(context_names)[self.context_slab[0]:self.context_slab[1]]
         self.communication_score = communication_score
         self.how = how
         self.outer_fraction = outer_fraction
@@ -488,12 +506,14 @@ class InteractionTensor(BaseTensor):
 class PreBuiltTensor(BaseTensor):
     """Wraps an existing N-way array (N >= 3) (tensor.py:886-970)."""
 
-    def __init__(self, tensor, order_names, order_labels=None, mask=None, loc_nans=None, device=None):
+    def __init__(self, tensor, order_names, order_labels=None, mask=None, loc_nans=None, device=None, shared_upload=False):
+        """``shared_upload=True`` (not in the reference; needs ``torch.distributed`` on NCCL): every rank of the job passes the
+        same host fp32 tensor, so each uploads 1 / world of it and an all-gather over NVLink builds the replicas."""
         BaseTensor.__init__(self)
         t = tensor.detach() if isinstance(tensor, torch.Tensor) else np.asarray(tensor)
         if device is None and isinstance(t, torch.Tensor) and t.is_cuda:
             device = t.device
-        X = as_device_tensor(t, device)                  # NaN / inf survive the cast to fp32; scanned on the device
+        X = as_device_tensor(t, device, shared_upload=shared_upload)   # NaN / inf survive the cast to fp32; scanned on the device
         # one reduction pass decides whether the clean-up passes (loc_nans, nan_to_num: tensor.py:933-946) are needed at all:
         # sum(x^2) is finite only if every entry is (it is also the ||X||^2 the factorization needs, so it is kept)
         nx2 = engine.sumsq(X)

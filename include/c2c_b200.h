@@ -186,6 +186,15 @@ int c2c_missing_rec_sumsq(const float* X, const uint8_t* mask, int ndim, const i
 int c2c_cp_normalize(float* const* A /*host array*/, int ndim, const int64_t* shape /*host*/, int ldr, int rank,
                      float* weights, void* stream);
 
+/* ---- one mode's update of tensorly's constrained_parafac (AO-ADMM; tensorly/solvers/admm.py `admm`), reached from cell2cell
+ * with tf_type='constrained_parafac' (cell2cell/tensor/factorization.py:128-136).  M: this mode's MTTKRP [I x ldr] fp32;
+ * G: Hadamard product of the other modes' Grams [ldr x ldr] fp32 (c2c_gram_hadamard); X64 / dual / aux: the factor, the dual
+ * variable and the split variable [I x rank] fp64, kept by the caller between outer iterations; A_mode [I x ldr] fp32 receives
+ * the new factor for the streaming passes.  constraint: 0 none, 1 non_negative, 2 l1_reg(param), 3 l2_square_reg(param).
+ * out: device double[2] = {||x - aux|| / ||x|| (this mode's term of tensorly's constraint error), inner iterations made}. */
+int c2c_admm_update(float* A_mode, double* X64, double* dual, double* aux, const float* M, const float* G, int64_t I,
+                    int rank, int ldr, int constraint, double param, int n_inner, double tol, double* out, void* stream);
+
 /* ---- CorrIndex of every pair of n decompositions (cell2cell/tensor/metrics.py:12-179: correlation_index,
  * _compute_correlation_index, pairwise_correlation_index; called per rank from cell2cell/tensor/factorization.py:360-369).
  * F: device double [n][rows][rank], the factor matrices of each decomposition stacked along the rows; seg_off: device

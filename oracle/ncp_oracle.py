@@ -30,6 +30,7 @@ import numpy as np
 __all__ = [
     "CPResult", "random_init", "svd_init", "initialize_cp", "mttkrp", "cp_to_tensor", "cp_norm", "cp_normalize",
     "non_negative_parafac", "non_negative_parafac_hals", "hals_nnls", "masked_norm_error", "unfold", "parafac",
+    "constrained_parafac", "admm",
 ]
 
 
@@ -382,3 +383,110 @@ def parafac(tensor, rank, n_iter_max=100, init="svd", tol=1e-8, random_state=Non
                 break
     out = (CPResult(weights, factors), errors)
     return out + (it_done,) if return_iters else out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# tensorly.decomposition.constrained_parafac (AO-ADMM) -- reached from cell2cell/tensor/factorization.py:128-136
+# --------------------------------------------------------------------------------------------------------------------
+def _constraint_of(mode, n_modes, non_negative=None, l1_reg=None, l2_square_reg=None):
+    """tensorly ``proximal_operator`` / ``validate_constraints``: a constraint given as a scalar applies to every mode, as a
+    dict ``{mode: value}`` or a list (one entry per mode) to the modes it names; at most one constraint per mode."""
+    found = []
+    for name, val in (("non_negative", non_negative), ("l1_reg", l1_reg), ("l2_square_reg", l2_square_reg)):
+        if val is None:
+            continue
+        if isinstance(val, dict):
+            v = val.get(mode)
+        elif isinstance(val, (list, tuple)):
+            v = val[mode]
+        else:
+            v = val
+        if v is None or v is False:
+            continue
+        found.append((name, v))
+    if len(found) > 1:
+        raise ValueError("You selected two constraints for the same mode. Consider to check your input")
+    return found[0] if found else (None, None)
+
+
+def _prox(x, name, param):
+    """tensorly.tenalg.proximal: non_negative -> clip(x, 0, max(x)); l1_reg -> soft thresholding; l2_square_reg -> x / (1 + 2 reg)."""
+    if name == "non_negative":
+        return np.clip(x, 0, None)
+    if name == "l1_reg":
+        return np.sign(x) * np.maximum(np.abs(x) - param, 0)
+    if name == "l2_square_reg":
+        return x / (1 + 2 * param)
+    return x
+
+
+def admm(utm, utu, x, dual, n_iter_max, constraint, param, tol):
+    """tensorly/solvers/admm.py ``admm`` with ``n_const`` given (the constrained_parafac call)."""
+    rho = np.trace(utu) / x.shape[1]
+    x_split = None
+    for _ in range(n_iter_max):
+        x_old = x.copy()
+        x_split = np.linalg.solve((utu + rho * np.eye(utu.shape[1])).T, (utm + rho * (x + dual)).T)
+        x = _prox(x_split.T - dual, constraint, param)
+        dual = dual + x - x_split.T
+        dual_residual = x - x_split.T
+        primal_residual = x - x_old
+        if np.linalg.norm(dual_residual) < tol * np.linalg.norm(x) and np.linalg.norm(primal_residual) < tol * np.linalg.norm(dual):
+            break
+    return x, x_split, dual
+
+
+def constrained_parafac(tensor, rank, n_iter_max=100, n_iter_max_inner=10, init="svd", tol_outer=1e-8, tol_inner=1e-6,
+                        random_state=None, cvg_criterion="abs_rec_error", non_negative=None, l1_reg=None, l2_square_reg=None):
+    """tensorly 0.8.x ``constrained_parafac`` (AO-ADMM) for the constraints the product supports -- PARITY UNPINNED like the
+    rest of this file, and restated from memory of the published source: ``initialize_constrained_parafac`` (random: seeded
+    ``random_cp``; svd: left singular vectors, mode 0 scaled by the singular values; then the proximal operator of every
+    mode), per outer iteration and mode ``admm(mttkrp, hadamard of the other Grams, ...)``, the Gram-form error from the last
+    mode's MTTKRP, stop on the constraint error or on the error decrease.  Returns ``(CPResult, errors)``."""
+    x = np.asarray(tensor, dtype=np.float64)
+    n = x.ndim
+    cons = [_constraint_of(m, n, non_negative, l1_reg, l2_square_reg) for m in range(n)]
+    if isinstance(init, str):
+        if init == "random":
+            factors = random_init(x.shape, rank, random_state)
+        else:
+            rng = _rng(random_state)
+            factors = []
+            for mode in range(n):
+                u, s, vt = np.linalg.svd(unfold(x, mode), full_matrices=False)
+                u, _ = _svd_flip(u, vt)
+                u = u[:, :rank].copy()
+                if mode == 0:
+                    k = min(rank, s.shape[0])
+                    u[:, :k] = u[:, :k] * s[:k]
+                if x.shape[mode] < rank:
+                    u = np.concatenate([u, rng.random_sample((u.shape[0], rank - x.shape[mode]))], axis=1)
+                factors.append(u[:, :rank])
+    else:
+        factors = [np.array(f, dtype=np.float64) for f in init[1]]
+    factors = [_prox(np.asarray(f, dtype=np.float64), *cons[m]) for m, f in enumerate(factors)]
+    norm_x = np.sqrt(np.sum(x ** 2))
+    duals = [np.zeros_like(f) for f in factors]
+    aux = [np.zeros_like(f).T for f in factors]
+    errors = []
+    m = None
+    for it in range(n_iter_max):
+        for mode in range(n):
+            g = np.ones((rank, rank))
+            for k in range(n):
+                if k != mode:
+                    g = g * (factors[k].T @ factors[k])
+            m = mttkrp(x, None, factors, mode)
+            factors[mode], aux[mode], duals[mode] = admm(m, g, factors[mode], duals[mode], n_iter_max_inner, cons[mode][0],
+                                                         cons[mode][1], tol_inner)
+        iprod = np.sum(m * factors[-1])
+        err = np.sqrt(np.abs(norm_x ** 2 + cp_norm(None, factors) ** 2 - 2 * iprod)) / norm_x
+        errors.append(err)
+        c_err = sum(np.linalg.norm(factors[k] - aux[k].T) / np.linalg.norm(factors[k]) for k in range(n))
+        if tol_outer and it >= 1:
+            dec = errors[-2] - errors[-1]
+            if c_err < tol_outer:
+                break
+            if (abs(dec) < tol_outer) if cvg_criterion == "abs_rec_error" else (dec < tol_outer):
+                break
+    return CPResult(np.ones(rank), factors), errors

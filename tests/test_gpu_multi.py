@@ -54,8 +54,15 @@ def _worker(rank, world, port, q):
     t = PreBuiltTensor(x, order_names=[list(range(s)) for s in shape])
     t.elbow_rank_selection(upper_rank=4, runs=3, init="random", random_state=5, n_iter_max=15, tol=-1.0, output_fig=False,
                            automatic_elbow=False, manual_elbow=2)
+    # every rank builds ITS context slab of the interaction tensor and the slabs feed one sharded factorization
+    from cell2cell_b200.sharded import build_sharded_interaction_tensor, compute_sharded_tensor_factorization
+    from cell2cell_b200.synthetic import synthetic_case
+    mats, ppi, kw = synthetic_case("balf", scale=0.05)
+    st = build_sharded_interaction_tensor(mats, ppi, **kw)
+    compute_sharded_tensor_factorization(st, 4, random_state=888, n_iter_max=30, tol=-1.0)
+    slab = (st.context_slab, tuple(st.tensor.shape), [df.values for df in st.factors.values()])
     q.put((rank, [np.asarray(f) for f in cp.factors], errs, np.asarray(t.elbow_metric_raw),
-           [np.asarray(f) for f in cp_n.factors], errs_n, [np.asarray(f) for f in cp20.factors], errs20))
+           [np.asarray(f) for f in cp_n.factors], errs_n, [np.asarray(f) for f in cp20.factors], errs20, slab))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,8 +91,17 @@ def _run_world(world):
     t = PreBuiltTensor(x, order_names=[list(range(s)) for s in shape])
     t.elbow_rank_selection(upper_rank=4, runs=3, init="random", random_state=5, n_iter_max=15, tol=-1.0, output_fig=False,
                            automatic_elbow=False, manual_elbow=2)
+    from cell2cell_b200.sharded import shard_bounds
+    from cell2cell_b200.synthetic import synthetic_case
+    from cell2cell_b200.tensor import InteractionTensor
+    mats, ppi, kw = synthetic_case("balf", scale=0.05)
+    whole = InteractionTensor(mats, ppi, **kw)
+    whole.compute_tensor_factorization(rank=4, init="random", random_state=888, n_iter_max=30, tol=-1.0)
     res.sort(key=lambda r: r[0])
-    for rank, factors, errs, raw, factors_n, errs_n, factors20, errs20 in res:
+    for rank, factors, errs, raw, factors_n, errs_n, factors20, errs20, slab in res:
+        assert slab[0] == shard_bounds(len(mats), world, rank) and slab[1][0] == slab[0][1] - slab[0][0]
+        for a, b in zip(slab[2], [df.values for df in whole.factors.values()]):
+            assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4
         for got, got_err in ((factors, errs), (factors_n, errs_n)):
             for a, b in zip(got, ref.factors):
                 assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4

@@ -693,7 +693,7 @@ def test_parafac_through_the_api_and_rejected_options():
     with pytest.raises(NotImplementedError):
         parafac(x, 3, orthogonalise=True)
     with pytest.raises(NotImplementedError):
-        _compute_tensor_factorization(x, 3, tf_type="constrained_parafac")
+        _compute_tensor_factorization(x, 3, tf_type="constrained_parafac", unimodality=True)
     with pytest.raises(ValueError):
         _compute_tensor_factorization(x, 3, tf_type="tucker")
 
@@ -723,3 +723,65 @@ def test_masked_run_dense_plus_correction_equals_fused_imputation(shape, rank, m
         assert rel_err(a, b) < 2e-5, rel_err(a, b)
         assert rel_err(c, b) < 2e-5, rel_err(c, b)
     np.testing.assert_allclose(np.asarray(got_err), np.asarray(old_err), rtol=1e-4, atol=3e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tf_type='constrained_parafac' (tensorly's AO-ADMM; factorization.py:128-136): passes + the single-CTA ADMM kernel
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,rank", [((4, 30, 6, 6), 3), ((5, 11, 17, 17), 5), ((10, 6, 8), 2), ((40, 500, 16, 8), 16)])
+@pytest.mark.parametrize("cons", [dict(non_negative=True), dict(l1_reg=0.05), dict(l2_square_reg={0: 0.1}), dict(),
+                                  dict(non_negative={0: True, 1: True}, l1_reg={2: 0.02})])
+def test_constrained_parafac_matches_oracle(shape, rank, cons):
+    from cell2cell_b200.tensor.factorization import constrained_parafac
+    x = lowrank(shape, max(2, rank - 1), seed=31, noise=0.05)
+    if "l1_reg" in cons and len(shape) == 3:
+        cons = {k: ({m: v for m, v in val.items() if m < 3} if isinstance(val, dict) else val) for k, val in cons.items()}
+    n_iter = 12
+    ref, ref_err = o.constrained_parafac(x.astype(np.float64), rank, n_iter_max=n_iter, init="random", random_state=5,
+                                         tol_outer=0, **cons)
+    got, got_err = constrained_parafac(x, rank, n_iter_max=n_iter, init="random", random_state=5, tol_outer=0,
+                                       return_errors=True, **cons)
+    assert len(got_err) == len(ref_err) == n_iter
+    np.testing.assert_allclose(np.asarray(got_err), np.asarray(ref_err), rtol=1e-3, atol=3e-6)
+    rec = o.cp_to_tensor(None, [np.asarray(f, dtype=np.float64) for f in got.factors])
+    rec_ref = o.cp_to_tensor(None, ref.factors)
+    assert rel_err(rec, rec_ref) < 1e-3
+    if cons.get("non_negative") is True:
+        assert all((np.asarray(f) >= 0).all() for f in got.factors)
+
+
+def test_constrained_parafac_admm_kernel_alone():
+    """One call of c2c_admm_update against the numpy restatement of tensorly's admm (rank not a multiple of 4, every prox)."""
+    from cell2cell_b200 import engine
+    rs = np.random.RandomState(3)
+    I, R = 700, 7
+    dev = torch.device("cuda")
+    for name, param in ((None, 0.0), ("non_negative", 0.0), ("l1_reg", 0.3), ("l2_square_reg", 0.25)):
+        B = rs.rand(50, R)
+        G = (B.T @ B).astype(np.float32)
+        M = rs.randn(I, R).astype(np.float32) * 3
+        x0, d0 = rs.randn(I, R), 0.1 * rs.randn(I, R)
+        want_x, want_split, want_dual = o.admm(M.astype(np.float64), G.astype(np.float64), x0.copy(), d0.copy(), 10, name, param, 1e-6)
+        A = engine.pack_factor(x0.astype(np.float32), R, dev)
+        X64, dual = torch.as_tensor(x0.copy()).to(dev), torch.as_tensor(d0.copy()).to(dev)
+        aux = torch.zeros_like(X64)
+        Gp = torch.zeros((engine.ldr_of(R), engine.ldr_of(R)), dtype=torch.float32, device=dev)
+        Gp[:R, :R] = torch.as_tensor(G).to(dev)
+        out = engine.admm_update(A, X64, dual, aux, engine.pack_factor(M, R, dev), Gp, R, constraint=name, param=param,
+                                 n_inner=10, tol=1e-6)
+        np.testing.assert_allclose(X64.cpu().numpy(), want_x, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(aux.cpu().numpy(), want_split.T, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(dual.cpu().numpy(), want_dual, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(A[:, :R].cpu().numpy(), want_x.astype(np.float32), rtol=1e-6, atol=1e-7)
+        want_c = np.linalg.norm(want_x - want_split.T) / np.linalg.norm(want_x)
+        assert abs(float(out[0]) - want_c) <= 1e-8 * max(want_c, 1e-30) + 1e-14 and 1 <= int(out[1]) <= 10
+
+
+def test_constrained_parafac_through_the_api():
+    from cell2cell_b200.tensor import PreBuiltTensor
+    shape = (6, 40, 8, 8)
+    x = lowrank(shape, 3, seed=2, noise=0.02)
+    t = PreBuiltTensor(x, order_names=[["e%d_%d" % (m, i) for i in range(s)] for m, s in enumerate(shape)])
+    t.compute_tensor_factorization(rank=3, tf_type="constrained_parafac", init="svd", n_iter_max=60, non_negative=True)
+    assert t.rank == 3 and t.explained_variance_ > 0.95
+    assert all((df.values >= 0).all() for df in t.factors.values())

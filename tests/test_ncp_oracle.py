@@ -131,3 +131,21 @@ def test_masked_mttkrp_is_dense_pass_plus_missing_entry_correction():
     np.testing.assert_allclose(np.einsum("abr,ar->br", T4, fs[0]), want[1], rtol=1e-12)
     np.testing.assert_allclose(np.einsum("svr,vr->sr", U4, fs[3]), want[2], rtol=1e-12)
     np.testing.assert_allclose(np.einsum("svr,sr->vr", U4, fs[2]), want[3], rtol=1e-12)
+
+
+def test_constrained_parafac_oracle_self_consistency():
+    """AO-ADMM restatement: non-negative factors under `non_negative`, a decreasing error tail, and with no constraint the
+    first ADMM step is the regularised least-squares step (rho-damped), converging to the ALS fixed point on an exact tensor."""
+    rs = np.random.RandomState(0)
+    fs = [rs.gamma(1.0, 1.0, size=(s, 3)) for s in (5, 12, 4, 4)]
+    x = o.cp_to_tensor(None, fs)
+    cp, errs = o.constrained_parafac(x, 3, n_iter_max=60, init="random", random_state=1, non_negative=True, tol_outer=0)
+    assert all((f >= 0).all() for f in cp.factors)
+    assert errs[-1] < 0.05 and errs[-1] <= errs[5]
+    direct = np.linalg.norm(x - o.cp_to_tensor(None, cp.factors)) / np.linalg.norm(x)
+    assert abs(direct - errs[-1]) < 1e-8
+    # soft thresholding shrinks: a large l1 penalty on mode 0 zeroes entries of that factor only
+    cp1, _ = o.constrained_parafac(x, 3, n_iter_max=10, init="random", random_state=1, l1_reg={0: 0.5}, tol_outer=0)
+    assert (cp1.factors[0] == 0).any() and not (cp1.factors[1] == 0).any()
+    with pytest.raises(ValueError):
+        o.constrained_parafac(x, 3, n_iter_max=1, init="random", non_negative=True, l1_reg=0.1)

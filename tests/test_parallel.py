@@ -5,7 +5,7 @@ import socket
 import numpy as np
 import torch.multiprocessing as mp
 
-from cell2cell_b200.parallel import lpt_schedule, run_units
+from cell2cell_b200.parallel import local_only, lpt_schedule, run_units, world
 
 
 def test_lpt_schedule_balances_and_is_deterministic():
@@ -39,7 +39,14 @@ def _worker(rank, size, port, out):
 
     vals = run_units(units, fn, cost=lambda u: u[0], gather="float")
     objs = run_units(units, lambda u: {"unit": u}, cost=lambda u: u[0], gather="object")
-    out.put((rank, vals, len(calls), [o["unit"] for o in objs]))
+    # work only ONE rank does must stay out of the collectives (bench.py's rank-0 reports): a world of one inside the guard
+    solo = None
+    if rank == 0:
+        with local_only():
+            assert world() == (0, 1)
+            solo = run_units([1, 2, 3], lambda u: u * 2.0, gather="object")
+    assert world() == (rank, size)
+    out.put((rank, vals, len(calls), [o["unit"] for o in objs], solo))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,7 +65,8 @@ def test_run_units_two_ranks_gloo():
     units = [(r, run) for r in range(1, 7) for run in range(3)]
     expect = [u[0] * 10.0 + u[1] for u in units]
     n_calls = 0
-    for rank, vals, calls, objs in res:
+    for rank, vals, calls, objs, solo in res:
+        assert solo == ([2.0, 4.0, 6.0] if rank == 0 else None)
         assert np.allclose(vals, expect)
         assert [tuple(o) for o in objs] == units
         n_calls += calls
