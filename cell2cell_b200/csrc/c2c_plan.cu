@@ -112,9 +112,15 @@ plan_count_rows_kernel(const uint8_t* __restrict__ mask, const PlanView v)
                 n += plan_resid_sv(v, mp, c, s, e - s * v.I3) ? 1 : 0;
             }
         }
+        // The list of a plane is stored by CLASS c = position mod 8, slot i of the list holding an entry of class i mod 8
+        // (0xFFFF where a class has run out): the eight lanes of a quarter-warp then gather B rows 48 B apart modulo 8 rows,
+        // i.e. from eight different 16-byte bank groups -- every LDS.128 of plane_corr_list is conflict-free.  Lane l scans
+        // the positions l, l + 32, ...: all of class l mod 8.  Length = 8 x the longest class.
+        n += __shfl_xor_sync(0xffffffffu, n, 8);
+        n += __shfl_xor_sync(0xffffffffu, n, 16);                      // every lane: the count of its class
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-        if (lane == 0) v.row_off[p + 1] = n;
+        for (int o = 4; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+        if (lane == 0) v.row_off[p + 1] = 8 * n;
     }
 }
 
@@ -211,18 +217,23 @@ plan_fill_csr_kernel(const uint8_t* __restrict__ mask, const PlanView v)
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long p = warp; p < v.P; p += nwarps) {
-        int off = v.row_off[p];
-        if (v.row_off[p + 1] == off) continue;
+        const int off = v.row_off[p];
+        const int len = v.row_off[p + 1] - off;
+        if (len == 0) continue;
         const int c = (int)(p / v.ppc0);
         const uint8_t* mp = mask + (size_t)p * v.E;
+        const int cls = lane & 7;                                      // class of every position this lane scans
+        const unsigned cmask = 0x01010101u << cls;                     // the four lanes of the class
+        int cnt = 0;                                                   // entries of the class placed so far
         for (int e0 = 0; e0 < v.E; e0 += 32) {
             const int e = e0 + lane;
             bool r = false;
             if (e < v.E) { const int s = e / v.I3; r = plan_resid_sv(v, mp, c, s, e - s * v.I3); }
-            const unsigned bal = __ballot_sync(0xffffffffu, r);
-            if (r) v.csr_ent[off + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
-            off += __popc(bal);
+            const unsigned bal = __ballot_sync(0xffffffffu, r) & cmask;
+            if (r) v.csr_ent[off + 8 * (cnt + __popc(bal & ((1u << lane) - 1u))) + cls] = (uint16_t)e;
+            cnt += __popc(bal);
         }
+        for (int k = cnt + (lane >> 3); k < len / 8; k += 4) v.csr_ent[off + 8 * k + cls] = (uint16_t)0xFFFFu;
     }
 }
 
@@ -604,6 +615,35 @@ __device__ __forceinline__ float lead_weight32(unsigned p, const LeadInfo& lead,
     return w;
 }
 
+constexpr __host__ __device__ int plan_b_pitch(int nq) { return ((nq / 4) & 1) ? nq : nq + 4; }
+constexpr __host__ __device__ int plan_pow2(int n) { return n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+
+// Every lane holds NP (a power of two <= 32) values; returns the sum over the 32 lanes of value `col`, where `col` is fixed by
+// the lane number: at the step of width o the lanes with that bit set keep the upper half of what they hold and send the lower
+// half (and vice versa), so the count halves per step; the widths that are left over when one value remains are plain
+// butterflies.  Lanes that differ only in those leftover low bits end with the same column.
+template <int NP>
+__device__ __forceinline__ float plan_halving_sum(float (&a)[NP], int lane, int& col)
+{
+    col = 0;
+    int o = 16;
+#pragma unroll
+    for (int n = NP; n > 1; n >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float send = up ? a[j] : a[j + n / 2];
+            const float keep = up ? a[j + n / 2] : a[j];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        if (up) col += n / 2;
+        o >>= 1;
+    }
+    float v = a[0];
+    for (; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 #define C2C_PLAN_PRELOAD 8
 // a warp per plane with residual entries: lanes stride the plane's list, B rows from shared memory (SMEM_B) or L1
 template <int NQ, bool SMEM_B>
@@ -615,10 +655,16 @@ plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __res
     pdl_wait();
     if (run_done(done)) return;
     extern __shared__ __align__(16) float pcl_smem[];
+    // shared-memory pitch of a B row: an ODD number of 16-byte quads, so that rows that differ modulo 8 (the class order of
+    // the list) start in different bank groups
+    constexpr int PB = SMEM_B ? plan_b_pitch(NQ) : NQ;
     if (SMEM_B) {
         const float4* src = reinterpret_cast<const float4*>(Bmat);
         float4* dst = reinterpret_cast<float4*>(pcl_smem);
-        for (int i = threadIdx.x; i < v.E * (NQ / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < v.E * (NQ / 4); i += blockDim.x) {
+            const int e = i / (NQ / 4), k = i - e * (NQ / 4);
+            dst[e * (PB / 4) + k] = src[i];
+        }
         __syncthreads();
     }
     const float* Bsrc = SMEM_B ? pcl_smem : Bmat;
@@ -633,48 +679,54 @@ plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __res
             continue;
         }
         const float wl = lane < R ? lead_weight32((unsigned)p, lead, NQ, lane) : 0.0f;
-        float w[NQ], acc[NQ];
+        float2 w[NQ / 2], acc[NQ / 2];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) { w[q] = __shfl_sync(0xffffffffu, wl, q); acc[q] = 0.0f; }
+        for (int q = 0; q < NQ / 2; ++q) {
+            w[q] = make_float2(__shfl_sync(0xffffffffu, wl, 2 * q), __shfl_sync(0xffffffffu, wl, 2 * q + 1));
+            acc[q] = make_float2(0.0f, 0.0f);
+        }
         for (int i0 = 0; i0 < n; i0 += 32 * C2C_PLAN_PRELOAD) {
             int ev[C2C_PLAN_PRELOAD];                                   // the list reads of a batch are in flight together
 #pragma unroll
             for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
                 const int i = i0 + u * 32 + lane;
-                ev[u] = i < n ? (int)v.csr_ent[(size_t)b0 + i] : -1;
+                ev[u] = i < n ? (int)v.csr_ent[(size_t)b0 + i] : 0xFFFF;
             }
 #pragma unroll
             for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
-                if (ev[u] < 0) continue;
-                const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)ev[u] * NQ);
-                float b[NQ];
+                if (ev[u] == 0xFFFF) continue;                          // padding of a class that has run out
+                const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)ev[u] * PB);
+                float2 b[NQ / 2];
 #pragma unroll
                 for (int k = 0; k < NQ / 4; ++k) {
                     const float4 x = b4[k];
-                    b[4 * k] = x.x; b[4 * k + 1] = x.y; b[4 * k + 2] = x.z; b[4 * k + 3] = x.w;
+                    b[2 * k] = make_float2(x.x, x.y); b[2 * k + 1] = make_float2(x.z, x.w);
                 }
-                float r0 = 0.0f, r1 = 0.0f;
+                float2 r2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
-                const float rec = r0 + r1;
+                for (int q = 0; q < NQ / 2; ++q) r2 = ffma2(w[q], b[q], r2);
+                const float rec = r2.x + r2.y;
+                const float2 rr = make_float2(rec, rec);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, b[q], acc[q]);
+                for (int q = 0; q < NQ / 2; ++q) acc[q] = ffma2(rr, b[q], acc[q]);
             }
         }
-        float mine = 0.0f;
+        // column sums over the lanes by recursive halving (about NQ shuffles instead of 5 NQ, fixed tree)
+        float vals[plan_pow2(NQ)];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            const float s = warp_sum(acc[q]);
-            if (lane == q) mine = s;
-        }
-        if (lane < NQ) Tout[(size_t)p * NQ + lane] = Tin[(size_t)p * NQ + lane] + mine;
+        for (int q = 0; q < plan_pow2(NQ); ++q) vals[q] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NQ / 2; ++q) { vals[2 * q] = acc[q].x; vals[2 * q + 1] = acc[q].y; }
+        int col;
+        const float mine = plan_halving_sum<plan_pow2(NQ)>(vals, lane, col);
+        if (col < NQ && (lane & ((32 / plan_pow2(NQ)) - 1)) == 0) Tout[(size_t)p * NQ + col] = Tin[(size_t)p * NQ + col] + mine;
     }
 }
 
 cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, const float* Bmat, const float* Tin, float* Tout,
                                        int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
 {
-    const size_t bbytes = (size_t)v.E * ldr * sizeof(float);
+    const size_t bbytes = (size_t)v.E * plan_b_pitch(ldr) * sizeof(float);
     const bool smem_b = bbytes <= 100 * 1024;
     const int block = ldr <= 16 ? 512 : 256;                           // <= 64 registers per thread at ldr <= 16: 32 warps per SM
     long long grid = (v.P * 32 + block - 1) / block;
@@ -795,7 +847,7 @@ cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const LeadInfo& lead, 
                                        cudaStream_t st, int pdl)
 {
     const int ni = (v.ngroups + 7) / 8;
-    int nj = (3 * nsm + ni - 1) / ni;                                  // ~3 CTAs per SM in all
+    int nj = (4 * nsm + ni - 1) / ni;                                  // ~4 CTAs per SM in all (64 registers x 256 threads)
     if (nj > max_parts) nj = max_parts;
     if (nj > v.nchunks) nj = v.nchunks;
     if (nj < 1) nj = 1;

@@ -23,7 +23,8 @@ def test_pairwise_corrindex_matches_the_oracle(sizes, R, n, method):
     sets = _sets(rs, sizes, R, n)
     # a permuted + rescaled copy of the first decomposition: CorrIndex 0 against it
     perm = rs.permutation(R)
-    sets[-1] = [f[:, perm] * (0.5 + rs.rand(R)) for f in sets[0]]
+    scale = 0.5 + rs.rand(R)                 # ONE scaling per column for every mode: the stacked matrix stays proportional
+    sets[-1] = [f[:, perm] * scale for f in sets[0]]
     got = pairwise_correlation_index(sets, method=method)
     want = mo.pairwise_correlation_index(sets, method=method)
     assert got.shape == (n, n) and list(got.index) == list(range(n))
