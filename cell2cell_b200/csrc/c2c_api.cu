@@ -1838,7 +1838,7 @@ extern "C" int c2c_mask_plan_scan(const float* X, const uint8_t* mask, int ndim,
     CK(cudaStreamSynchronize(st), "mask plan scan");
     for (int i = 0; i < 6; ++i) info[i] = (int64_t)cnt[i];
     info[6] = (int64_t)c2c_plan_lists_bytes((long long)cnt[1], (long long)cnt[3]);
-    info[7] = C2C_VERSION;
+    info[7] = (int64_t)cnt[6];                                         // residual entries (info[1] = list slots incl. padding)
     return 0;
 }
 

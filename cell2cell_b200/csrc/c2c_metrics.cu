@@ -51,18 +51,21 @@ corrindex_pairs_kernel(const double* __restrict__ F, int n, long long S, int R, 
                 t2[t] = X2[(size_t)r0 * R + t];
             }
             __syncthreads();
+            // two-level sums (a tile's 32 rows first, then across tiles): rounding grows with 32 + S / 32, not with S
             if (tid < 2 * R) {
                 const double* tt = tid < R ? t1 + tid : t2 + (tid - R);
-                for (int s = 0; s < rows; ++s) nacc += tt[(size_t)s * R] * tt[(size_t)s * R];
+                double a = 0.0;
+                for (int s = 0; s < rows; ++s) a += tt[(size_t)s * R] * tt[(size_t)s * R];
+                nacc += a;
             }
 #pragma unroll
             for (int u = 0; u < 64; ++u) {
                 const int e = tid + u * CI_THREADS;
                 if (e < nent) {
                     const int q = e / R, r = e - q * R;
-                    double a = acc[u];
+                    double a = 0.0;
                     for (int s = 0; s < rows; ++s) a += t1[(size_t)s * R + q] * t2[(size_t)s * R + r];
-                    acc[u] = a;
+                    acc[u] += a;
                 }
             }
         }

@@ -118,9 +118,16 @@ plan_count_rows_kernel(const uint8_t* __restrict__ mask, const PlanView v)
         // the positions l, l + 32, ...: all of class l mod 8.  Length = 8 x the longest class.
         n += __shfl_xor_sync(0xffffffffu, n, 8);
         n += __shfl_xor_sync(0xffffffffu, n, 16);                      // every lane: the count of its class
+        int tot = n;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
-        if (lane == 0) v.row_off[p + 1] = 8 * n;
+        for (int o = 4; o > 0; o >>= 1) {
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
+        }
+        if (lane == 0) {
+            v.row_off[p + 1] = 8 * n;
+            if (tot) atomicAdd(v.counters + 6, (unsigned long long)tot);   // residual entries, without the padding
+        }
     }
 }
 

@@ -26,14 +26,16 @@
 struct PlanView {
     // header (sized from the shape alone)
     unsigned long long* counters;     // [0] missing entries, [1] residual entries, [2] non-zero value under a zero mask byte,
-                                      // [3] rows (of 32) of the position-major lists, [4] model has missing entries, [5] overflow
+                                      // [3] rows (of 32) of the position-major lists, [4] model has missing entries, [5] overflow,
+                                      // [6] residual entries without the class padding of the by-plane list ([1] counts its slots)
     uint8_t* g;                       // [P]        plane has an observed entry
     int* hs;                          // [C0 x I2]  row s of the planes of context c has an observed entry
     int* hv;                          // [C0 x I3]  column v ...
-    int* row_off;                     // [P + 1]    residual entries by plane
+    int* row_off;                     // [P + 1]    list slots by plane (8 x the longest position class of the plane)
     int* ell_off;                     // [nchunks * ngroups + 1]  rows of 32 by (chunk, position group)
     // lists (sized by the scan)
-    uint16_t* csr_ent;                // [n_resid]  in-plane position, plane by plane, increasing
+    uint16_t* csr_ent;                // [slots]    in-plane position, plane by plane; slot i holds a position of class i mod 8
+                                      //            (increasing within a class), 0xFFFF = padding
     uint16_t* ell_ent;                // [ell_rows][32]  plane index within its chunk, 0xFFFF = padding
     long long P; long long ppc0;      // planes; planes per index of the first mode
     int E, I2, I3, C0, nchunks, ngroups;

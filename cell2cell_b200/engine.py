@@ -321,7 +321,8 @@ class MaskPlan:
                                                _ptr(self.lists), self.lists.numel(), _stream()), "c2c_mask_plan_fill")
 
     n_missing = property(lambda self: int(self.info[0]))
-    n_residual = property(lambda self: int(self.info[1]))
+    n_residual = property(lambda self: int(self.info[7]))        # entries the separable model cannot express
+    n_list_slots = property(lambda self: int(self.info[1]))      # slots of the by-plane list (class padding included)
     model_missing = property(lambda self: bool(self.info[4]))
 
     def args(self):

@@ -782,6 +782,7 @@ def test_constrained_parafac_through_the_api():
     shape = (6, 40, 8, 8)
     x = lowrank(shape, 3, seed=2, noise=0.02)
     t = PreBuiltTensor(x, order_names=[["e%d_%d" % (m, i) for i in range(s)] for m, s in enumerate(shape)])
-    t.compute_tensor_factorization(rank=3, tf_type="constrained_parafac", init="svd", n_iter_max=60, non_negative=True)
-    assert t.rank == 3 and t.explained_variance_ > 0.95
+    t.compute_tensor_factorization(rank=3, tf_type="constrained_parafac", init="random", random_state=0, n_iter_max=60,
+                                   non_negative=True)
+    assert t.rank == 3 and t.explained_variance_ > 0.95     # (the oracle: 0.985 after its 11 outer iterations)
     assert all((df.values >= 0).all() for df in t.factors.values())
