@@ -394,6 +394,7 @@ struct Ws {
     float* Tw; float* Uw; float* cpart;      // masked runs, dense pass + missing-entry correction (c2c_corr.cu, c2c_plan.cu)
     int cparts;                              // partial U buffers reserved in cpart
     float* Dmat; float* Ymat; float* Ypart;  // restricted Grams of the mask plan's separable model (c2c_plan.cu)
+    float* Wmat;                             // Khatri-Rao rows of the leading factors, [P][ldr] (residual lists, c2c_plan.cu)
     double* S; double* gram_part; double* iprod_part; double* normX2; double* sums_part; double* scratch_d;
     int* flags;
     size_t bytes;
@@ -436,6 +437,7 @@ static void carve(Ws& w, const Geo& g, int rank, int masked, char* base)
     w.Dmat = (float*)take(plan_ws ? (size_t)(C0 + 1) * ldr * ldr * sizeof(float) : 0);
     w.Ymat = (float*)take(plan_ws ? (size_t)(C0 + 1) * ldr * ldr * sizeof(float) : 0);
     w.Ypart = (float*)take(plan_ws ? (size_t)C0 * c2c_lead_ctx_parts(C0, sm_count()) * 2 * ldr * ldr * sizeof(float) : 0);
+    w.Wmat = (float*)take(plan_ws ? (size_t)g.P * ldr * sizeof(float) : 0);
     w.S = (double*)take((size_t)2 * g.ndim * ldr * ldr * sizeof(double));        // two banks (c2c_update.cuh)
     const long long nblk_g = nblk > 512 ? nblk : 512;             // lead_update runs at most 2 CTAs per SM, capped at 512
     w.gram_part = (double*)take((size_t)nblk_g * ldr * ldr * sizeof(double));
@@ -1350,9 +1352,10 @@ static int enqueue_iteration_plan(const RunCtx& c)
             src = c.w.Tw;
         }
         if (lists) {
-            e = c2c_launch_plane_corr_list(c.pv, li, c.w.Bmat, src, c.w.Tw, c.R, c.ldr, done, nsm, c.st, c.pdl);
+            e = c2c_launch_wmat(li, g.P, c.ldr, c.w.Wmat, done, c.st);
+            if (e == cudaSuccess) e = c2c_launch_plane_corr_list(c.pv, c.w.Wmat, c.w.Bmat, src, c.w.Tw, c.ldr, done, nsm, c.st, c.pdl);
             if (e != cudaSuccess) return cuda_fail(e, "plane_corr_list launch");
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+            g_launches.fetch_add(2, std::memory_order_relaxed);
         }
         if ((rc = launch_lead_update(c2, mode)) != 0) return rc;
     }
@@ -1366,6 +1369,12 @@ static int enqueue_iteration_plan(const RunCtx& c)
         if (e != cudaSuccess) return cuda_fail(e, "lead_ctx_gram launch");
         g_launches.fetch_add(2, std::memory_order_relaxed);
     }
+    if (lists) {                                                       // the leading factors are final for this iteration
+        LeadInfo li; fill_lead(li, g, A);
+        e = c2c_launch_wmat(li, g.P, c.ldr, c.w.Wmat, done, c.st);
+        if (e != cudaSuccess) return cuda_fail(e, "wmat launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     for (int j = 0; j < 2; ++j) {
         const float* src = c.w.U;
         if (gram) {
@@ -1375,9 +1384,14 @@ static int enqueue_iteration_plan(const RunCtx& c)
             src = c.w.Uw;
         }
         if (lists) {
-            LeadInfo li; fill_lead(li, g, A);
-            e = c2c_launch_fiber_corr_list(c.pv, li, A[g.ndim - 2], A[g.ndim - 1], src, c.w.Uw, c.w.cpart, c.w.cparts, c.R, c.ldr, done,
-                                           nsm, c.st, c.pdl);
+            if (j == 1) {                                              // A_{N-2} has just been updated: B with it
+                const long long nB = g.E * c.ldr;
+                e = c2c_launch_ex(bmat_kernel, dim3((unsigned)((nB + 255) / 256)), dim3(256), 0, c.st, 0, A[g.ndim - 2], A[g.ndim - 1],
+                                  g.I2, g.I3, c.ldr, c.w.Bmat, done);
+                if (e != cudaSuccess) return cuda_fail(e, "bmat launch");
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+            }
+            e = c2c_launch_fiber_corr_list(c.pv, c.w.Wmat, c.w.Bmat, src, c.w.Uw, c.w.cpart, c.w.cparts, c.ldr, done, nsm, c.st, c.pdl);
             if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_list launch");
             g_launches.fetch_add(2, std::memory_order_relaxed);
         }
@@ -1916,9 +1930,10 @@ extern "C" int c2c_masked_contract_planned(const float* X, int ndim, const int64
             const long long nB = g.E * ldr;
             bmat_kernel<<<(int)((nB + 255) / 256), 256, 0, st>>>(A[ndim - 2], A[ndim - 1], g.I2, g.I3, ldr, w.Bmat, nullptr);
             CKL("bmat launch");
-            e = c2c_launch_plane_corr_list(v, li, w.Bmat, src, w.Tw, rank, ldr, nullptr, nsm, st, 0);
+            e = c2c_launch_wmat(li, g.P, ldr, w.Wmat, nullptr, st);
+            if (e == cudaSuccess) e = c2c_launch_plane_corr_list(v, w.Wmat, w.Bmat, src, w.Tw, ldr, nullptr, nsm, st, 0);
             if (e != cudaSuccess) return cuda_fail(e, "plane_corr_list launch");
-            g_launches.fetch_add(1, std::memory_order_relaxed);
+            g_launches.fetch_add(2, std::memory_order_relaxed);
             src = w.Tw;
         }
         CK(cudaMemcpyAsync(out, src, (size_t)g.P * ldr * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy T");
@@ -1933,9 +1948,13 @@ extern "C" int c2c_masked_contract_planned(const float* X, int ndim, const int64
             src = w.Uw;
         }
         if (lst) {
-            e = c2c_launch_fiber_corr_list(v, li, A[ndim - 2], A[ndim - 1], src, w.Uw, w.cpart, w.cparts, rank, ldr, nullptr, nsm, st, 0);
+            const long long nB = g.E * ldr;
+            bmat_kernel<<<(int)((nB + 255) / 256), 256, 0, st>>>(A[ndim - 2], A[ndim - 1], g.I2, g.I3, ldr, w.Bmat, nullptr);
+            CKL("bmat launch");
+            e = c2c_launch_wmat(li, g.P, ldr, w.Wmat, nullptr, st);
+            if (e == cudaSuccess) e = c2c_launch_fiber_corr_list(v, w.Wmat, w.Bmat, src, w.Uw, w.cpart, w.cparts, ldr, nullptr, nsm, st, 0);
             if (e != cudaSuccess) return cuda_fail(e, "fiber_corr_list launch");
-            g_launches.fetch_add(2, std::memory_order_relaxed);
+            g_launches.fetch_add(4, std::memory_order_relaxed);
             src = w.Uw;
         }
         CK(cudaMemcpyAsync(out, src, (size_t)g.E * ldr * sizeof(float), cudaMemcpyDeviceToDevice, st), "copy U");

@@ -1,7 +1,7 @@
 // Mask plan of the masked factorization: see c2c_plan.cuh for the model.  Three groups of kernels:
 //   plan_*            built once per (tensor, mask): separable model g / hs / hv, residual counts, offsets, the two lists
 //   *_ctx_gram, *_corr_gram   the contraction of the reconstruction over the model-missing set, as restricted Grams
-//   *_corr_list       the same contraction over the residual list (entries the separable model cannot express)
+//   wmat, corr_rows   the same contraction over the residual lists (entries the separable model cannot express)
 // All of them are exact restatements of tensorly's imputation `tensor*mask + cp_to_tensor(cp, mask=1-mask)` followed by
 // unfolding_dot_khatri_rao (cell2cell/tensor/coupled_factorization.py:342-345): the same products, summed in another order.
 #include "c2c_plan.cuh"
@@ -10,22 +10,22 @@ static inline size_t plan_align(size_t x) { return (x + 255) / 256 * 256; }
 
 size_t c2c_plan_header_bytes(long long P, int E, int I2, int I3, int C0)
 {
-    const long long nchunks = (P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK, ngroups = (E + 31) / 32;
+    const long long nchunks = (P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK;
     return plan_align(C2C_PLAN_NCOUNTERS * sizeof(unsigned long long)) + plan_align((size_t)P) +
            plan_align((size_t)C0 * I2 * sizeof(int)) + plan_align((size_t)C0 * I3 * sizeof(int)) +
-           plan_align((size_t)(P + 1) * sizeof(int)) + plan_align((size_t)(nchunks * ngroups + 1) * sizeof(int));
+           plan_align((size_t)(P + 1) * sizeof(int)) + plan_align((size_t)(nchunks * E + 1) * sizeof(int));
 }
 
-size_t c2c_plan_lists_bytes(long long n_resid, long long ell_rows)
+size_t c2c_plan_lists_bytes(long long n_resid, long long pos_slots)
 {
     return plan_align((size_t)(n_resid > 0 ? n_resid : 1) * sizeof(uint16_t)) +
-           plan_align((size_t)(ell_rows > 0 ? ell_rows : 1) * 32 * sizeof(uint16_t));
+           plan_align((size_t)(pos_slots > 0 ? pos_slots : 1) * sizeof(uint16_t));
 }
 
 void c2c_plan_view(PlanView& v, long long P, int E, int I2, int I3, int C0, void* header, void* lists, long long n_resid)
 {
     v.P = P; v.E = E; v.I2 = I2; v.I3 = I3; v.C0 = C0; v.ppc0 = P / C0;
-    v.nchunks = (int)((P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK); v.ngroups = (E + 31) / 32;
+    v.nchunks = (int)((P + C2C_PLAN_CHUNK - 1) / C2C_PLAN_CHUNK);
     char* h = (char*)header;
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = h ? h + off : nullptr; off += plan_align(bytes); return p; };
@@ -34,10 +34,10 @@ void c2c_plan_view(PlanView& v, long long P, int E, int I2, int I3, int C0, void
     v.hs = (int*)take((size_t)C0 * I2 * sizeof(int));
     v.hv = (int*)take((size_t)C0 * I3 * sizeof(int));
     v.row_off = (int*)take((size_t)(P + 1) * sizeof(int));
-    v.ell_off = (int*)take((size_t)((long long)v.nchunks * v.ngroups + 1) * sizeof(int));
+    v.pos_off = (int*)take((size_t)((long long)v.nchunks * E + 1) * sizeof(int));
     char* l = (char*)lists;
     v.csr_ent = (uint16_t*)l;
-    v.ell_ent = l ? (uint16_t*)(l + plan_align((size_t)(n_resid > 0 ? n_resid : 1) * sizeof(uint16_t))) : nullptr;
+    v.pos_ent = l ? (uint16_t*)(l + plan_align((size_t)(n_resid > 0 ? n_resid : 1) * sizeof(uint16_t))) : nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -131,28 +131,38 @@ plan_count_rows_kernel(const uint8_t* __restrict__ mask, const PlanView v)
     }
 }
 
-// a warp per (chunk of 256 planes, group of 32 positions): depth of its ELL block = the longest list among the 32 positions
+// a warp per (chunk of planes, group of 32 positions), lane = position: the list of (chunk, position) holds the chunk's planes
+// that are residual at the position, stored by CLASS = plane number mod 8 exactly as the by-plane lists are (so that the
+// gathers of W rows from shared memory are conflict-free too); slots = 8 x the longest class -> pos_off[k E + e + 1]
 __global__ void __launch_bounds__(256)
-plan_count_ell_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+plan_count_pos_kernel(const uint8_t* __restrict__ mask, const PlanView v)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long nblocks = (long long)v.nchunks * v.ngroups;
+    const int ngroups = (v.E + 31) / 32;
+    const long long nblocks = (long long)v.nchunks * ngroups;
     for (long long b = warp; b < nblocks; b += nwarps) {
-        const int k = (int)(b / v.ngroups), gq = (int)(b - (long long)k * v.ngroups);
+        const int k = (int)(b / ngroups), gq = (int)(b - (long long)k * ngroups);
         const int e = gq * 32 + lane;
-        int n = 0;
-        if (e < v.E) {
-            const int s = e / v.I3, vv = e - s * v.I3;
-            const long long p0 = (long long)k * C2C_PLAN_CHUNK;
-            const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
-            for (long long p = p0; p < p1; ++p)
-                if (v.g[p]) n += plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv) ? 1 : 0;
-        }
+        if (e >= v.E) continue;
+        const int s = e / v.I3, vv = e - s * v.I3;
+        const long long p0 = (long long)k * C2C_PLAN_CHUNK;                    // a multiple of 8: class of plane p0 + j is j mod 8
+        const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
+        int cnt[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, o));
-        if (lane == 0) v.ell_off[b + 1] = n;
+        for (int j = 0; j < 8; ++j) cnt[j] = 0;
+        for (long long pb = p0; pb < p1; pb += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long p = pb + j;
+                if (p < p1 && v.g[p]) cnt[j] += plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv) ? 1 : 0;
+            }
+        }
+        int m = cnt[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) m = max(m, cnt[j]);
+        v.pos_off[(size_t)k * v.E + e + 1] = 8 * m;
     }
 }
 
@@ -185,7 +195,7 @@ plan_scan_kernel(const PlanView v)
 {
     __shared__ unsigned long long sh[1024];
     const unsigned long long n_resid = plan_block_scan(v.row_off, v.P, sh);
-    const unsigned long long ell_rows = plan_block_scan(v.ell_off, (long long)v.nchunks * v.ngroups, sh);
+    const unsigned long long pos_slots = plan_block_scan(v.pos_off, (long long)v.nchunks * v.E, sh);
     int missing = 0;
     for (long long i = threadIdx.x; i < v.P; i += 1024) missing |= v.g[i] == 0;
     for (int i = threadIdx.x; i < v.C0 * v.I2; i += 1024) missing |= v.hs[i] == 0;
@@ -193,9 +203,9 @@ plan_scan_kernel(const PlanView v)
     missing = __syncthreads_or(missing);
     if (threadIdx.x == 0) {
         v.counters[1] = n_resid;
-        v.counters[3] = ell_rows;
+        v.counters[3] = pos_slots;
         v.counters[4] = missing ? 1ull : 0ull;
-        v.counters[5] = (n_resid >= (1ull << 31) || ell_rows >= (1ull << 26)) ? 1ull : 0ull;
+        v.counters[5] = (n_resid >= (1ull << 31) || pos_slots >= (1ull << 31)) ? 1ull : 0ull;
     }
 }
 
@@ -207,9 +217,9 @@ cudaError_t c2c_plan_scan(const float* X, const uint8_t* mask, const PlanView& v
     if (grid > (long long)nsm * 16) grid = (long long)nsm * 16;
     plan_fit_kernel<<<(unsigned)grid, 256, 0, st>>>(X, mask, v);
     plan_count_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, v);
-    long long g2 = ((long long)v.nchunks * v.ngroups + 7) / 8;
+    long long g2 = ((long long)v.nchunks * ((v.E + 31) / 32) + 7) / 8;
     if (g2 > (long long)nsm * 16) g2 = (long long)nsm * 16;
-    plan_count_ell_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
+    plan_count_pos_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
     plan_scan_kernel<<<1, 1024, 0, st>>>(v);
     return cudaGetLastError();
 }
@@ -245,29 +255,39 @@ plan_fill_csr_kernel(const uint8_t* __restrict__ mask, const PlanView v)
 }
 
 __global__ void __launch_bounds__(256)
-plan_fill_ell_kernel(const uint8_t* __restrict__ mask, const PlanView v)
+plan_fill_pos_kernel(const uint8_t* __restrict__ mask, const PlanView v)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long nblocks = (long long)v.nchunks * v.ngroups;
+    const int ngroups = (v.E + 31) / 32;
+    const long long nblocks = (long long)v.nchunks * ngroups;
     for (long long b = warp; b < nblocks; b += nwarps) {
-        const int base = v.ell_off[b], depth = v.ell_off[b + 1] - base;
-        if (depth == 0) continue;
-        const int k = (int)(b / v.ngroups), gq = (int)(b - (long long)k * v.ngroups);
+        const int k = (int)(b / ngroups), gq = (int)(b - (long long)k * ngroups);
         const int e = gq * 32 + lane;
-        int n = 0;
-        if (e < v.E) {
-            const int s = e / v.I3, vv = e - s * v.I3;
-            const long long p0 = (long long)k * C2C_PLAN_CHUNK;
-            const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
-            for (long long p = p0; p < p1; ++p)
-                if (v.g[p] && plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv)) {
-                    v.ell_ent[((size_t)base + n) * 32 + lane] = (uint16_t)(p - p0);
-                    ++n;
+        if (e >= v.E) continue;
+        const int off = v.pos_off[(size_t)k * v.E + e];
+        const int len8 = (v.pos_off[(size_t)k * v.E + e + 1] - off) / 8;
+        if (len8 == 0) continue;
+        const int s = e / v.I3, vv = e - s * v.I3;
+        const long long p0 = (long long)k * C2C_PLAN_CHUNK;
+        const long long p1 = p0 + C2C_PLAN_CHUNK < v.P ? p0 + C2C_PLAN_CHUNK : v.P;
+        int cnt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt[j] = 0;
+        for (long long pb = p0; pb < p1; pb += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long p = pb + j;
+                if (p < p1 && v.g[p] && plan_resid_sv(v, mask + (size_t)p * v.E, (int)(p / v.ppc0), s, vv)) {
+                    v.pos_ent[(size_t)off + 8 * cnt[j] + j] = (uint16_t)(p - p0);
+                    ++cnt[j];
                 }
+            }
         }
-        for (; n < depth; ++n) v.ell_ent[((size_t)base + n) * 32 + lane] = (uint16_t)0xFFFF;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            for (int c = cnt[j]; c < len8; ++c) v.pos_ent[(size_t)off + 8 * c + j] = (uint16_t)0xFFFFu;
     }
 }
 
@@ -276,9 +296,9 @@ cudaError_t c2c_plan_fill(const uint8_t* mask, const PlanView& v, int nsm, cudaS
     long long grid = (v.P + 7) / 8;
     if (grid > (long long)nsm * 16) grid = (long long)nsm * 16;
     plan_fill_csr_kernel<<<(unsigned)grid, 256, 0, st>>>(mask, v);
-    long long g2 = ((long long)v.nchunks * v.ngroups + 7) / 8;
+    long long g2 = ((long long)v.nchunks * ((v.E + 31) / 32) + 7) / 8;
     if (g2 > (long long)nsm * 16) g2 = (long long)nsm * 16;
-    plan_fill_ell_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
+    plan_fill_pos_kernel<<<(unsigned)g2, 256, 0, st>>>(mask, v);
     return cudaGetLastError();
 }
 
@@ -608,35 +628,45 @@ cudaError_t c2c_launch_fiber_corr_gram(const PlanView& v, const float* A2, const
 // ---------------------------------------------------------------------------------------------------------------------
 // the residual lists
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lead_weight32(unsigned p, const LeadInfo& lead, int ldr, int r)
+// Wmat[p, 4 quad .. 4 quad + 3]: a thread per (plane, column quad); the padding columns of packed factors are zero, so are W's
+__global__ void __launch_bounds__(256)
+wmat_kernel(const LeadInfo lead, long long P, int ldr, float* __restrict__ Wmat, const int* done)
 {
-    float w = 1.0f;
-    unsigned rem = p;
-    for (int k = lead.nl - 1; k >= 0; --k) {
-        const unsigned d = (unsigned)lead.dim[k];
-        const unsigned q = rem / d;
-        const unsigned i = rem - q * d;
-        rem = q;
-        w *= lead.fac[k][(size_t)i * ldr + r];
+    if (run_done(done)) return;
+    const int nq = ldr / 4;
+    const long long n = P * nq;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long p = t / nq;
+        const int quad = (int)(t - p * nq);
+        reinterpret_cast<float4*>(Wmat)[t] = lead_quad(p, lead, ldr, quad);
     }
-    return w;
+}
+
+cudaError_t c2c_launch_wmat(const LeadInfo& lead, long long P, int ldr, float* Wmat, const int* done, cudaStream_t st)
+{
+    const long long n = P * (ldr / 4);
+    long long grid = (n + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    return c2c_launch_ex(wmat_kernel, dim3((unsigned)grid), dim3(256), 0, st, 0, lead, P, ldr, Wmat, done);
 }
 
 constexpr __host__ __device__ int plan_b_pitch(int nq) { return ((nq / 4) & 1) ? nq : nq + 4; }
 constexpr __host__ __device__ int plan_pow2(int n) { return n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+constexpr __host__ __device__ int plan_lpr(int nq) { return nq <= 16 ? 16 : 32; }     // lanes per list row
 
-// Every lane holds NP (a power of two <= 32) values; returns the sum over the 32 lanes of value `col`, where `col` is fixed by
-// the lane number: at the step of width o the lanes with that bit set keep the upper half of what they hold and send the lower
-// half (and vice versa), so the count halves per step; the widths that are left over when one value remains are plain
-// butterflies.  Lanes that differ only in those leftover low bits end with the same column.
-template <int NP>
-__device__ __forceinline__ float plan_halving_sum(float (&a)[NP], int lane, int& col)
+// Every lane of a group of LPR lanes holds NP <= LPR values (NP a power of two); returns the sum over the group of value `col`,
+// where `col` is fixed by the lane number: at the step of width o the lanes with that bit set keep the upper half of what they
+// hold and send the lower half (and vice versa), so the count halves per step; the widths that are left over when one value
+// remains are plain butterflies.  Lanes that differ only in those leftover low bits end with the same column.  Fixed tree.
+template <int NP, int LPR>
+__device__ __forceinline__ float plan_halving_sum(float (&a)[NP], int sl, int& col)
 {
+    static_assert(NP <= LPR, "one value per lane at the end");
     col = 0;
-    int o = 16;
+    int o = LPR / 2;
 #pragma unroll
     for (int n = NP; n > 1; n >>= 1) {
-        const bool up = (lane & o) != 0;
+        const bool up = (sl & o) != 0;
 #pragma unroll
         for (int j = 0; j < n / 2; ++j) {
             const float send = up ? a[j] : a[j + n / 2];
@@ -652,185 +682,188 @@ __device__ __forceinline__ float plan_halving_sum(float (&a)[NP], int lane, int&
 }
 
 #define C2C_PLAN_PRELOAD 8
-// a warp per plane with residual entries: lanes stride the plane's list, B rows from shared memory (SMEM_B) or L1
-template <int NQ, bool SMEM_B>
-__global__ void __launch_bounds__(512)
-plane_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ Bmat, const float* Tin,
-                       float* Tout, int R, const int* done)
+// One list row per group of LPR lanes (two rows per warp at NQ <= 16): sum over the row's entries j of <own, tab[j]> tab[j, :].
+// The lanes stride the row's class-ordered list, so the eight lanes of a quarter-warp gather rows of eight different classes
+// (row number mod 8): with an odd number of 16-byte quads per table row every LDS.128 is conflict-free.  `n` = this group's
+// slots (0: nothing to do), `nmax` = the longest of the warp's rows (the loop is warp-uniform).  Returns the group's sum of
+// column `col`.
+template <int NQ, int LPR, int PB>
+__device__ __forceinline__ float plan_row_sum(const float* tab, const uint16_t* __restrict__ ent, int n, int nmax,
+                                              const float* __restrict__ own, int sl, int& col)
+{
+    float2 w[NQ / 2], acc[NQ / 2];
+#pragma unroll
+    for (int q = 0; q < NQ / 2; ++q) { w[q] = make_float2(0.0f, 0.0f); acc[q] = make_float2(0.0f, 0.0f); }
+    if (n > 0) {
+#pragma unroll
+        for (int k = 0; k < NQ / 4; ++k) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(own) + k);
+            w[2 * k] = make_float2(x.x, x.y); w[2 * k + 1] = make_float2(x.z, x.w);
+        }
+    }
+    for (int i0 = 0; i0 < nmax; i0 += LPR * C2C_PLAN_PRELOAD) {
+        int ev[C2C_PLAN_PRELOAD];                                       // the list reads of a batch are in flight together
+#pragma unroll
+        for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
+            const int i = i0 + u * LPR + sl;
+            ev[u] = i < n ? (int)ent[i] : 0xFFFF;
+        }
+#pragma unroll
+        for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
+            if (ev[u] == 0xFFFF) continue;                              // padding of a class that has run out / past the row
+            const float4* b4 = reinterpret_cast<const float4*>(tab + (size_t)ev[u] * PB);
+            float2 b[NQ / 2];
+#pragma unroll
+            for (int k = 0; k < NQ / 4; ++k) {
+                const float4 x = b4[k];
+                b[2 * k] = make_float2(x.x, x.y); b[2 * k + 1] = make_float2(x.z, x.w);
+            }
+            float2 r2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int q = 0; q < NQ / 2; ++q) r2 = ffma2(w[q], b[q], r2);
+            const float rec = r2.x + r2.y;
+            const float2 rr = make_float2(rec, rec);
+#pragma unroll
+            for (int q = 0; q < NQ / 2; ++q) acc[q] = ffma2(rr, b[q], acc[q]);
+        }
+    }
+    // column sums over the group's lanes by recursive halving (about NQ shuffles instead of 5 NQ)
+    constexpr int NP = plan_pow2(NQ);
+    float vals[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) vals[q] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < NQ / 2; ++q) { vals[2 * q] = acc[q].x; vals[2 * q + 1] = acc[q].y; }
+    return plan_halving_sum<NP, LPR>(vals, sl, col);
+}
+
+// MODE 0 -- rows = planes: own = Wmat[p], table = Bmat (every in-plane position; in shared memory when SMEM_TAB, else read
+//           through L1), entries = in-plane positions; Tout[p] = Tin[p] + sum.  1-D grid, the warps stride the planes.
+// MODE 1 -- rows = positions of a chunk of planes: own = Bmat[e], table = the chunk's rows of Wmat (always in shared memory),
+//           entries = plane numbers within the chunk; CTA (i, j) takes the positions [i epi, (i + 1) epi) and the chunks
+//           [j cpj, (j + 1) cpj), restaging the table per chunk; out = part[j][e] (first chunk: store, then accumulate --
+//           the same lane every time, so no race and a fixed order).
+template <int NQ, int MODE, bool SMEM_TAB>
+__global__ void __launch_bounds__(NQ <= 16 ? 512 : 256)
+corr_rows_kernel(const PlanView v, const float* __restrict__ Wmat, const float* __restrict__ Bmat, const float* Tin,
+                 float* out, int epi, int cpj, const int* done)
 {
     pdl_trigger();
     pdl_wait();
     if (run_done(done)) return;
-    extern __shared__ __align__(16) float pcl_smem[];
-    // shared-memory pitch of a B row: an ODD number of 16-byte quads, so that rows that differ modulo 8 (the class order of
-    // the list) start in different bank groups
-    constexpr int PB = SMEM_B ? plan_b_pitch(NQ) : NQ;
-    if (SMEM_B) {
-        const float4* src = reinterpret_cast<const float4*>(Bmat);
-        float4* dst = reinterpret_cast<float4*>(pcl_smem);
-        for (int i = threadIdx.x; i < v.E * (NQ / 4); i += blockDim.x) {
-            const int e = i / (NQ / 4), k = i - e * (NQ / 4);
-            dst[e * (PB / 4) + k] = src[i];
-        }
-        __syncthreads();
-    }
-    const float* Bsrc = SMEM_B ? pcl_smem : Bmat;
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const bool copy = Tin != Tout;
-    for (long long p = warp; p < v.P; p += nwarps) {
-        const int b0 = v.row_off[p], n = v.row_off[p + 1] - b0;
-        if (n == 0) {
-            if (copy && lane < NQ) Tout[(size_t)p * NQ + lane] = Tin[(size_t)p * NQ + lane];
-            continue;
-        }
-        const float wl = lane < R ? lead_weight32((unsigned)p, lead, NQ, lane) : 0.0f;
-        float2 w[NQ / 2], acc[NQ / 2];
-#pragma unroll
-        for (int q = 0; q < NQ / 2; ++q) {
-            w[q] = make_float2(__shfl_sync(0xffffffffu, wl, 2 * q), __shfl_sync(0xffffffffu, wl, 2 * q + 1));
-            acc[q] = make_float2(0.0f, 0.0f);
-        }
-        for (int i0 = 0; i0 < n; i0 += 32 * C2C_PLAN_PRELOAD) {
-            int ev[C2C_PLAN_PRELOAD];                                   // the list reads of a batch are in flight together
-#pragma unroll
-            for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
-                const int i = i0 + u * 32 + lane;
-                ev[u] = i < n ? (int)v.csr_ent[(size_t)b0 + i] : 0xFFFF;
+    extern __shared__ __align__(16) float crk_smem[];
+    constexpr int LPR = plan_lpr(NQ), NROW = 32 / LPR;
+    constexpr int PB = SMEM_TAB ? plan_b_pitch(NQ) : NQ;
+    constexpr int NP = plan_pow2(NQ);
+    const int lane = threadIdx.x & 31, sl = lane & (LPR - 1), sub = lane / LPR;
+    const bool writer = (sl & (LPR / NP - 1)) == 0;
+    if (MODE == 0) {
+        if (SMEM_TAB) {
+            const float4* src = reinterpret_cast<const float4*>(Bmat);
+            float4* dst = reinterpret_cast<float4*>(crk_smem);
+            for (int i = threadIdx.x; i < v.E * (NQ / 4); i += blockDim.x) {
+                const int e = i / (NQ / 4), k = i - e * (NQ / 4);
+                dst[e * (PB / 4) + k] = src[i];
             }
-#pragma unroll
-            for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
-                if (ev[u] == 0xFFFF) continue;                          // padding of a class that has run out
-                const float4* b4 = reinterpret_cast<const float4*>(Bsrc + (size_t)ev[u] * PB);
-                float2 b[NQ / 2];
-#pragma unroll
-                for (int k = 0; k < NQ / 4; ++k) {
-                    const float4 x = b4[k];
-                    b[2 * k] = make_float2(x.x, x.y); b[2 * k + 1] = make_float2(x.z, x.w);
+            __syncthreads();
+        }
+        const float* tab = SMEM_TAB ? crk_smem : Bmat;
+        const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+        const bool copy = Tin != out;
+        for (long long g0 = warp * NROW; g0 < v.P; g0 += nwarps * NROW) {
+            const long long p = g0 + sub;
+            int b0 = 0, n = 0;
+            if (p < v.P) { b0 = v.row_off[p]; n = v.row_off[p + 1] - b0; }
+            int nmax = n;
+            if (NROW == 2) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, n, 16));
+            if (nmax == 0) {
+                if (copy && p < v.P && sl < NQ) out[(size_t)p * NQ + sl] = Tin[(size_t)p * NQ + sl];
+                continue;
+            }
+            int col;
+            const float mine = plan_row_sum<NQ, LPR, PB>(tab, v.csr_ent + b0, n, nmax, Wmat + (size_t)(p < v.P ? p : 0) * NQ, sl, col);
+            if (p < v.P && col < NQ && writer) out[(size_t)p * NQ + col] = Tin[(size_t)p * NQ + col] + mine;
+        }
+    } else {
+        const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int e_begin = blockIdx.x * epi;
+        const int e_end = e_begin + epi < v.E ? e_begin + epi : v.E;
+        const int k_begin = blockIdx.y * cpj;
+        const int k_end = k_begin + cpj < v.nchunks ? k_begin + cpj : v.nchunks;
+        float* part = out + (size_t)blockIdx.y * v.E * NQ;
+        for (int k = k_begin; k < k_end; ++k) {
+            const long long p0 = (long long)k * C2C_PLAN_CHUNK;
+            const int np = (int)(v.P - p0 < C2C_PLAN_CHUNK ? v.P - p0 : C2C_PLAN_CHUNK);
+            __syncthreads();
+            {
+                const float4* src = reinterpret_cast<const float4*>(Wmat + (size_t)p0 * NQ);
+                float4* dst = reinterpret_cast<float4*>(crk_smem);
+                for (int i = threadIdx.x; i < np * (NQ / 4); i += blockDim.x) {
+                    const int pl = i / (NQ / 4), q = i - pl * (NQ / 4);
+                    dst[pl * (PB / 4) + q] = src[i];
                 }
-                float2 r2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                for (int q = 0; q < NQ / 2; ++q) r2 = ffma2(w[q], b[q], r2);
-                const float rec = r2.x + r2.y;
-                const float2 rr = make_float2(rec, rec);
-#pragma unroll
-                for (int q = 0; q < NQ / 2; ++q) acc[q] = ffma2(rr, b[q], acc[q]);
+            }
+            __syncthreads();
+            const int* off = v.pos_off + (size_t)k * v.E;
+            for (int g0 = e_begin + wid * NROW; g0 < e_end; g0 += nw * NROW) {
+                const int e = g0 + sub;
+                const bool live = e < e_end;
+                int b0 = 0, n = 0;
+                if (live) { b0 = off[e]; n = off[e + 1] - b0; }
+                int nmax = n;
+                if (NROW == 2) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, n, 16));
+                int col = 0;
+                float mine = 0.0f;
+                if (nmax > 0) mine = plan_row_sum<NQ, LPR, PB>(crk_smem, v.pos_ent + b0, n, nmax, Bmat + (size_t)(live ? e : 0) * NQ, sl, col);
+                else {                                                     // the column this lane would end with (plan_halving_sum)
+                    int o = LPR / 2;
+                    for (int m = NP; m > 1; m >>= 1) { if (sl & o) col += m / 2; o >>= 1; }
+                }
+                if (live && col < NQ && writer) {
+                    float* dstp = part + (size_t)e * NQ + col;
+                    *dstp = k == k_begin ? mine : *dstp + mine;
+                }
             }
         }
-        // column sums over the lanes by recursive halving (about NQ shuffles instead of 5 NQ, fixed tree)
-        float vals[plan_pow2(NQ)];
-#pragma unroll
-        for (int q = 0; q < plan_pow2(NQ); ++q) vals[q] = 0.0f;
-#pragma unroll
-        for (int q = 0; q < NQ / 2; ++q) { vals[2 * q] = acc[q].x; vals[2 * q + 1] = acc[q].y; }
-        int col;
-        const float mine = plan_halving_sum<plan_pow2(NQ)>(vals, lane, col);
-        if (col < NQ && (lane & ((32 / plan_pow2(NQ)) - 1)) == 0) Tout[(size_t)p * NQ + col] = Tin[(size_t)p * NQ + col] + mine;
     }
 }
 
-cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, const float* Bmat, const float* Tin, float* Tout,
-                                       int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
+#define C2C_PLAN_DISPATCH_ROWS(CALL)                                                                                     \
+    switch (ldr) {                                                                                                       \
+        case 4: CALL(4); break; case 8: CALL(8); break; case 12: CALL(12); break; case 16: CALL(16); break;              \
+        case 20: CALL(20); break; case 24: CALL(24); break; case 28: CALL(28); break; case 32: CALL(32); break;          \
+        default: return cudaErrorNotSupported;                                                                           \
+    }
+
+cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Tin, float* Tout,
+                                       int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
 {
     const size_t bbytes = (size_t)v.E * plan_b_pitch(ldr) * sizeof(float);
     const bool smem_b = bbytes <= 100 * 1024;
     const int block = ldr <= 16 ? 512 : 256;                           // <= 64 registers per thread at ldr <= 16: 32 warps per SM
-    long long grid = (v.P * 32 + block - 1) / block;
+    const int nrow = 32 / plan_lpr(ldr);
+    long long grid = ((v.P + nrow - 1) / nrow * 32 + block - 1) / block;
     if (grid > (long long)nsm * (smem_b ? 2 : 8)) grid = (long long)nsm * (smem_b ? 2 : 8);
 #define PCL_CALL(N)                                                                                                      \
     do {                                                                                                                 \
         cudaError_t e_;                                                                                                  \
         if (smem_b) {                                                                                                    \
             if (bbytes > 48 * 1024) {                                                                                    \
-                e_ = cudaFuncSetAttribute(plane_corr_list_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+                e_ = cudaFuncSetAttribute(corr_rows_kernel<N, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
                 if (e_ != cudaSuccess) return e_;                                                                        \
             }                                                                                                            \
-            e_ = c2c_launch_ex(plane_corr_list_kernel<N, true>, dim3((unsigned)grid), dim3(block), bbytes, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+            e_ = c2c_launch_ex(corr_rows_kernel<N, 0, true>, dim3((unsigned)grid), dim3(block), bbytes, st, pdl, v, Wmat, Bmat, Tin, Tout, 0, 0, done); \
         } else                                                                                                           \
-            e_ = c2c_launch_ex(plane_corr_list_kernel<N, false>, dim3((unsigned)grid), dim3(block), 0, st, pdl, v, lead, Bmat, Tin, Tout, R, done); \
+            e_ = c2c_launch_ex(corr_rows_kernel<N, 0, false>, dim3((unsigned)grid), dim3(block), 0, st, pdl, v, Wmat, Bmat, Tin, Tout, 0, 0, done); \
         if (e_ != cudaSuccess) return e_;                                                                                \
     } while (0)
-    C2C_PLAN_DISPATCH(PCL_CALL)
+    C2C_PLAN_DISPATCH_ROWS(PCL_CALL)
 #undef PCL_CALL
     return cudaSuccess;
 }
 
-// CTA (i, j): 8 position groups (one per warp, 32 positions each, accumulators and B rows in registers) x a range of plane
-// chunks; the Khatri-Rao rows of a chunk are staged in shared memory once per CTA and read by all 8 warps.
-template <int NQ>
-__global__ void __launch_bounds__(256)
-fiber_corr_list_kernel(const PlanView v, const LeadInfo lead, const float* __restrict__ A2, const float* __restrict__ A3,
-                       float* __restrict__ part, int R, int cpj, const int* done)
-{
-    pdl_trigger();
-    pdl_wait();
-    if (run_done(done)) return;
-    __shared__ __align__(16) float sW[C2C_PLAN_CHUNK * NQ];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int gq = blockIdx.x * 8 + wid;                               // this warp's position group
-    const int e = gq * 32 + lane;
-    const bool live = gq < v.ngroups && e < v.E;
-    float b[NQ], acc[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) { b[q] = 0.0f; acc[q] = 0.0f; }
-    if (live) {
-        const int s = e / v.I3, vv = e - s * v.I3;
-#pragma unroll
-        for (int k = 0; k < NQ / 4; ++k) {
-            const float4 x = *(reinterpret_cast<const float4*>(A2 + (size_t)s * NQ) + k);
-            const float4 y = *(reinterpret_cast<const float4*>(A3 + (size_t)vv * NQ) + k);
-            b[4 * k] = x.x * y.x; b[4 * k + 1] = x.y * y.y; b[4 * k + 2] = x.z * y.z; b[4 * k + 3] = x.w * y.w;
-        }
-    }
-    const int k_begin = blockIdx.y * cpj;
-    const int k_end = k_begin + cpj < v.nchunks ? k_begin + cpj : v.nchunks;
-    for (int k = k_begin; k < k_end; ++k) {
-        const long long p0 = (long long)k * C2C_PLAN_CHUNK;
-        const int np = (int)(v.P - p0 < C2C_PLAN_CHUNK ? v.P - p0 : C2C_PLAN_CHUNK);
-        __syncthreads();
-        for (int t = threadIdx.x; t < np * NQ; t += blockDim.x) {
-            const int pl = t / NQ, q = t - pl * NQ;
-            sW[t] = q < R ? lead_weight32((unsigned)(p0 + pl), lead, NQ, q) : 0.0f;
-        }
-        __syncthreads();
-        if (gq < v.ngroups) {
-            const int base = v.ell_off[(size_t)k * v.ngroups + gq];
-            const int depth = v.ell_off[(size_t)k * v.ngroups + gq + 1] - base;
-            const uint16_t* ent = v.ell_ent + (size_t)base * 32 + lane;
-            for (int d0 = 0; d0 < depth; d0 += C2C_PLAN_PRELOAD) {
-                unsigned pls[C2C_PLAN_PRELOAD];
-#pragma unroll
-                for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) pls[u] = d0 + u < depth ? (unsigned)ent[(size_t)(d0 + u) * 32] : 0xFFFFu;
-#pragma unroll
-                for (int u = 0; u < C2C_PLAN_PRELOAD; ++u) {
-                    const unsigned pl = pls[u];
-                    if (pl == 0xFFFFu) continue;
-                    const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)pl * NQ);
-                    float w[NQ];
-#pragma unroll
-                    for (int kk = 0; kk < NQ / 4; ++kk) {
-                        const float4 x = w4[kk];
-                        w[4 * kk] = x.x; w[4 * kk + 1] = x.y; w[4 * kk + 2] = x.z; w[4 * kk + 3] = x.w;
-                    }
-                    float r0 = 0.0f, r1 = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < NQ; q += 2) { r0 = fmaf(w[q], b[q], r0); r1 = fmaf(w[q + 1], b[q + 1], r1); }
-                    const float rec = r0 + r1;
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) acc[q] = fmaf(rec, w[q], acc[q]);
-                }
-            }
-        }
-    }
-    if (live) {
-        float4* out = reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * v.E + e) * NQ);
-#pragma unroll
-        for (int k = 0; k < NQ / 4; ++k) out[k] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-    }
-}
-
-// Uout = Uin + sum of the plane-range partials, in a fixed order
+// Uout = Uin + sum of the chunk-range partials, in a fixed order
 __global__ void __launch_bounds__(256)
 plan_reduce_kernel(const float* __restrict__ part, int nparts, long long n4, const float* Uin, float* Uout,
                    const int* done)
@@ -849,23 +882,48 @@ plan_reduce_kernel(const float* __restrict__ part, int nparts, long long n4, con
     reinterpret_cast<float4*>(Uout)[i] = make_float4(u.x + s.x, u.y + s.y, u.z + s.z, u.w + s.w);
 }
 
-cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const LeadInfo& lead, const float* A2, const float* A3, const float* Uin,
-                                       float* Uout, float* part, int max_parts, int R, int ldr, const int* done, int nsm,
-                                       cudaStream_t st, int pdl)
+cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Uin, float* Uout,
+                                       float* part, int max_parts, int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
 {
-    const int ni = (v.ngroups + 7) / 8;
-    int nj = (4 * nsm + ni - 1) / ni;                                  // ~4 CTAs per SM in all (64 registers x 256 threads)
-    if (nj > max_parts) nj = max_parts;
-    if (nj > v.nchunks) nj = v.nchunks;
-    if (nj < 1) nj = 1;
-    const int cpj = (v.nchunks + nj - 1) / nj;
-    nj = (v.nchunks + cpj - 1) / cpj;
-    const dim3 grid((unsigned)ni, (unsigned)nj);
-#define FCL_CALL(N) do { const cudaError_t e_ = c2c_launch_ex(fiber_corr_list_kernel<N>, grid, dim3(256), 0, st, pdl, v, lead, A2, A3, part, R, cpj, done); \
-                         if (e_ != cudaSuccess) return e_; } while (0)
-    C2C_PLAN_DISPATCH(FCL_CALL)
+    const size_t tbytes = (size_t)C2C_PLAN_CHUNK * plan_b_pitch(ldr) * sizeof(float);
+    const int block = ldr <= 16 ? 512 : 256;
+    // CTAs resident per SM: 64 registers x 512 threads (or ~128 x 256) -> 2 by registers; the staged chunk of W rows by smem
+    int per_sm = (int)((220 * 1024) / (tbytes + 1024));
+    if (per_sm > 2) per_sm = 2;
+    if (per_sm < 1) per_sm = 1;
+    const int resident = nsm * per_sm;
+    int nparts = v.nchunks < max_parts ? v.nchunks : max_parts;       // chunk ranges (= partials)
+    if (nparts > resident) nparts = resident;
+    if (nparts < 1) nparts = 1;
+    const int cpj = (v.nchunks + nparts - 1) / nparts;
+    nparts = (v.nchunks + cpj - 1) / cpj;
+    // position ranges: one wave of CTAs in all, or two when that fills the machine better (118 chunks: 2 x 118 of 296 places
+    // against 5 x 118 of 2 x 296)
+    int ni = resident / nparts;
+    {
+        const int ni2 = 2 * resident / nparts;
+        if (ni < 1 || (double)ni2 * nparts / (2.0 * resident) > (double)ni * nparts / resident + 0.1) ni = ni2;
+    }
+    const int nrow = 32 / plan_lpr(ldr), rows_per_trip = (block / 32) * nrow;
+    const int max_ni = (v.E + rows_per_trip - 1) / rows_per_trip;
+    if (ni > max_ni) ni = max_ni;
+    if (ni < 1) ni = 1;
+    const int epi = (v.E + ni - 1) / ni;
+    ni = (v.E + epi - 1) / epi;
+    const dim3 grid((unsigned)ni, (unsigned)nparts);
+#define FCL_CALL(N)                                                                                                      \
+    do {                                                                                                                 \
+        cudaError_t e_;                                                                                                  \
+        if (tbytes > 48 * 1024) {                                                                                        \
+            e_ = cudaFuncSetAttribute(corr_rows_kernel<N, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tbytes); \
+            if (e_ != cudaSuccess) return e_;                                                                            \
+        }                                                                                                                \
+        e_ = c2c_launch_ex(corr_rows_kernel<N, 1, true>, grid, dim3(block), tbytes, st, pdl, v, Wmat, Bmat, (const float*)nullptr, part, epi, cpj, done); \
+        if (e_ != cudaSuccess) return e_;                                                                                \
+    } while (0)
+    C2C_PLAN_DISPATCH_ROWS(FCL_CALL)
 #undef FCL_CALL
     const long long n4 = (long long)v.E * ldr / 4;
-    return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, pdl, (const float*)part, nj, n4, Uin,
+    return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, pdl, (const float*)part, nparts, n4, Uin,
                          Uout, done);
 }

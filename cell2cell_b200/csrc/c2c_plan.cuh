@@ -14,35 +14,38 @@
 // flops per mode instead of O(N_missing R), and no pass over the mask at all.  The plan holds the tightest separable model
 // of ANY mask (g / hs / hv = "some entry observed": it never calls an observed entry missing) plus the RESIDUAL -- entries
 // the model calls observed but the mask does not (empty for cell2cell's own masks, everything for an unstructured mask) --
-// as two lists: by plane (CSR, for the leading modes) and by position within 256-plane chunks (32-wide ELL, for the
-// trailing modes).
+// as two lists of the same form: by plane (in-plane positions, for the leading modes) and by position within chunks of
+// C2C_PLAN_CHUNK planes (plane numbers within the chunk, for the trailing modes).  Both contractions are then the SAME
+// row-wise sum  out[row, :] = sum over the row's entries j of <own[row], tab[j]> tab[j, :]  -- own = W[p], tab = B for a plane
+// row; own = B[e], tab = the chunk's W rows for a position row -- with `tab` staged in shared memory (corr_rows_kernel).
 #pragma once
 #include "c2c_common.cuh"
 
-#define C2C_PLAN_CHUNK 256            // planes per chunk of the position-major residual lists
+#define C2C_PLAN_CHUNK 1024           // planes per chunk of the position-major residual lists (their W rows fit shared memory)
 #define C2C_PLAN_MAX_E 65535          // in-plane positions are stored as uint16
 #define C2C_PLAN_NCOUNTERS 8
 
 struct PlanView {
     // header (sized from the shape alone)
     unsigned long long* counters;     // [0] missing entries, [1] residual entries, [2] non-zero value under a zero mask byte,
-                                      // [3] rows (of 32) of the position-major lists, [4] model has missing entries, [5] overflow,
+                                      // [3] slots of the position-major lists, [4] model has missing entries, [5] overflow,
                                       // [6] residual entries without the class padding of the by-plane list ([1] counts its slots)
     uint8_t* g;                       // [P]        plane has an observed entry
     int* hs;                          // [C0 x I2]  row s of the planes of context c has an observed entry
     int* hv;                          // [C0 x I3]  column v ...
     int* row_off;                     // [P + 1]    list slots by plane (8 x the longest position class of the plane)
-    int* ell_off;                     // [nchunks * ngroups + 1]  rows of 32 by (chunk, position group)
+    int* pos_off;                     // [nchunks * E + 1]  list slots by (chunk, position) (8 x the longest plane class)
     // lists (sized by the scan)
     uint16_t* csr_ent;                // [slots]    in-plane position, plane by plane; slot i holds a position of class i mod 8
                                       //            (increasing within a class), 0xFFFF = padding
-    uint16_t* ell_ent;                // [ell_rows][32]  plane index within its chunk, 0xFFFF = padding
+    uint16_t* pos_ent;                // [slots]    plane number within its chunk, (chunk, position) by (chunk, position);
+                                      //            slot i holds a plane of class i mod 8, 0xFFFF = padding
     long long P; long long ppc0;      // planes; planes per index of the first mode
-    int E, I2, I3, C0, nchunks, ngroups;
+    int E, I2, I3, C0, nchunks;
 };
 
 size_t c2c_plan_header_bytes(long long P, int E, int I2, int I3, int C0);
-size_t c2c_plan_lists_bytes(long long n_resid, long long ell_rows);
+size_t c2c_plan_lists_bytes(long long n_resid, long long pos_slots);
 // carve the caller's buffers (lists may be null before the scan)
 void c2c_plan_view(PlanView& v, long long P, int E, int I2, int I3, int C0, void* header, void* lists, long long n_resid);
 
@@ -68,12 +71,13 @@ cudaError_t c2c_launch_lead_ctx_gram(const PlanView& v, const LeadInfo& lead, in
 cudaError_t c2c_launch_fiber_corr_gram(const PlanView& v, const float* A2, const float* A3, const float* Ymat, const float* U0,
                                        float* Uw, int R, int ldr, const int* done, cudaStream_t st, int pdl);
 
-// ---- corrections over the residual list ------------------------------------------------------------------------------------
+// ---- corrections over the residual lists ----------------------------------------------------------------------------------
+// Wmat[p, :] = Khatri-Rao row of the leading factors of plane p ([P][ldr]; recomputed whenever a leading factor changed)
+cudaError_t c2c_launch_wmat(const LeadInfo& lead, long long P, int ldr, float* Wmat, const int* done, cudaStream_t st);
 // Tout[p, :] = Tin[p, :] + sum over the residual entries e of plane p of <W[p], B[e]> B[e, :]   (Tin == Tout: in place)
-cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const LeadInfo& lead, const float* Bmat, const float* Tin, float* Tout,
-                                       int R, int ldr, const int* done, int nsm, cudaStream_t st, int pdl);
+cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Tin, float* Tout,
+                                       int ldr, const int* done, int nsm, cudaStream_t st, int pdl);
 // Uout[e, :] = Uin[e, :] + sum over the residual planes p at position e of <W[p], B[e]> W[p, :];  part: scratch
 // [max_parts][E * ldr]
-cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const LeadInfo& lead, const float* A2, const float* A3, const float* Uin,
-                                       float* Uout, float* part, int max_parts, int R, int ldr, const int* done, int nsm,
-                                       cudaStream_t st, int pdl);
+cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Uin, float* Uout,
+                                       float* part, int max_parts, int ldr, const int* done, int nsm, cudaStream_t st, int pdl);

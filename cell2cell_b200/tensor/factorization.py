@@ -9,6 +9,8 @@ calls replaced by the device driver (``cell2cell_b200.engine`` -> ``libc2c_b200.
   ``_multiple_runs_elbow_analysis`` (:272-373), ``_compute_norm_error`` (:376-432), ``normalized_error`` (:435-458) and
   ``_compute_elbow`` (:146-183, Kneedle restated in ``elbow.py`` because kneed is not installable here).
 """
+import os
+
 import numpy as np
 import torch
 from tqdm.auto import tqdm
@@ -479,7 +481,7 @@ def _run_elbow_analysis(tensor, upper_rank=50, tf_type="non_negative_cp", init="
 
 def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_negative_cp", init="svd",
                                   svd="truncated_svd", metric="error", random_state=None, mask=None, n_iter_max=100,
-                                  tol=10e-7, verbose=False, batch_runs=True, host_threads=1, **kwargs):
+                                  tol=10e-7, verbose=False, batch_runs=True, host_threads=None, **kwargs):
     """``runs`` factorizations per rank; ndarray (runs x upper_rank) of losses (factorization.py:272-373).
 
     The ``upper_rank * runs`` units are independent; when ``torch.distributed`` is initialised they are spread over the
@@ -487,6 +489,10 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
     assert isinstance(runs, int), "runs must be an integer"
     assert metric in ("similarity", "error"), "`metric` must be either 'similarity' or 'error'"
     from ..parallel import run_units
+    if host_threads is None:
+        # host threads issuing this rank's units, each on a CUDA stream of its own: the host part of one bin of runs (factor
+        # init, upload, graph capture, read-back) overlaps the device part of another (parallel._run_local)
+        host_threads = int(os.environ.get("C2C_B200_HOST_THREADS", "1"))
     kwargs = dict(kwargs or {})
     kwargs["return_errors"] = True
     X = as_device_tensor(tensor)
