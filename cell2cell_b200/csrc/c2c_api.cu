@@ -319,12 +319,17 @@ static void mma_geometry(Geo& g, int rank)
                 int r2 = (512 - acc) / (g.fm_ntile * (n == 16 ? 16 : 8));
                 g.fm_ring2 = r2 > C2C_MMA_RING2 ? C2C_MMA_RING2 : r2;
             }
-            g.fm_nj = nsm / best_es;
-            g.fm_grid = g.fm_nj * best_es;
-            g.fm_nst = (g.P + 7) / 8;
-            g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, best_in_smem ? ldr : 0, best_nx);
-            if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
-            g.mma_fiber_ok = 1;
+            // three prep groups fill the ring round-robin: with a ring shallower than that a group could run two laps ahead of
+            // the MMA warp and pass an mbarrier wait on the parity of an EARLIER phase (the cause of the wrong sums of the
+            // all-TMEM N = 32 experiment of round 1, whose ring was 2 deep) -- such a geometry is refused
+            if (g.fm_ring2 >= C2C_MMA_PREP_GROUPS) {
+                g.fm_nj = nsm / best_es;
+                g.fm_grid = g.fm_nj * best_es;
+                g.fm_nst = (g.P + 7) / 8;
+                g.fm_smem = c2c_fiber_mma_smem(n, g.fm_na, best_in_smem ? ldr : 0, best_nx);
+                if ((long long)g.fm_nj > g.max_parts) g.max_parts = g.fm_nj;
+                g.mma_fiber_ok = 1;
+            }
         }
     }
     g.mma_ok = 1;
@@ -1352,10 +1357,13 @@ static int enqueue_iteration_plan(const RunCtx& c)
             src = c.w.Tw;
         }
         if (lists) {
-            e = c2c_launch_wmat(li, g.P, c.ldr, c.w.Wmat, done, c.st);
+            // mode 0 finds the W rows of the previous iteration's fiber corrections (before the first iteration: of the
+            // initial factors, ncp_run_impl): the leading factors have not changed since
+            e = cudaSuccess;
+            if (mode > 0) { e = c2c_launch_wmat(li, g.P, c.ldr, c.w.Wmat, done, c.st); g_launches.fetch_add(1, std::memory_order_relaxed); }
             if (e == cudaSuccess) e = c2c_launch_plane_corr_list(c.pv, c.w.Wmat, c.w.Bmat, src, c.w.Tw, c.ldr, done, nsm, c.st, c.pdl);
             if (e != cudaSuccess) return cuda_fail(e, "plane_corr_list launch");
-            g_launches.fetch_add(2, std::memory_order_relaxed);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if ((rc = launch_lead_update(c2, mode)) != 0) return rc;
     }
@@ -1541,6 +1549,13 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
     c.pdl = (use_pdl() && fused && (mask == nullptr || c.plan)) ? 1 : 0;
     c.mma_zero = g.mma_ok && g.mma_fiber_ok && mask == nullptr;
     if (c.mma_zero) CK(cudaMemsetAsync(c.w.T, 0, (size_t)g.P * ldr * sizeof(float), st), "memset T");
+
+    if (c.plan && c.n_resid > 0) {                                     // W rows of the initial factors (enqueue_iteration_plan, mode 0)
+        LeadInfo li; fill_lead(li, g, (const float* const*)c.A);
+        const cudaError_t e = c2c_launch_wmat(li, g.P, ldr, c.w.Wmat, nullptr, st);
+        if (e != cudaSuccess) return cuda_fail(e, "wmat launch");
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
 
     // `unroll` iterations are captured once and replayed: ~6 launches per iteration become a fraction of a graph launch, and
     // the dependent launches also link one iteration to the next

@@ -390,8 +390,13 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
 // takes its A operand from TMEM, the X ring slot is released by the prep warps.  The TMEM budget then decides the depth of
 // the prep ring (`ring2`): (512 - accumulator columns) / (16 columns x tiles), 2..4.  -DC2C_FM_SMEM_A restores the
 // shared-memory A operand (MN-major descriptors over the TMA image).
-// It is a template parameter (ALLTS): validated for N = 16 (prep ring of 3); the N = 32 instance (prep ring of 2) gave wrong
-// results / did not finish in the one run it got, so N = 32 keeps the shared-memory A operand for now.
+// It is a template parameter (ALLTS): validated for N = 16 (prep ring of 3).  The N = 32 instance only fits TMEM with a prep
+// ring of 2 and gave wrong sums / did not finish: three prep groups take the stages round-robin, so with a 2-deep ring the
+// group that has finished stage t + 1 moves on to stage t + 4 -- the slot of stage t, two laps later -- while the group of
+// stage t may still be waiting for that slot; both wait on the same mbarrier parity, the later one passes on the completion
+// of the EARLIER phase and the two groups fill the slot together.  A ring at least as deep as the number of prep groups makes
+// every slot-lap wait unambiguous (a group is at most one lap ahead); the launcher refuses shallower rings (c2c_api.cu), and
+// N = 32 keeps the shared-memory A operand (ring of 4).
 
 struct FiberMmaArgs {
     long long P; int E, R, ldr;

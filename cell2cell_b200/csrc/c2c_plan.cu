@@ -863,7 +863,8 @@ cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const float* Wmat, con
     return cudaSuccess;
 }
 
-// Uout = Uin + sum of the chunk-range partials, in a fixed order
+// Uout = Uin + sum of the chunk-range partials, in a fixed order: thread (g, x) sums the partials g, g + 4, ... of float4 x
+// (four short chains instead of one long one: the kernel is a latency chain of L2 reads), the four sums are added g = 0..3
 __global__ void __launch_bounds__(256)
 plan_reduce_kernel(const float* __restrict__ part, int nparts, long long n4, const float* Uin, float* Uout,
                    const int* done)
@@ -871,15 +872,33 @@ plan_reduce_kernel(const float* __restrict__ part, int nparts, long long n4, con
     pdl_trigger();
     pdl_wait();
     if (run_done(done)) return;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
+    __shared__ float4 sh[3][64];
+    const int x = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const long long i = (long long)blockIdx.x * 64 + x;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < nparts; ++c) {
-        const float4 x = reinterpret_cast<const float4*>(part)[(size_t)c * n4 + i];
-        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    if (i < n4) {
+        const float4* p4 = reinterpret_cast<const float4*>(part) + i;
+        int c = grp;
+        for (; c + 12 < nparts; c += 16) {                             // four loads in flight
+            const float4 a = p4[(size_t)c * n4], b = p4[(size_t)(c + 4) * n4], d = p4[(size_t)(c + 8) * n4], f = p4[(size_t)(c + 12) * n4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+            s.x += f.x; s.y += f.y; s.z += f.z; s.w += f.w;
+        }
+        for (; c < nparts; c += 4) {
+            const float4 a = p4[(size_t)c * n4];
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
     }
-    const float4 u = reinterpret_cast<const float4*>(Uin)[i];
-    reinterpret_cast<float4*>(Uout)[i] = make_float4(u.x + s.x, u.y + s.y, u.z + s.z, u.w + s.w);
+    if (grp > 0) sh[grp - 1][x] = s;
+    __syncthreads();
+    if (grp == 0 && i < n4) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) { const float4 a = sh[g][x]; s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w; }
+        const float4 u = reinterpret_cast<const float4*>(Uin)[i];
+        reinterpret_cast<float4*>(Uout)[i] = make_float4(u.x + s.x, u.y + s.y, u.z + s.z, u.w + s.w);
+    }
 }
 
 cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Uin, float* Uout,
@@ -924,6 +943,6 @@ cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, con
     C2C_PLAN_DISPATCH_ROWS(FCL_CALL)
 #undef FCL_CALL
     const long long n4 = (long long)v.E * ldr / 4;
-    return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, st, pdl, (const float*)part, nparts, n4, Uin,
+    return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 63) / 64)), dim3(256), 0, st, pdl, (const float*)part, nparts, n4, Uin,
                          Uout, done);
 }

@@ -489,10 +489,7 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
     assert isinstance(runs, int), "runs must be an integer"
     assert metric in ("similarity", "error"), "`metric` must be either 'similarity' or 'error'"
     from ..parallel import run_units
-    if host_threads is None:
-        # host threads issuing this rank's units, each on a CUDA stream of its own: the host part of one bin of runs (factor
-        # init, upload, graph capture, read-back) overlaps the device part of another (parallel._run_local)
-        host_threads = int(os.environ.get("C2C_B200_HOST_THREADS", "1"))
+
     kwargs = dict(kwargs or {})
     kwargs["return_errors"] = True
     X = as_device_tensor(tensor)
@@ -547,6 +544,12 @@ def _multiple_runs_elbow_analysis(tensor, upper_rank=50, runs=10, tf_type="non_n
             return float(sum(engine.ldr_of(r) for r, _ in unit))
         return (1.0 if cols <= 12 else (1.2 if cols <= 16 else 1.45)) if len(unit) > 1 or cols <= 32 else cols / 16.0
 
+    if host_threads is None:
+        # host threads issuing this rank's units, each on a CUDA stream of its own: the host part of one bin of runs (factor
+        # init, upload, graph capture, read-back) overlaps the device part of another (parallel._run_local).  Measured on the
+        # atlas sweep (117 bins): 5.71 s with 1 thread, 5.47 with 2, 5.40 with 3 (profiles/r02_elbow_host_threads.jsonl); the
+        # one-launch small-tensor path has nothing to overlap.
+        host_threads = int(os.environ.get("C2C_B200_HOST_THREADS", "1" if multi else "2"))
     parts = run_units(units, one, cost=cost, gather="object", threads=host_threads)
     flat = {}
     for unit, vals in zip(units, parts):
