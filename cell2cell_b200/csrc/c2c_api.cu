@@ -767,7 +767,14 @@ extern "C" int c2c_build_ccc(const float* expr, const int64_t* expr_off, const i
     // the reference would carry into the score (only complexes differ, but the flag is per launch).
     a.exact = agg_kind == C2C_AGG_MIN ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (K % 4 == 0) { if (a.exact) build_ccc_kernel<true, true><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a);
+    if (K % 4 == 0 && K <= 64 && a.exact && !env_int("C2C_B200_BUILD_GENERAL", 0)) {
+        // the common case: a branch-free quad of scores per thread (c2c_small.cuh)
+        const size_t smem_f = (size_t)C2C_BUILD_TILE * 2 * K * sizeof(float);
+        if (score_kind == 0)      build_ccc_fast_kernel<0><<<(int)grid, C2C_SMALL_THREADS, smem_f, st>>>(a);
+        else if (score_kind == 1) build_ccc_fast_kernel<1><<<(int)grid, C2C_SMALL_THREADS, smem_f, st>>>(a);
+        else                      build_ccc_fast_kernel<2><<<(int)grid, C2C_SMALL_THREADS, smem_f, st>>>(a);
+    }
+    else if (K % 4 == 0) { if (a.exact) build_ccc_kernel<true, true><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a);
                       else         build_ccc_kernel<true, false><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a); }
     else            { if (a.exact) build_ccc_kernel<false, true><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a);
                       else         build_ccc_kernel<false, false><<<(int)grid, C2C_SMALL_THREADS, smem, st>>>(a); }

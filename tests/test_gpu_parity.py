@@ -457,6 +457,70 @@ def test_full_size_properties(shape, rank):
     np.testing.assert_allclose(errs2, errs, rtol=1e-5)
 
 
+@pytest.mark.parametrize("K", [8, 40])
+@pytest.mark.parametrize("score", ["expression_product", "expression_mean", "expression_gmean"])
+def test_build_fast_kernel_equals_general_kernel_on_special_values(score, K):
+    """K % 4 == 0 with fp32 partner values takes build_ccc_fast (branch-free quads); the general kernel
+    (C2C_B200_BUILD_GENERAL=1) is the one the golden grid pinned in round 1.  Same bits -- scores and mask -- on values that
+    exercise every rare case: zeros, NaN (absent genes / cell types), infinities, subnormal / tiny / huge products, negative
+    values, two-subunit 'min' complexes, tiles that straddle contexts (L not a multiple of the 16-plane tile); and against
+    a float64 numpy statement of compute_ccc_matrix (communication_scores.py:195-203)."""
+    from cell2cell_b200 import engine
+    C, G, L = 3, 64, 100
+    rs = np.random.RandomState(5)
+    expr = rs.gamma(1.0, 2.0, size=(C, G, K)).astype(np.float32)
+    special = np.array([0.0, 0.0, 0.0, np.nan, np.inf, -np.inf, 1e-30, 3e-38, 1e-44, 1e-20, 1e20, 1e19, -1.5, -0.0, 1.0, 2.5e-16],
+                       dtype=np.float32)
+    pick = rs.rand(C, G, K) < 0.35
+    expr[pick] = special[rs.randint(0, len(special), size=int(pick.sum()))]
+    lig, rec, rec2 = rs.randint(0, G, size=L), rs.randint(0, G, size=L), rs.randint(0, G, size=L)
+    two = rs.rand(L) < 0.4                                           # receptor l is a two-subunit complex ('min')
+    cell_col = np.tile(np.arange(K, dtype=np.int32), (C, 1))
+    cell_col[1, 3] = -1                                              # a cell type absent from context 1
+    sub_rows, a_first, b_first, b_count = [], np.zeros(L, np.int32), np.zeros(L, np.int32), np.ones(L, np.int32)
+    for l in range(L):
+        a_first[l] = len(sub_rows); sub_rows.append(lig[l])
+        b_first[l] = len(sub_rows); sub_rows.append(rec[l])
+        if two[l]:
+            sub_rows.append(rec2[l]); b_count[l] = 2
+    a_count = np.ones((C, L), dtype=np.int32)
+    b_cnt = np.tile(b_count, (C, 1))
+    a_count[2, 5] = 0; b_cnt[2, 5] = 0                               # a gene absent from context 2
+    a_count[0, 7] = -1; b_cnt[0, 7] = -1                             # complexes with a missing subunit: zeros
+    args = (expr.reshape(-1), np.arange(C, dtype=np.int64) * G * K, np.full(C, K, np.int32), cell_col,
+            np.tile(a_first, C), a_count.reshape(-1), np.tile(b_first, C), b_cnt.reshape(-1), np.asarray(sub_rows, np.int32),
+            C, L, K, score, "min", True, torch.device("cuda", 0))
+    Xf, Mf = engine.build_ccc(*args)
+    os.environ["C2C_B200_BUILD_GENERAL"] = "1"
+    try:
+        Xg, Mg = engine.build_ccc(*args)
+    finally:
+        del os.environ["C2C_B200_BUILD_GENERAL"]
+    xf, xg = Xf.cpu().numpy(), Xg.cpu().numpy()
+    np.testing.assert_array_equal(Mf.cpu().numpy(), Mg.cpu().numpy())
+    np.testing.assert_array_equal(xf.view(np.uint32), xg.view(np.uint32))
+    # float64 statement of the reference's score on the same operands
+    e64 = expr.astype(np.float64)
+    with np.errstate(all="ignore"):
+        a = np.stack([e64[c][lig] for c in range(C)])
+        b = np.stack([np.where(two[:, None], np.fmin(e64[c][rec], e64[c][rec2]), e64[c][rec]) for c in range(C)])
+    for side in (a, b):
+        side[1, :, 3] = np.nan
+        side[2, 5] = np.nan
+        side[0, 7] = 0.0
+    with np.errstate(all="ignore"):
+        va, vb = a[:, :, :, None], b[:, :, None, :]
+        ref = va * vb if score == "expression_product" else ((va + vb) / 2.0 if score == "expression_mean" else np.sqrt(va * vb))
+    want_mask = (~np.isnan(ref)).astype(np.uint8)
+    np.testing.assert_array_equal(Mf.cpu().numpy(), want_mask)
+    fmax = float(np.finfo(np.float32).max)
+    with np.errstate(all="ignore"):
+        want = np.clip(np.nan_to_num(ref, nan=0.0, posinf=fmax, neginf=-fmax), -fmax, fmax).astype(np.float32)
+    ok = np.isfinite(want) & (want_mask == 1)
+    d = ulp_distance(np.abs(xf[ok]), np.abs(want[ok]))
+    assert d.max() <= 1, "max ulp distance %d" % d.max()
+
+
 def test_full_size_build_roundtrip():
     """Config 4 size build (60 x 2000 x 40 x 40): sampled planes against a numpy recomputation, mask all ones under 'outer'
     when nothing is missing, checksum stable across two builds."""
