@@ -735,6 +735,9 @@ static int check_common(const float* X, const float* const* A, int ndim, int ldr
     if (!A) return fail(-11, "A is NULL");
     for (int i = 0; i < ndim; ++i) if (!A[i]) return fail(-11, "A[%d] is NULL", i);
     if (ldr != ldr_of(rank)) return fail(-12, "ldr must be rank rounded up to a multiple of 4 (%d), got %d", ldr_of(rank), ldr);
+    // every entry point dispatches 128-bit loads / bulk copies / TMA on X and float4 loads on the packed factors
+    if (((uintptr_t)X & 15) != 0) return fail(-25, "X must be 16-byte aligned");
+    for (int i = 0; i < ndim; ++i) if (((uintptr_t)A[i] & 15) != 0) return fail(-25, "A[%d] must be 16-byte aligned", i);
     return 0;
 }
 

@@ -70,12 +70,16 @@ def unpack_factor(t, rank):
 def _check_tensor(X, mask):
     if not (isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()):
         raise C2CError("tensor must be a contiguous fp32 CUDA tensor")
+    if X.data_ptr() % 16 != 0:
+        raise C2CError("tensor storage must be 16-byte aligned (a view at an odd storage offset is not: use .clone())")
     if not 3 <= X.dim() <= MAX_NDIM:
         raise C2CError("tensor must have between 3 and %d dimensions, got %d" % (MAX_NDIM, X.dim()))
     if mask is not None:
         if not (isinstance(mask, torch.Tensor) and mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous()
                 and mask.shape == X.shape and mask.device == X.device):
             raise C2CError("mask must be a contiguous uint8 CUDA tensor of the tensor's shape on the same device")
+        if mask.data_ptr() % 4 != 0:
+            raise C2CError("mask storage must be 4-byte aligned (use .clone())")
 
 
 class Workspace:
@@ -107,6 +111,8 @@ def _ws_for(X, rank, mask, ws):
 
 def sumsq(X, ws=None):
     """sum(X**2) with fp64 accumulation (tensorly ``tl.norm(tensor, 2) ** 2``)."""
+    if not (isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float32 and X.is_contiguous() and X.data_ptr() % 16 == 0):
+        raise C2CError("tensor must be a contiguous, 16-byte aligned fp32 CUDA tensor")
     with torch.cuda.device(X.device):
         out = torch.zeros(1, dtype=torch.float64, device=X.device)
         scratch = torch.empty(1184 * 8, dtype=torch.uint8, device=X.device)

@@ -17,7 +17,7 @@ from collections import Counter, OrderedDict
 
 import numpy as np
 
-__all__ = ["complex_table", "ContextRows", "context_rows", "plain_rows", "select_elements", "ordered",
+__all__ = ["complex_table", "ContextRows", "context_rows", "context_tables", "plain_rows", "select_elements", "ordered",
            "filter_lr_pairs", "resolve", "group_rows"]
 
 ZERO_ROW = "zero"       # complex with a subunit missing from the context: a row of zeros (rnaseq.py:195)
@@ -103,6 +103,24 @@ def context_rows(index, complexes, upper_letter_comparison):
     return ContextRows(list(rows.keys()), rows)
 
 
+def context_tables(indexes, complexes, upper_letter_comparison, keep=8):
+    """``context_rows`` of every context; contexts whose indexes are equal (the usual case: one gene universe for every
+    sample) share ONE ``ContextRows`` object -- the name handling is 13 ms of Python per 4000-gene context otherwise."""
+    seen, tables = [], []
+    for idx in indexes:
+        hit = None
+        for prev, tab in seen:
+            if prev is idx or (len(prev) == len(idx) and prev.equals(idx)):
+                hit = tab
+                break
+        if hit is None:
+            hit = context_rows(list(idx), complexes, upper_letter_comparison)
+            seen.insert(0, (idx, hit))
+            del seen[keep:]
+        tables.append(hit)
+    return tables
+
+
 def select_elements(lists, outer, fraction):
     """``inner``: intersection; ``outer``: names present in at least ``fraction`` of the contexts
     (find_elements.py:32-76: abundance = count / n_contexts, kept when >= fraction)."""
@@ -169,7 +187,13 @@ def resolve(tables, columns, genes, cells, ligands, receptors):
     count_u = np.zeros((C, max(U, 1)), dtype=np.int32)
     sub_rows = []
     n_sub = 0
-    for c, tab in enumerate(tables):
+    done = {}                                              # contexts that share a ContextRows object (same index) share its
+    for c, tab in enumerate(tables):                       # first / count rows and its sub_rows (row numbers are per matrix)
+        prev = done.get(id(tab))
+        if prev is not None:
+            first_u[c], count_u[c] = first_u[prev], count_u[prev]
+            continue
+        done[id(tab)] = c
         for n, u in uniq.items():
             d = tab.rows.get(n)
             if d is None:

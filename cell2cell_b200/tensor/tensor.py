@@ -478,7 +478,7 @@ class InteractionTensor(BaseTensor):
         else:
             complexes = None
             complex_agg_method = "min"
-        tables = [bi.context_rows(list(df.index), complexes, upper_letter_comparison) for df in rnaseq_matrices]
+        tables = bi.context_tables([df.index for df in rnaseq_matrices], complexes, upper_letter_comparison)
         if verbose:
             print("Building tensor for the provided context")
         tensor, genes, cells, ppi_names, mask = _build(tables, rnaseq_matrices, ppi_data, how, outer_fraction,

@@ -84,3 +84,31 @@ def test_lpt_and_groups():
     ppi = pd.DataFrame({"A": list("abcd"), "B": list("efgh"), "g": ["y", "x", "y", "x"]})
     keys, off, rows = bi.group_rows(ppi, "g")
     assert keys == ["x", "y"] and off.tolist() == [0, 2, 4] and rows.tolist() == [1, 3, 0, 2]
+
+
+def test_context_tables_share_the_descriptor_of_equal_indexes():
+    """Contexts with equal gene indexes share ONE ContextRows (and, in ``resolve``, one set of first / count rows and
+    sub_rows): same index arrays, hence the same tensor, as resolving every context on its own."""
+    mats, ppi = hard_case(3)
+    mats = list(mats) + [mats[0].copy(), mats[1].iloc[::-1].copy(), mats[0].copy()]       # equal, permuted (not equal), equal
+    complexes = bi.complex_table(ppi, "&", ("A", "B"))[4]
+    shared = bi.context_tables([df.index for df in mats], complexes, True)
+    each = [bi.context_rows(list(df.index), complexes, True) for df in mats]
+    n0 = len(mats) - 3
+    assert shared[n0] is shared[0] and shared[n0 + 2] is shared[0] and shared[n0 + 1] is not shared[1]
+    for a, b in zip(shared, each):
+        assert a.names == b.names and dict(a.rows) == dict(b.rows)
+    names = [t.names for t in each]
+    columns = [list(df.columns) for df in mats]
+    genes = bi.ordered(names[0], bi.select_elements(names, True, 0.0))
+    cells = bi.ordered(columns[0], bi.select_elements(columns, True, 0.0))
+    f = bi.filter_lr_pairs(ppi, genes, "&", True, ("A", "B"))
+    lig, rec = f["A"].tolist(), f["B"].tolist()
+    ia = bi.resolve(shared, columns, genes, cells, lig, rec)
+    ib = bi.resolve(each, columns, genes, cells, lig, rec)
+    vals = [df.values for df in mats]
+    Xa = emulate_build(vals, ia, len(mats), len(lig), len(cells), "expression_gmean", "min")
+    Xb = emulate_build(vals, ib, len(mats), len(lig), len(cells), "expression_gmean", "min")
+    np.testing.assert_array_equal(np.isnan(Xa), np.isnan(Xb))
+    np.testing.assert_array_equal(np.nan_to_num(Xa), np.nan_to_num(Xb))
+    assert len(ia["sub_rows"]) < len(ib["sub_rows"])
