@@ -289,7 +289,6 @@ trail_update_kernel(const TrailUpdArgs a)
             float nv = sA[t] * fmaxf(m, a.eps) / fmaxf(den, a.eps);
             if (a.run_flags != nullptr && a.run_flags[a.run_of[r & 31]]) nv = sA[t];          // this run has stopped
             ip += (double)m * (double)nv;
-            if (a.nruns > 1 && which == 1) atomicAdd(&s_ip[a.run_of[r & 31]], (double)m * (double)nv);
             gA[(size_t)i * ldr + r] = nv;
             nv_keep[nk & 1] = nv;
         }
@@ -298,6 +297,25 @@ trail_update_kernel(const TrailUpdArgs a)
         for (int t = threadIdx.x; t < I * R; t += blockDim.x, ++nk) sA[t] = nv_keep[nk & 1];
         if (which == 1) iprod = ip;
         __syncthreads();
+        if (a.nruns > 1 && which == 1) {
+            // batched runs: <M, A_new> per run, in a fixed order (was: one shared-memory fp64 atomicAdd -- a CAS loop -- per
+            // factor entry onto a handful of addresses: 86 us of a 28-column bin's iteration).  Column sums by warp w for the
+            // columns w, w + nwarps, ... (lanes stride the rows, fixed shuffle tree), then one thread per run adds its columns.
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+            for (int r = warp; r < R; r += nwarps) {
+                double v = 0.0;
+                for (int i = lane; i < I; i += 32) v += (double)sM[i * R + r] * (double)sA[i * R + r];
+                v = warp_sum(v);
+                if (lane == 0) red[r] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < a.nruns) {
+                double sum = 0.0;
+                for (int r = 0; r < R; ++r) if (a.run_of[r & 31] == threadIdx.x) sum += red[r];
+                s_ip[threadIdx.x] = sum;
+            }
+            __syncthreads();
+        }
         // Gram of the new factor (fp64), to shared memory and to the new bank
         for (int t = threadIdx.x; t < RR; t += blockDim.x) {
             const int q = t / R, r = t - q * R;
@@ -319,13 +337,25 @@ trail_update_kernel(const TrailUpdArgs a)
     // reconstruction error (Gram form), stop rule, iteration counter
     if (a.nruns > 1) {
         // batched runs: one error / stop decision per run
-        for (int pr = threadIdx.x; pr < RR; pr += blockDim.x) {
-            const int q = pr / R, r = pr - q * R;
-            if (a.run_of[q & 31] == a.run_of[r & 31]) {
-                double g = 1.0;
-                for (int j = 0; j < N; ++j) g *= sS[(size_t)j * RR + pr];
-                atomicAdd(&s_rn[a.run_of[q & 31]], g);
+        // ||rec||^2 per run = sum over the run's own R_b x R_b block of the Hadamard product of the Grams, in a fixed order:
+        // thread q sums row q over the columns of its run, then one thread per run adds its rows
+        if (threadIdx.x < R) {
+            const int q = threadIdx.x;
+            double rowsum = 0.0;
+            for (int r = 0; r < R; ++r) {
+                if (a.run_of[q & 31] == a.run_of[r & 31]) {
+                    double g = 1.0;
+                    for (int j = 0; j < N; ++j) g *= sS[(size_t)j * RR + q * R + r];
+                    rowsum += g;
+                }
             }
+            red[q] = rowsum;
+        }
+        __syncthreads();
+        if (threadIdx.x < a.nruns) {
+            double sum = 0.0;
+            for (int q = 0; q < R; ++q) if (a.run_of[q & 31] == threadIdx.x) sum += red[q];
+            s_rn[threadIdx.x] = sum;
         }
         __syncthreads();
         const int it = a.state[0];
