@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #define C2C_VERSION 100
@@ -64,6 +65,37 @@ static std::atomic<long long> g_launches{0};
 extern "C" int c2c_version(void) { return C2C_VERSION; }
 extern "C" const char* c2c_last_error(void) { return g_err; }
 extern "C" long long c2c_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Executable graphs whose launches may still be in flight when the run that enqueued them returns (a run that is never polled
+// -- check_every <= 0 -- does not wait for the device any more: the host part of the NEXT run, its capture and instantiation,
+// then overlaps this run's iterations).  An exec object must outlive its launches, so it is parked here with an event
+// recorded after its last launch and destroyed by a later call once that event has completed.
+struct PendingGraph { cudaGraphExec_t exec; cudaGraph_t graph; cudaEvent_t done; int device; };
+static std::mutex g_pending_mu;
+static std::vector<PendingGraph> g_pending;
+
+static void reap_pending_graphs(bool wait)
+{
+    std::lock_guard<std::mutex> lock(g_pending_mu);
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    size_t keep = 0;
+    for (size_t i = 0; i < g_pending.size(); ++i) {
+        PendingGraph& p = g_pending[i];
+        bool finished = false;
+        if (p.device == dev) {
+            const cudaError_t q = wait ? cudaEventSynchronize(p.done) : cudaEventQuery(p.done);
+            if (q == cudaSuccess) finished = true;
+            else if (q != cudaErrorNotReady) { (void)cudaGetLastError(); finished = true; }   // a failed context: nothing left to protect
+        }
+        if (finished) { cudaGraphExecDestroy(p.exec); cudaGraphDestroy(p.graph); cudaEventDestroy(p.done); }
+        else g_pending[keep++] = p;
+    }
+    g_pending.resize(keep);
+}
+
+// waits for and releases every parked graph of the current device (tests / orderly shutdown; never required for correctness)
+extern "C" int c2c_release_pending(void) { reap_pending_graphs(true); return 0; }
 
 static int sm_count()
 {
@@ -1567,6 +1599,7 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
 
+    reap_pending_graphs(false);
     // `unroll` iterations are captured once and replayed: ~6 launches per iteration become a fraction of a graph launch, and
     // the dependent launches also link one iteration to the next
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
@@ -1619,10 +1652,25 @@ static int ncp_run_impl(const float* X, const uint8_t* mask, int ndim, const int
         }
     }
     if (use_graph) {
-        // the exec object must outlive its in-flight launches
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
-        if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+        // the exec object must outlive its in-flight launches: a run that was never polled parks it (see PendingGraph) and
+        // returns without waiting for the device; a polled run has synchronised anyway
+        bool parked = false;
+        if (rc == 0 && check_every <= 0) {
+            PendingGraph p; p.exec = exec; p.graph = graph; p.done = nullptr; p.device = -1;
+            if (cudaGetDevice(&p.device) == cudaSuccess && cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming) == cudaSuccess) {
+                if (cudaEventRecord(p.done, st) == cudaSuccess) {
+                    std::lock_guard<std::mutex> lock(g_pending_mu);
+                    g_pending.push_back(p);
+                    parked = true;
+                } else cudaEventDestroy(p.done);
+            }
+            if (!parked) (void)cudaGetLastError();
+        }
+        if (!parked) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+            if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "synchronize after graph replay");
+        }
     }
     return rc;
 }

@@ -387,6 +387,8 @@ def ncp_run(X, mask, factors, rank, tf_type="non_negative_cp", n_iter_max=100, t
     for f, s in zip(factors, X.shape):
         if f.shape != (s, ldr_of(rank)) or f.dtype != torch.float32 or not f.is_contiguous() or f.device != X.device:
             raise C2CError("factors must be packed fp32 [I_n, ldr] tensors on the tensor's device (pack_factor)")
+    if tol < 0 and cvg_criterion == "abs_rec_error":
+        check_every = 0             # |err[-2] - err[-1]| < tol never holds: nothing to poll, the run is only enqueued
     with torch.cuda.device(X.device):
         ws = _ws_for(X, rank, mask, ws)
         errors = torch.zeros(max(int(n_iter_max), 1), dtype=torch.float64, device=X.device)
@@ -434,6 +436,8 @@ def ncp_run_batched(X, factors, run_ranks, n_iter_max=100, tol=1e-6, cvg_criteri
     for f, s in zip(factors, X.shape):
         if f.shape != (s, ldr_of(rank)) or f.dtype != torch.float32 or not f.is_contiguous() or f.device != X.device:
             raise C2CError("factors must be packed fp32 [I_n, ldr] tensors on the tensor's device (pack_factor)")
+    if tol < 0 and cvg_criterion == "abs_rec_error":
+        check_every = 0
     with torch.cuda.device(X.device):
         ws = _ws_for(X, rank, None, ws)
         n_it = max(int(n_iter_max), 1)

@@ -48,6 +48,10 @@ int c2c_version(void);
 const char* c2c_last_error(void);
 /* kernels this library has enqueued so far in the process (graph replays count every kernel they run) */
 long long c2c_launch_count(void);
+/* A factorization run that is never polled (check_every <= 0) returns once its iterations are ENQUEUED on `stream`: results
+ * (factors, errors, state) are ordered after it on that stream, as for any asynchronous CUDA call.  The CUDA-graph objects of
+ * such runs are parked and released by later calls; this waits for and releases those of the current device (optional). */
+int c2c_release_pending(void);
 /* Smallest rank whose two streaming passes run on the tensor pipe (TMA + tcgen05.mma kind::tf32, three-term split for
  * fp32 accuracy) instead of the FFMA kernels; below it the contraction is cheap enough for the CUDA cores to hide under
  * the HBM stream.  Returns the previous value; a value > 32 turns the tensor-pipe path off.  No counterpart in the
