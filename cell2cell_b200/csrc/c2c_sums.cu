@@ -17,13 +17,15 @@ template <int NQ, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS, 1)
 recon_sums_stream_kernel(const float* __restrict__ X, const LeadInfo lead, const float* __restrict__ A2,
                          const float* __restrict__ A3, long long P, int I2, int I3, int R, int ldr, int nquads, int nslots,
-                         double* __restrict__ sums_part)
+                         int nq_total, double* __restrict__ sums_part)
 {
     extern __shared__ __align__(16) float sW[];                      // [2][nslots * U][NQ]
     __shared__ double red[4][THREADS / 32];
     const int t = threadIdx.x;
-    const int slot = t / nquads, pos = t - slot * nquads;
-    const bool on = slot < nslots;
+    // blockIdx.y = part of the plane's float4 positions this CTA owns (planes with more positions than a CTA has threads are
+    // split over gridDim.y CTAs, each reading only its share of every plane): positions [blockIdx.y * nquads, ... + nquads)
+    const int slot = t / nquads, pos = blockIdx.y * nquads + (t - slot * nquads);
+    const bool on = slot < nslots && pos < nq_total;
     const int k4 = I3 >> 2;
     const int s = pos / k4, v0 = (pos - s * k4) << 2;
     const size_t E = (size_t)I2 * I3;
@@ -102,17 +104,22 @@ recon_sums_stream_kernel(const float* __restrict__ X, const LeadInfo lead, const
         if ((t & 31) == 0) red[k][t >> 5] = wsum;
     }
     __syncthreads();
+    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
     if (t < 4) {
         double tot = 0.0;
         for (int w = 0; w < THREADS / 32; ++w) tot += red[t][w];
-        sums_part[(size_t)blockIdx.x * 5 + t] = tot;
+        sums_part[blk * 5 + t] = tot;
     }
-    if (t == 4) sums_part[(size_t)blockIdx.x * 5 + 4] = blockIdx.x == 0 ? (double)P * (double)E : 0.0;
+    if (t == 4) sums_part[blk * 5 + 4] = blk == 0 ? (double)P * (double)E : 0.0;
 }
 
 template <int NQ, int THREADS, int U>
-static cudaError_t launch_one(const ContractArgs& a, int nquads, int grid_max, cudaStream_t st, int* grid_out)
+static cudaError_t launch_one(const ContractArgs& a, int nq_total, int grid_max, cudaStream_t st, int* grid_out)
 {
+    const int nparts = (nq_total + THREADS - 1) / THREADS;           // CTAs sharing a plane
+    const int nquads = (nq_total + nparts - 1) / nparts;             // positions per CTA
+    grid_max /= nparts;
+    if (grid_max < 1) return cudaErrorNotSupported;
     int nslots_max = THREADS / nquads;
     const int smem_cap = (int)((48 * 1024) / (2 * U * NQ * sizeof(float)));     // both W buffers within 48 KB
     if (nslots_max > smem_cap) nslots_max = smem_cap;
@@ -126,9 +133,9 @@ static cudaError_t launch_one(const ContractArgs& a, int nquads, int grid_max, c
     if (grid > grid_max) grid = grid_max;
     const size_t smem = 2 * (size_t)batch * NQ * sizeof(float);
     if (smem > 48 * 1024) return cudaErrorNotSupported;
-    recon_sums_stream_kernel<NQ, THREADS, U><<<(unsigned)grid, THREADS, smem, st>>>(a.X, a.lead, a.A2, a.A3, a.P, a.I2, a.I3, a.R,
-                                                                               a.ldr, nquads, (int)nslots, a.sums);
-    *grid_out = (int)grid;
+    recon_sums_stream_kernel<NQ, THREADS, U><<<dim3((unsigned)grid, (unsigned)nparts), THREADS, smem, st>>>(
+        a.X, a.lead, a.A2, a.A3, a.P, a.I2, a.I3, a.R, a.ldr, nquads, (int)nslots, nq_total, a.sums);
+    *grid_out = (int)grid * nparts;
     return cudaGetLastError();
 }
 
@@ -139,15 +146,14 @@ cudaError_t c2c_launch_sums_stream(const ContractArgs& a, int grid_max, cudaStre
     if (((uintptr_t)a.X & 15) != 0) return cudaErrorNotSupported;
     const long long nq = (long long)a.I2 * (a.I3 >> 2);
     const int nq4 = (a.R + 3) / 4;
+    if (nq > 8 * 512) return cudaErrorNotSupported;                   // at most 8 CTAs per plane (in-plane size <= 128 x 128)
     if (nq4 <= 3) {
-        if (nq > 512) return cudaErrorNotSupported;
         switch (nq4) {
             case 1: return launch_one<4, 512, 8>(a, (int)nq, grid_max, st, grid_out);
             case 2: return launch_one<8, 512, 8>(a, (int)nq, grid_max, st, grid_out);
             default: return launch_one<12, 512, 6>(a, (int)nq, grid_max, st, grid_out);
         }
     }
-    if (nq > 256) return cudaErrorNotSupported;
     switch (nq4) {
         case 4: return launch_one<16, 256, 8>(a, (int)nq, grid_max, st, grid_out);
         case 5: return launch_one<20, 256, 8>(a, (int)nq, grid_max, st, grid_out);

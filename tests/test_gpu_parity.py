@@ -216,7 +216,9 @@ def test_small_steps_match_numpy():
         assert rel_err(a[:, :rank].cpu().numpy(), b) < 1e-6
 
 
-@pytest.mark.parametrize("shape,rank", [((4, 30, 6, 6), 4), ((5, 11, 17, 17), 10), ((2, 3, 4, 8, 4), 3), ((6, 9, 8, 12), 40)])
+@pytest.mark.parametrize("shape,rank", [((4, 30, 6, 6), 4), ((5, 11, 17, 17), 10), ((2, 3, 4, 8, 4), 3), ((6, 9, 8, 12), 40),
+                                        # planes split over 2 / 2 / 3 CTAs of the streaming kernel (positions > threads per CTA)
+                                        ((3, 50, 40, 40), 20), ((2, 37, 48, 48), 10), ((2, 21, 44, 60), 32)])
 @pytest.mark.parametrize("masked", [False, True])
 def test_recon_sums_and_sumsq(shape, rank, masked):
     from cell2cell_b200 import engine
