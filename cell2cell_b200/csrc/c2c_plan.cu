@@ -5,6 +5,7 @@
 // All of them are exact restatements of tensorly's imputation `tensor*mask + cp_to_tensor(cp, mask=1-mask)` followed by
 // unfolding_dot_khatri_rao (cell2cell/tensor/coupled_factorization.py:342-345): the same products, summed in another order.
 #include "c2c_plan.cuh"
+#include <cstdlib>
 
 static inline size_t plan_align(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -911,6 +912,11 @@ cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, con
     if (per_sm > 2) per_sm = 2;
     if (per_sm < 1) per_sm = 1;
     const int resident = nsm * per_sm;
+    {   // C2C_B200_PLAN_MAX_PARTS: fewer chunk ranges than chunks, so that a CTA walks several chunks (tests of that path;
+        // it is otherwise only taken beyond ~300 k planes)
+        const char* e = getenv("C2C_B200_PLAN_MAX_PARTS");
+        if (e && atoi(e) > 0 && atoi(e) < max_parts) max_parts = atoi(e);
+    }
     int nparts = v.nchunks < max_parts ? v.nchunks : max_parts;       // chunk ranges (= partials)
     if (nparts > resident) nparts = resident;
     if (nparts < 1) nparts = 1;

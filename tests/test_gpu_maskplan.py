@@ -120,3 +120,27 @@ def test_masked_stop_rule_with_plan():
     got, got_err = non_negative_parafac(xz, rank, n_iter_max=200, init="random", tol=1e-5, random_state=3, mask=mask,
                                         return_errors=True)
     assert abs(len(got_err) - len(ref_err)) <= 2
+
+
+@pytest.mark.parametrize("max_parts", ["1", "3"])
+def test_position_lists_walked_several_chunks_per_cta(max_parts, monkeypatch):
+    """Beyond ~300 k planes a CTA of the position-side correction walks several 1024-plane chunks and accumulates into its
+    partial (same lane, fixed order).  C2C_B200_PLAN_MAX_PARTS forces that path on a 7-chunk tensor."""
+    from cell2cell_b200 import engine
+    shape, rank = (7, 1000, 8, 8), 10
+    mask = make_mask(shape, "random", seed=11)
+    x = lowrank(shape, 3, seed=1) * mask
+    rs = np.random.RandomState(5)
+    fs = [rs.random_sample((s, rank)) for s in shape]
+    X, M = torch.as_tensor(x).cuda(), torch.as_tensor(mask).cuda()
+    A = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in fs]
+    plan = engine.MaskPlan(X, M)
+    ref = engine.masked_contract_planned(X, M, A, rank, 1, plan=plan).cpu().numpy()
+    monkeypatch.setenv("C2C_B200_PLAN_MAX_PARTS", max_parts)
+    got = engine.masked_contract_planned(X, M, A, rank, 1, plan=plan).cpu().numpy()
+    assert rel_err(got, ref) < 1e-6, rel_err(got, ref)
+    f32 = [f.astype(np.float32).astype(np.float64) for f in fs]
+    W, B = khatri_rao_rows(f32[:-2]), khatri_rao_rows(f32[-2:])
+    m2 = mask.reshape(W.shape[0], B.shape[0]).astype(np.float64)
+    ximp = x.reshape(m2.shape).astype(np.float64) * m2 + (W @ B.T) * (1 - m2)
+    assert rel_err(got[:, :rank], ximp.T @ W) < 2e-6
