@@ -830,13 +830,6 @@ corr_rows_kernel(const PlanView v, const float* __restrict__ Wmat, const float* 
     }
 }
 
-#define C2C_PLAN_DISPATCH_ROWS(CALL)                                                                                     \
-    switch (ldr) {                                                                                                       \
-        case 4: CALL(4); break; case 8: CALL(8); break; case 12: CALL(12); break; case 16: CALL(16); break;              \
-        case 20: CALL(20); break; case 24: CALL(24); break; case 28: CALL(28); break; case 32: CALL(32); break;          \
-        default: return cudaErrorNotSupported;                                                                           \
-    }
-
 cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const float* Wmat, const float* Bmat, const float* Tin, float* Tout,
                                        int ldr, const int* done, int nsm, cudaStream_t st, int pdl)
 {
@@ -859,7 +852,7 @@ cudaError_t c2c_launch_plane_corr_list(const PlanView& v, const float* Wmat, con
             e_ = c2c_launch_ex(corr_rows_kernel<N, 0, false>, dim3((unsigned)grid), dim3(block), 0, st, pdl, v, Wmat, Bmat, Tin, Tout, 0, 0, done); \
         if (e_ != cudaSuccess) return e_;                                                                                \
     } while (0)
-    C2C_PLAN_DISPATCH_ROWS(PCL_CALL)
+    C2C_PLAN_DISPATCH(PCL_CALL)
 #undef PCL_CALL
     return cudaSuccess;
 }
@@ -946,7 +939,7 @@ cudaError_t c2c_launch_fiber_corr_list(const PlanView& v, const float* Wmat, con
         e_ = c2c_launch_ex(corr_rows_kernel<N, 1, true>, grid, dim3(block), tbytes, st, pdl, v, Wmat, Bmat, (const float*)nullptr, part, epi, cpj, done); \
         if (e_ != cudaSuccess) return e_;                                                                                \
     } while (0)
-    C2C_PLAN_DISPATCH_ROWS(FCL_CALL)
+    C2C_PLAN_DISPATCH(FCL_CALL)
 #undef FCL_CALL
     const long long n4 = (long long)v.E * ldr / 4;
     return c2c_launch_ex(plan_reduce_kernel, dim3((unsigned)((n4 + 63) / 64)), dim3(256), 0, st, pdl, (const float*)part, nparts, n4, Uin,
