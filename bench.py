@@ -514,13 +514,19 @@ def run_ours(args, rank_id, local_rank, world):
         U20 = torch.empty((shape[-2] * shape[-1], 20), dtype=torch.float32, device=dev)
         tp20 = time_kernel(lambda: engine.plane_contract(X, None, f20, 20, ws=ws20, out=T20), 20)
         tf20 = time_kernel(lambda: engine.fiber_contract(X, None, f20, 20, ws=ws20, out=U20), 20)
+        call_ms = {"plane_contract_ms": tp20 * 1e3, "fiber_contract_ms": tf20 * 1e3}
+        try:                                           # the tensor-pipe kernels alone (no memset / reduction / copy around them)
+            tp20 = engine.time_pass_kernel(X, f20, 20, 0, reps=20, ws=ws20)[0] * 1e-3
+            tf20 = engine.time_pass_kernel(X, f20, 20, 1, reps=20, ws=ws20)[0] * 1e-3
+        except Exception:                              # noqa: BLE001
+            pass
         med = float(np.median(t20))
         pk = peaks()[0]
         r20 = {"rank": 20, "iterations_per_s_per_gpu": iters / med, "calls": [round(iters / t, 1) for t in t20],
                "passes": "plane_mma / fiber_mma (TMA + tcgen05.mma kind::tf32, 3-term split)",
                "roofline": {"bound": "hbm", "kernel": "fiber_mma<32>", "achieved": n_x * 4 / tf20 / 1e9, "peak": pk, "unit": "GB/s",
                             "frac": n_x * 4 / tf20 / 1e9 / pk, "plane_mma_ms": tp20 * 1e3, "fiber_mma_ms": tf20 * 1e3,
-                            "plane_mma_frac": n_x * 4 / tp20 / 1e9 / pk,
+                            "plane_mma_frac": n_x * 4 / tp20 / 1e9 / pk, "whole_calls": call_ms,
                             "iteration_frac_of_2_pass_traffic": 2 * n_x * 4 * iters / med / 1e9 / pk}}
         del ws20, f20, T20, U20
 
@@ -576,6 +582,14 @@ def run_ours(args, rank_id, local_rank, world):
     reps = 20 if n_x * 4 > 256e6 else 200
     t_plane = time_kernel(lambda: engine.plane_contract(X, None, f, rank, ws=ws, out=T), reps)
     t_fiber = time_kernel(lambda: engine.fiber_contract(X, None, f, rank, ws=ws, out=U), reps)
+    # the streaming kernels ALONE (the API calls above also run a tail kernel, the reduction of the partials and a copy):
+    # average launch duration over back-to-back launches, CUDA events on the launching stream inside the library
+    try:
+        k_plane = engine.time_pass_kernel(X, f, rank, 0, reps=reps, ws=ws)
+        k_fiber = engine.time_pass_kernel(X, f, rank, 1, reps=reps, ws=ws)
+        k_plane, k_fiber = (k_plane[0] * 1e-3, k_plane[1]), (k_fiber[0] * 1e-3, k_fiber[1])
+    except Exception:                                  # noqa: BLE001 -- shape outside the streaming kernels: whole-call timings
+        k_plane, k_fiber = (t_plane, "plane_contract (whole call)"), (t_fiber, "fiber_contract (whole call)")
 
     times = torch.tensor([sec, e2e_sec], dtype=torch.float64, device=dev)
     my_clk = clk.summary()
@@ -591,8 +605,9 @@ def run_ours(args, rank_id, local_rank, world):
     peak, peak_kind = peaks()
     total_iters = world * args.steps * iters
     value = total_iters / sec
-    worst = max(t_plane, t_fiber)
-    name = "plane_stream" if t_plane >= t_fiber else "fiber_stream"
+    # the dominant kernel of the step = the streaming kernel with the longer launch (largest share of the timed region: the
+    # committed ncu launch list shows the same order)
+    worst, name = max(k_plane, k_fiber)
     line = {
         "metric": METRIC if args.workload == "atlas" else "NCP iterations/s", "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
@@ -614,8 +629,14 @@ def run_ours(args, rank_id, local_rank, world):
         "per_gpu_ms_per_step": [round(1e3 * float(v) / args.steps, 3) for v in per_rank],
         "roofline": {"bound": "hbm", "kernel": name, "achieved": n_x * 4 / worst / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": n_x * 4 / worst / 1e9 / peak, "traffic": ncu_traffic(name), "peak_kind": "of " + peak_kind,
+                     "kernels": {k_plane[1]: {"ms": k_plane[0] * 1e3, "gbs": n_x * 4 / k_plane[0] / 1e9, "frac": n_x * 4 / k_plane[0] / 1e9 / peak},
+                                 k_fiber[1]: {"ms": k_fiber[0] * 1e3, "gbs": n_x * 4 / k_fiber[0] / 1e9, "frac": n_x * 4 / k_fiber[0] / 1e9 / peak},
+                                 "note": "average launch duration of the kernel alone, back-to-back launches, CUDA events on the "
+                                         "launching stream (c2c_time_pass_kernel)"},
                      "plane_contract_ms": t_plane * 1e3, "fiber_contract_ms": t_fiber * 1e3,
                      "plane_contract_gbs": n_x * 4 / t_plane / 1e9, "fiber_contract_gbs": n_x * 4 / t_fiber / 1e9,
+                     "whole_call_note": "plane_contract / fiber_contract = the C-ABI call: streaming kernel + tail kernel + "
+                                        "fixed-order reduction of the partials + a copy",
                      "iteration": {"passes_made": 2, "bytes_moved": 2 * n_x * 4,
                                    "achieved_gbs": 2 * n_x * 4 * value / world / 1e9,
                                    "frac": 2 * n_x * 4 * value / world / 1e9 / peak,

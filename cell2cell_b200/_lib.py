@@ -36,6 +36,7 @@ SIGNATURES = {
     "c2c_last_error": (_c.c_char_p, []),
     "c2c_launch_count": (_c.c_longlong, []),
     "c2c_release_pending": (_i, []),
+    "c2c_time_pass_kernel": (_i, [_p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _i, _i, _c.POINTER(_c.c_float), _c.POINTER(_i), _p, _sz, _p]),
     "c2c_set_mma_min_rank": (_i, [_i]),
     "c2c_plane_contract": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),
     "c2c_fiber_contract": (_i, [_p, _p, _i, _c.POINTER(_i64), _c.POINTER(_p), _i, _i, _p, _p, _sz, _p]),

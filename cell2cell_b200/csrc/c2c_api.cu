@@ -547,8 +547,10 @@ struct PassOpts {
     long long zero_n;
     const XgComm* xg;          // context-sharded run: the partial U is summed over the ranks inside the reduce kernel (c2c_xgpu.cuh)
     double* xg_S; const int* xg_state; int xg_N;
+    bool main_only;            // c2c_time_pass_kernel: only the streaming kernel itself (no memset, tail, reduce); -60 if the
+                               // shape takes the register-staged kernels
 };
-static const PassOpts kPlainPass = {0, false, nullptr, 0, nullptr, nullptr, nullptr, 0};
+static const PassOpts kPlainPass = {0, false, nullptr, 0, nullptr, nullptr, nullptr, 0, false};
 static int use_pdl() { static int v = -1; if (v < 0) v = env_int("C2C_B200_NO_PDL", 0) ? 0 : 1; return v; }
 
 // T[P x ldr] = plane contraction of Xh with the two trailing factors
@@ -562,7 +564,7 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
         memset(&pa, 0, sizeof(pa));
         pa.P = g.P; pa.E = (int)g.E; pa.I2 = g.I2; pa.I3 = g.I3; pa.R = a.R; pa.ldr = a.ldr; pa.A2 = a.A2; pa.A3 = a.A3; pa.T = T;
         pa.done = a.done; pa.nkb = g.pm_nkb; pa.ntiles = g.pm_ntiles; pa.nx = g.pm_nstages; pa.dbg = mma_dbg();
-        if (!po.t_zeroed) CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
+        if (!po.t_zeroed && !po.main_only) CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
         const cudaError_t e = c2c_launch_plane_mma(g.mma_n, map, pa, g.pm_grid, g.pm_smem, st, po.t_zeroed ? po.pdl : 0);
         if (e != cudaSuccess) return cuda_fail(e, "plane_mma launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -581,8 +583,9 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
         if (e != cudaSuccess) return cuda_fail(e, "plane_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         a.p0 = g.ps_nstage * g.ps_spw;                 // the tail (< one stage of planes) goes to the register-staged kernel
-        if (a.p0 >= g.P) return 0;
+        if (a.p0 >= g.P || po.main_only) return 0;
     }
+    if (po.main_only) return fail(-60, "this shape / rank takes the register-staged plane kernel");
     const int vec = g.vec_plane;
     const size_t smem = ((size_t)g.I2 * 4 * g.np2 + (size_t)g.I3 * 2 * g.np2) * sizeof(float);
     int grid = plane_grid(g, vec);
@@ -630,6 +633,7 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
         g_launches.fetch_add(1, std::memory_order_relaxed);
         nparts = g.fm_nj;
         legacy = false;
+        if (po.main_only) return 0;
     } else if (!masked && g.fs_ok) {
         StreamArgs sa;
         memset(&sa, 0, sizeof(sa));
@@ -641,6 +645,7 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
                                        : c2c_launch_fiber_stream_v1_s1(g.np2, sa, g.fs_nthr, g.fs_nslots, g.fs_merge, g.fs_wall, g.fs_grid, block, g.fs_smem, st, po.pdl);
         if (e != cudaSuccess) return cuda_fail(e, "fiber_stream launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (po.main_only) return 0;
         nparts = (long long)g.fs_grid * (g.fs_merge ? 1 : g.fs_nslots);
         a.p0 = g.fs_nstage * g.fs_tp;
         legacy = a.p0 < g.P;
@@ -651,6 +656,7 @@ static int launch_fiber(const Geo& g, ContractArgs a, bool masked, const Ws& w, 
             nparts += g.fc_nslots;
         }
     }
+    if (po.main_only) return fail(-60, "this shape / rank takes the register-staged fiber kernel");
     if (legacy) {
         if (masked) {
             const long long n = g.E * a.ldr;
@@ -968,6 +974,44 @@ extern "C" int c2c_fiber_contract(const float* X, const uint8_t* mask, int ndim,
     if ((rc = maybe_impute(g, a, masked, w, (cudaStream_t)stream)) != 0) return rc;
     if ((rc = launch_fiber(g, a, masked, w, (cudaStream_t)stream)) != 0) return rc;
     CK(cudaMemcpyAsync(U, w.U, (size_t)g.E * ldr * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream), "copy U");
+    return 0;
+}
+
+// Measurement aid (bench.py roofline): average duration of the streaming kernel of one pass ALONE -- plane_stream / plane_mma
+// (which = 0) or fiber_stream / fiber_mma (which = 1) -- over `reps` back-to-back launches, CUDA events on the launching stream.
+// The API calls above add a memset, a tail kernel, the partial reduction and a copy around it.  *kind: 0 FFMA kernel, 1 tensor pipe.
+extern "C" int c2c_time_pass_kernel(const float* X, int ndim, const int64_t* shape, const float* const* A, int ldr, int rank,
+                                    int which, int reps, float* ms_out, int* kind, void* ws, size_t ws_bytes, void* stream)
+{
+    Geo g; int rc;
+    if (!shape) return fail(-1, "shape is NULL");
+    if ((rc = make_geo(g, ndim, shape, rank)) != 0) return rc;
+    if ((rc = check_common(X, A, ndim, ldr, rank)) != 0) return rc;
+    if (!ms_out || reps < 1 || (which != 0 && which != 1)) return fail(-14, "ms_out is NULL, reps < 1 or which not in {0, 1}");
+    Ws w;
+    if ((rc = get_ws(w, g, rank, 0, ws, ws_bytes)) != 0) return rc;
+    ContractArgs a = base_args(g, X, nullptr, A, ldr, rank, nullptr);
+    PassOpts po = kPlainPass;
+    po.main_only = true; po.t_zeroed = true;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CK(cudaEventCreate(&e0), "event create");
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return cuda_fail(cudaGetLastError(), "event create"); }
+    rc = 0;
+    for (int i = -1; i < reps && rc == 0; ++i) {                        // i = -1: warm-up launch
+        if (i == 0) cudaEventRecord(e0, st);
+        rc = which == 0 ? launch_plane(g, a, false, w.T, st, po) : launch_fiber(g, a, false, w, st, po);
+    }
+    float ms = 0.0f;
+    if (rc == 0) {
+        cudaEventRecord(e1, st);
+        const cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "time pass kernel");
+    } else cudaStreamSynchronize(st);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != 0) return rc;
+    *ms_out = ms / (float)reps;
+    if (kind) *kind = which == 0 ? (g.mma_ok ? 1 : 0) : (g.mma_fiber_ok ? 1 : 0);
     return 0;
 }
 

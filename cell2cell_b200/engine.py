@@ -155,6 +155,20 @@ def fiber_contract(X, mask, factors, rank, ws=None, out=None):
         return U
 
 
+def time_pass_kernel(X, factors, rank, which, reps=20, ws=None):
+    """(milliseconds, kernel name) of the streaming kernel of one unmasked pass ALONE (``c2c_time_pass_kernel``): ``which`` 0 =
+    plane pass, 1 = fiber pass; average over ``reps`` back-to-back launches, CUDA events on the launching stream."""
+    _check_tensor(X, None)
+    with torch.cuda.device(X.device):
+        ws = _ws_for(X, rank, None, ws)
+        ms, kind = ctypes.c_float(0.0), ctypes.c_int(0)
+        check(lib().c2c_time_pass_kernel(_ptr(X), X.dim(), _shape_arr(X.shape), _ptr_arr(factors), ldr_of(rank), int(rank), int(which),
+                                         int(reps), ctypes.byref(ms), ctypes.byref(kind), ws.ptr, ws.nbytes, _stream()),
+              "c2c_time_pass_kernel")
+        name = ("plane_" if which == 0 else "fiber_") + ("mma" if kind.value else "stream")
+        return float(ms.value), name
+
+
 def mttkrp_from_contraction(TU, shape, factors, rank, mode):
     """M of ``mode`` from T (leading modes) or U (trailing modes) -- the L2-resident half of the MTTKRP."""
     with torch.cuda.device(TU.device):

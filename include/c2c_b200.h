@@ -208,6 +208,15 @@ int c2c_admm_update(float* A_mode, double* X64, double* dual, double* aux, const
 int c2c_corrindex_pairs(const double* F, int n, int64_t rows, int rank, const int64_t* seg_off, int nseg, int method,
                         double tol, double* out, int* status, void* stream);
 
+/* Measurement aid (no counterpart in the reference): average duration, in ms, of the streaming kernel of one unmasked pass ALONE
+ * -- plane_stream / plane_mma (which = 0) or fiber_stream / fiber_mma (which = 1) -- over `reps` back-to-back launches, timed
+ * with CUDA events on `stream` (c2c_plane_contract / c2c_fiber_contract add a memset, a tail kernel, the reduction of the
+ * partials and a copy).  *kind (optional): 0 = FFMA kernel, 1 = tensor-pipe kernel.  -60: the shape takes the register-staged
+ * kernels.  Synchronises the stream. */
+int c2c_time_pass_kernel(const float* X, int ndim, const int64_t* shape /*host*/, const float* const* A /*host array*/, int ldr,
+                         int rank, int which, int reps, float* ms_out /*host*/, int* kind /*host*/, void* ws, size_t ws_bytes,
+                         void* stream);
+
 /* ---- whole factorization (tensorly non_negative_parafac / non_negative_parafac_hals semantics) --------------------
  * Factors A hold the initial values on entry (K7: host-seeded random or svd init is done by the caller) and the result
  * on exit.  errors: device double[n_iter_max] (tensorly's rec_errors); state: device int[2] = {iterations done,
