@@ -300,7 +300,8 @@ int c2c_ncp_run_sharded(const float* X_local, int ndim, const int64_t* local_sha
  * c2c_mask_plan_scan fills it and returns (synchronising the stream) info[8] (host):
  *   [0] missing entries  [1] slots of the by-plane residual list (entries + class padding; 0 = no residual entries)
  *   [2] 1 if a non-zero value sits under a zero mask byte (plan not usable)
- *   [3] list rows        [4] 1 if the separable model misses anything        [5] 1 on overflow (plan not usable)
+ *   [3] slots of the by-position residual lists (per 1024-plane chunk)          [4] 1 if the separable model misses anything
+ *   [5] 1 on overflow (plan not usable)
  *   [6] bytes of the `lists` device buffer c2c_mask_plan_fill needs          [7] residual entries
  * X may be NULL (no zero-fill check).  c2c_mask_plan_fill writes the residual lists (nothing to do when info[1] == 0).
  */
