@@ -852,3 +852,49 @@ def test_constrained_parafac_through_the_api():
                                    non_negative=True)
     assert t.rank == 3 and t.explained_variance_ > 0.95     # (the oracle: 0.985 after its 11 outer iterations)
     assert all((df.values >= 0).all() for df in t.factors.values())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# unpolled runs are only enqueued; the bench's kernel-only timing aid
+# ----------------------------------------------------------------------------------------------------------------------
+def test_unpolled_runs_are_stream_ordered_and_equal_polled_runs():
+    """check_every <= 0 (what fixed-iteration runs pass): the call returns once the iterations are enqueued and the CUDA-graph
+    objects are parked; a second run enqueued right behind it on the same stream, sharing the workspace, must see the first one's
+    work finished (stream order) -- both give exactly what polled runs give."""
+    from cell2cell_b200 import engine
+    from cell2cell_b200._lib import lib
+    shape, rank, n_it = (6, 300, 40, 40), 10, 25
+    X = torch.as_tensor(lowrank(shape, 4, seed=9)).cuda()
+    ws = engine.Workspace(shape, rank, False, X.device)
+    mk = lambda sd: [engine.pack_factor(np.random.RandomState(sd + k).random_sample((s, rank)).astype(np.float32), rank, X.device)  # noqa: E731
+                     for k, s in enumerate(shape)]
+    a1, a2, b1, b2 = mk(1), mk(50), mk(1), mk(50)
+    e1 = engine.ncp_run(X, None, a1, rank, n_iter_max=n_it, tol=-1.0, check_every=0, ws=ws, sync=False)
+    e2 = engine.ncp_run(X, None, a2, rank, n_iter_max=n_it, tol=-1.0, check_every=0, ws=ws, sync=False)
+    torch.cuda.synchronize()
+    assert lib().c2c_release_pending() == 0
+    p1 = engine.ncp_run(X, None, b1, rank, n_iter_max=n_it, tol=1e-30, check_every=5, ws=ws)      # polled every 5 iterations
+    p2 = engine.ncp_run(X, None, b2, rank, n_iter_max=n_it, tol=1e-30, check_every=5, ws=ws)
+    for got, want in ((a1, b1), (a2, b2)):
+        for g, w in zip(got, want):
+            assert rel_err(g.cpu().numpy(), w.cpu().numpy()) < 1e-5
+    np.testing.assert_allclose(e1[0].cpu().numpy()[:n_it - 1], p1[0][:n_it - 1], rtol=1e-5)
+    np.testing.assert_allclose(e2[0].cpu().numpy()[:n_it - 1], p2[0][:n_it - 1], rtol=1e-5)
+    assert int(e1[1].cpu()[0]) == n_it and p1[1] == n_it
+
+
+def test_time_pass_kernel_times_the_streaming_kernels_alone():
+    from cell2cell_b200 import engine
+    from cell2cell_b200._lib import C2CError
+    shape, rank = (60, 400, 40, 40), 10
+    X = torch.as_tensor(lowrank(shape, 3, seed=2)).cuda()
+    f = [engine.pack_factor(np.random.RandomState(k).random_sample((s, rank)).astype(np.float32), rank, X.device)
+         for k, s in enumerate(shape)]
+    for which, names in ((0, ("plane_stream", "plane_mma")), (1, ("fiber_stream", "fiber_mma"))):
+        ms, name = engine.time_pass_kernel(X, f, rank, which, reps=5)
+        assert name in names and 0.0 < ms < 5.0, (name, ms)
+    small = torch.as_tensor(lowrank((3, 7, 5, 6), 2, seed=1)).cuda()               # register-staged kernels: refused
+    fs = [engine.pack_factor(np.random.RandomState(k).random_sample((s, 3)).astype(np.float32), 3, small.device)
+          for k, s in enumerate(small.shape)]
+    with pytest.raises(C2CError):
+        engine.time_pass_kernel(small, fs, 3, 0, reps=2)
