@@ -79,3 +79,21 @@ def list_corrections(resid, factors):
     r2 = resid.reshape(W.shape[0], B.shape[0])
     rec = (W @ B.T) * r2
     return rec @ B, rec.T @ W
+
+
+def list_slots(resid, chunk=1024):
+    """(slots of the by-plane lists, slots of the by-position lists) of the plan's class-ordered residual lists: a list row is
+    padded to 8 x its longest class -- class = in-plane position mod 8 for a plane's row, plane number within the chunk mod 8 for
+    the row of a (chunk of `chunk` planes, position) pair (c2c_plan.cu: plan_count_rows / plan_count_pos)."""
+    P = resid.shape[0]
+    r2 = resid.reshape(P, -1)
+    E = r2.shape[1]
+    cls_e = np.arange(E) % 8
+    by_plane = sum(8 * int(max(np.bincount(cls_e[row], minlength=8))) for row in r2 if row.any())
+    by_pos = 0
+    for p0 in range(0, P, chunk):
+        blk = r2[p0:p0 + chunk]
+        cls_p = np.arange(blk.shape[0]) % 8
+        counts = np.stack([blk[cls_p == c].sum(axis=0) for c in range(8)])               # [8, E]
+        by_pos += int(8 * counts.max(axis=0).sum())
+    return by_plane, by_pos

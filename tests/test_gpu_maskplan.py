@@ -8,7 +8,7 @@ import pytest
 torch = pytest.importorskip("torch")
 
 from oracle import ncp_oracle as o                                   # noqa: E402
-from tests.mask_model import fit_separable, khatri_rao_rows          # noqa: E402
+from tests.mask_model import fit_separable, khatri_rao_rows, list_slots   # noqa: E402
 from tests.test_gpu_parity import _compare_run, lowrank, rel_err     # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -61,6 +61,8 @@ def test_plan_model_and_corrected_contractions(shape, rank, kind):
     assert plan.n_missing == int((mask == 0).sum())
     assert plan.n_residual == int(resid.sum())
     assert plan.model_missing == bool((~g).any() or (~hs).any() or (~hv).any())
+    by_plane, by_pos = list_slots(resid)                           # class padding of both residual lists
+    assert plan.n_list_slots == by_plane and int(plan.info[3]) == by_pos
     if kind == "outer":
         assert plan.n_residual == 0
     A = [engine.pack_factor(f.astype(np.float32), rank, X.device) for f in fs]
