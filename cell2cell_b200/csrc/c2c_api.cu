@@ -129,6 +129,7 @@ struct Geo {
     long long max_parts;
     // tensor-core (TMA + tcgen05) passes, c2c_mma.cuh; mma_ok = 0 -> the FFMA kernels do the pass
     int mma_ok, mma_n;         // mma_ok: plane_mma applies;  mma_fiber_ok: fiber_mma applies too
+    int pm_n;                  // N of plane_mma: 16, 24 (ranks 17-24) or 32; fiber_mma runs at mma_n (16 / 32)
     int mma_fiber_ok;
     int pm_nstages, pm_grid, pm_nkb; long long pm_ntiles; size_t pm_smem;
     int fm_es, fm_na, fm_na_total, fm_ntile, fm_nstages, fm_grid, fm_nj, fm_stack, fm_in_smem, fm_ring2; long long fm_nst; size_t fm_smem;
@@ -294,9 +295,12 @@ static void mma_geometry(Geo& g, int rank)
     const int n = rank <= 16 ? 16 : 32;
     g.mma_n = n;
     const int ldr = ldr_of(rank);
+    static const int plane_n24 = env_int("C2C_B200_NO_MMA_N24", 0) ? 0 : 1;
+    const int pn = (rank > 16 && rank <= 24 && plane_n24) ? 24 : n;
+    g.pm_n = pn;
     {   // plane_mma: B ring and the factor copies are fixed, the rest of shared memory is the X ring
         const size_t xb = 128 * 128;
-        const size_t fixed = c2c_plane_mma_smem(n, g.I2, g.I3, 0);
+        const size_t fixed = c2c_plane_mma_smem(pn, g.I2, g.I3, 0);
         if (fixed + 3 * xb > C2C_MMA_SMEM_BUDGET) return;
         int nx = (int)((C2C_MMA_SMEM_BUDGET - fixed) / (xb + 16));
         if (nx > 12) nx = 12;
@@ -304,7 +308,7 @@ static void mma_geometry(Geo& g, int rank)
         g.pm_nkb = (int)((g.E + 31) / 32);
         g.pm_ntiles = (g.P + 127) / 128;
         g.pm_grid = nsm;                                 // P >= 128 * nsm: a CTA's share spans at least one whole tile
-        g.pm_smem = c2c_plane_mma_smem(n, g.I2, g.I3, nx);
+        g.pm_smem = c2c_plane_mma_smem(pn, g.I2, g.I3, nx);
     }
     {   // fiber_mma: split the in-plane positions into `es` parts (es divides the SM count when it can) so that the CTA's
         // running sums and >= 5 X slots of 8 planes fit in shared memory and its accumulators + lo(X) ring in TMEM --
@@ -565,7 +569,7 @@ static int launch_plane(const Geo& g, ContractArgs a, bool masked, float* T, cud
         pa.P = g.P; pa.E = (int)g.E; pa.I2 = g.I2; pa.I3 = g.I3; pa.R = a.R; pa.ldr = a.ldr; pa.A2 = a.A2; pa.A3 = a.A3; pa.T = T;
         pa.done = a.done; pa.nkb = g.pm_nkb; pa.ntiles = g.pm_ntiles; pa.nx = g.pm_nstages; pa.dbg = mma_dbg();
         if (!po.t_zeroed && !po.main_only) CK(cudaMemsetAsync(T, 0, (size_t)g.P * a.ldr * sizeof(float), st), "memset T");
-        const cudaError_t e = c2c_launch_plane_mma(g.mma_n, map, pa, g.pm_grid, g.pm_smem, st, po.t_zeroed ? po.pdl : 0);
+        const cudaError_t e = c2c_launch_plane_mma(g.pm_n, map, pa, g.pm_grid, g.pm_smem, st, po.t_zeroed ? po.pdl : 0);
         if (e != cudaSuccess) return cuda_fail(e, "plane_mma launch");
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return 0;

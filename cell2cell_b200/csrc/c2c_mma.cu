@@ -21,6 +21,7 @@ cudaError_t c2c_launch_plane_mma(int n, const CUtensorMap& map, const PlaneMmaAr
 {
     switch (n) {
         case 16: return launch_plane_n<16>(map, a, grid, smem, st, pdl);
+        case 24: return launch_plane_n<24>(map, a, grid, smem, st, pdl);
         case 32: return launch_plane_n<32>(map, a, grid, smem, st, pdl);
         default: return cudaErrorInvalidValue;
     }
@@ -39,7 +40,7 @@ cudaError_t c2c_launch_fiber_mma(int n, int stack, int allts, const CUtensorMap&
 size_t c2c_plane_mma_smem(int n, int I2, int I3, int nx)
 {
     const size_t xb = 128 * 128, bb = 2 * (size_t)n * 128;
-    const int nr = 256 / (2 * n);
+    const int nr = 256 / (n == 24 ? 64 : 2 * n);
     return 1024 + (size_t)nx * xb + (size_t)C2C_MMA_RING2 * bb + (size_t)(I2 + I3) * n * sizeof(float) +
            (size_t)(2 * nx + 2 * C2C_MMA_RING2 + 2 * nr) * 8 + 16;
 }

@@ -148,10 +148,15 @@ struct PlaneMmaArgs {
     int dbg;                   // timing experiments only: 1 skip lo(X), 2 skip B generation, 4 skip MMAs, 8 skip epilogue reads
 };
 
+// N = 24 (ranks 17-24): an M = 128 MMA takes N in multiples of 16, so the stacked MMA runs at 2N = 48 and the lo(x) hi(b) MMA at
+// N = 32 over B rows 0..31 -- its columns 24..31 (lo(x) x the first eight lo(b) rows) land in the 8 spare columns of a 64-column
+// accumulator slot and are never read: 80 tensor columns per k-step instead of the 96 of N = 32.
 template <int N> struct PlaneMmaSmem {
     static constexpr int X_BYTES = 128 * 128;              // 128 planes x 32 floats
     static constexpr int B_BYTES = 2 * N * 128;            // rows 0..N-1: hi(KR^T), rows N..2N-1: lo(KR^T); 32 floats each
-    static constexpr int NR = 256 / (2 * N);               // accumulator ring (2N columns each)
+    static constexpr int ACC = N == 24 ? 64 : 2 * N;       // TMEM columns of one accumulator slot: hi | lo (| spare)
+    static constexpr int N_LO = N == 24 ? 32 : N;          // N of the lo(x) hi(b) MMA
+    static constexpr int NR = 256 / ACC;                   // accumulator ring
     static constexpr int ALO_COL = 256;                    // lo(X) ring: C2C_MMA_RING2 x 32 columns
     static constexpr int TM_COLS = 512;
 };
@@ -207,7 +212,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
         // ---- MMA issuer: chains of up to C2C_PM_CHUNK k blocks, each into the next accumulator of the ring.  The whole
         // warp runs the (uniform) control flow, one elected lane issues; descriptors advance by adding to their address field.
         {
-            constexpr unsigned IDESC2 = umma_idesc_tf32(2 * N, 0), IDESC1 = umma_idesc_tf32(N, 0);
+            constexpr unsigned IDESC2 = umma_idesc_tf32(2 * N, 0), IDESC1 = umma_idesc_tf32(L::N_LO, 0);
             const unsigned long long DK = umma_desc(0, 16, 1024, C2C_UMMA_LAYOUT_SW128);
             const unsigned xa0 = smem_u32(xring) >> 4, ba0 = smem_u32(bring) >> 4;
             int sx = 0; unsigned phx = 0; int s2 = 0; unsigned ph2 = 0; int r = 0; unsigned phr = 0;
@@ -219,7 +224,7 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
                     const long long chunk_end = g + C2C_PM_CHUNK < piece_end ? g + C2C_PM_CHUNK : piece_end;
                     mbar_wait(tempty + r, phr ^ 1u);
                     tc_fence_after();
-                    const unsigned d = tmem + (unsigned)(r * 2 * N);
+                    const unsigned d = tmem + (unsigned)(r * L::ACC);
                     for (long long gg = g; gg < chunk_end; ++gg) {
 #ifndef C2C_PM_ALL_TS
                         mbar_wait(fullx + sx, phx);              // (all-TS: the issuer never touches the X ring -- its slots may be
@@ -289,10 +294,11 @@ plane_mma_kernel(const __grid_constant__ CUtensorMap mapX, const PlaneMmaArgs a)
 #pragma unroll
                     for (int c0 = 0; c0 < N; c0 += 16) {
                         float vh[16], vl[16];
-                        tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(r * 2 * N + c0), vh);
-                        tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(r * 2 * N + N + c0), vl);
+                        tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(r * L::ACC + c0), vh);
+                        tmem_ld16(tmem + ((unsigned)(lg * 32) << 16) + (unsigned)(r * L::ACC + N + c0), vl);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[c0 + j] += fmaf(vh[j], unbias, vl[j]);
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < N) acc[c0 + j] += fmaf(vh[j], unbias, vl[j]);   // N = 24: the last load reads 8 columns too many
                     }
                 }
                 tc_fence_before();

@@ -561,7 +561,7 @@ def mma_from_rank_1():
 
 
 @pytest.mark.parametrize("shape", MMA_SHAPES)
-@pytest.mark.parametrize("rank", [1, 5, 16, 20, 32])
+@pytest.mark.parametrize("rank", [1, 5, 16, 17, 20, 24, 25, 32])       # 17-24: plane_mma at N = 24
 def test_mma_passes_match_einsum(shape, rank, mma_from_rank_1):
     """T and U of the tensor-pipe passes against float64 einsum (every mode's MTTKRP is derived from them)."""
     from cell2cell_b200 import engine
