@@ -553,41 +553,49 @@ class PreBuiltTensor(BaseTensor):
         self._loc_nans = value
 
 
+_DEFAULT_TAIL = ["Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
+
+
+def _default_categories(n_orders):
+    """Category used for an order whose elements get no metadata of their own (tensor.py:1283-1292)."""
+    if n_orders < 3:
+        raise ValueError("Too few dimensions in the tensor")
+    if n_orders == 3:
+        return list(_DEFAULT_TAIL)
+    if n_orders == 4:
+        return ["Contexts"] + _DEFAULT_TAIL
+    return ["Contexts-{}".format(i + 1) for i in range(n_orders - 3)] + _DEFAULT_TAIL
+
+
 def generate_tensor_metadata(interaction_tensor, metadata_dicts, fill_with_order_elements=True):
-    """Per-order metadata DataFrames (Element, Category) (tensor.py:1255-1315)."""
-    tensor_dim = len(interaction_tensor.tensor.shape)
-    assert tensor_dim == len(metadata_dicts), "metadata_dicts should be of the same size as the number of orders/dimensions in the tensor"
-    if interaction_tensor.order_labels is None:
-        if tensor_dim == 4:
-            default_cats = ["Contexts", "Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
-        elif tensor_dim > 4:
-            default_cats = ["Contexts-{}".format(i + 1) for i in range(tensor_dim - 3)] + \
-                           ["Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
-        elif tensor_dim == 3:
-            default_cats = ["Ligand-Receptor Pairs", "Sender Cells", "Receiver Cells"]
+    """One ``(Element, Category)`` DataFrame per order of the tensor (tensor.py:1255-1315).
+
+    ``metadata_dicts[i]`` maps the elements of order ``i`` to their category, or is None: the order then gets no table
+    (``fill_with_order_elements=False``), or one whose category is the element itself (fewer than 75 elements) or the order's
+    label (the tensor's ``order_labels``, else the default names)."""
+    names_per_order = interaction_tensor.order_names
+    n_orders = len(interaction_tensor.tensor.shape)
+    assert n_orders == len(metadata_dicts), \
+        "metadata_dicts should be of the same size as the number of orders/dimensions in the tensor"
+    labels = interaction_tensor.order_labels
+    if labels is None:
+        labels = _default_categories(n_orders)
+    else:
+        assert len(labels) == n_orders, "The length of order_labels must match the number of orders/dimensions in the tensor"
+    tables = []
+    for label, names, mapping in zip(labels, names_per_order, metadata_dicts):
+        if mapping is None and not fill_with_order_elements:
+            tables.append(None)
+            continue
+        elements = pd.Index(names)
+        if mapping is not None:
+            category = [mapping[e] for e in elements]
+        elif len(elements) < 75:
+            category = elements
         else:
-            raise ValueError("Too few dimensions in the tensor")
-    else:
-        assert len(interaction_tensor.order_labels) == tensor_dim, \
-            "The length of order_labels must match the number of orders/dimensions in the tensor"
-        default_cats = interaction_tensor.order_labels
-    if fill_with_order_elements:
-        metadata = [pd.DataFrame(index=names) for names in interaction_tensor.order_names]
-    else:
-        metadata = [pd.DataFrame(index=names) if (meta is not None) else None
-                    for names, meta in zip(interaction_tensor.order_names, metadata_dicts)]
-    for i, meta in enumerate(metadata):
-        if meta is not None:
-            if metadata_dicts[i] is not None:
-                meta["Category"] = [metadata_dicts[i][idx] for idx in meta.index]
-            else:
-                if len(meta.index) < 75:
-                    meta["Category"] = meta.index
-                else:
-                    meta["Category"] = len(meta.index) * [default_cats[i]]
-            meta.index.name = "Element"
-            meta.reset_index(inplace=True)
-    return metadata
+            category = [label] * len(elements)
+        tables.append(pd.DataFrame({"Element": elements, "Category": category}))
+    return tables
 
 
 def interactions_to_tensor(interactions, experiment="single_cell", context_names=None, how="inner", outer_fraction=0.0,

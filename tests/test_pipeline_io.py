@@ -100,3 +100,33 @@ def test_pipeline_on_device_equals_direct_calls(tmp_path, capsys):
     assert back.tensor.is_cuda and torch.equal(back.tensor, out.tensor) and list(back.factors) == list(out.factors)
     with pytest.raises(ValueError):
         io.load_tensor(p, backend="numpy")
+
+
+def test_generate_tensor_metadata_equals_the_reference_function():
+    """``generate_tensor_metadata`` against the reference's own function (file imported unmodified through the harness) on a
+    stand-in tensor object: mapped orders, short / long unmapped orders, order labels given or not, 3- / 4- / 5-way."""
+    import types
+    import numpy as np
+    import pandas as pd
+    import pytest
+    from oracle.ref_harness import load_reference, reference_available
+    from cell2cell_b200.tensor.tensor import generate_tensor_metadata
+    if not reference_available():
+        pytest.skip("reference not present (GPU box)")
+    ref = load_reference().tensor.generate_tensor_metadata
+    for shape, labels in (((3, 80, 4, 4), None), ((3, 80, 4, 4), ["Ctx", "LR", "S", "R"]), ((80, 4, 4), None), ((2, 3, 90, 5, 5), None)):
+        names = [["e%d_%d" % (k, i) for i in range(n)] for k, n in enumerate(shape)]
+        obj = types.SimpleNamespace(tensor=np.zeros(shape), order_names=names, order_labels=labels)
+        dicts = [None] * len(shape)
+        dicts[0] = {n: "g%d" % (i % 2) for i, n in enumerate(names[0])}
+        for fill in (True, False):
+            want = ref(obj, list(dicts), fill_with_order_elements=fill)
+            got = generate_tensor_metadata(obj, list(dicts), fill_with_order_elements=fill)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    pd.testing.assert_frame_equal(a.reset_index(drop=True), b.reset_index(drop=True), check_dtype=False)
+    with pytest.raises(ValueError):
+        generate_tensor_metadata(types.SimpleNamespace(tensor=np.zeros((4, 4)), order_names=[["a"] * 4] * 2, order_labels=None),
+                                 [None, None])
